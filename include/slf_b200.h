@@ -1,0 +1,203 @@
+/*
+ * slf_b200.h -- C ABI of libslf_b200.so, the B200 (sm_100a) implementation of the
+ * sailfish lattice-Boltzmann hot path.
+ *
+ * The reference (sailfish-team/sailfish) has no FFI: its device interface is the
+ * "backend" duck type (sailfish/backend_cuda.py:34-332, pycuda driver calls) plus
+ * the kernel-name/argument contract of the Mako-generated module
+ * (sailfish/templates/models/lb_single_fluid.mako, sailfish/templates/kernel_utils.mako).
+ * Every entry point below names the reference interface it replaces.  The Python
+ * binding is sailfish_b200/backend_b200.py (ctypes); INTEGRATION.md shows how the
+ * reference selects it with --backends=b200.
+ *
+ * Conventions
+ *   - plain C types only; device pointers travel as uint64_t, streams/events as
+ *     opaque uint64_t handles (0 = default stream);
+ *   - every function returns 0 on success, a negative SLF_E* code or a positive
+ *     cudaError_t otherwise; slf_last_error() gives the message (thread local);
+ *   - all launches are asynchronous on the given stream;
+ *   - no CPU fallback exists: without a CUDA device slf_init() fails.
+ *
+ * Memory layout (identical to the reference, subdomain_runner.py:359-379,
+ * templates/kernel_common.mako:459-461, geo_helpers.mako:163-176):
+ *   gi        = gx + arr_nx * (gy + arr_ny * gz)      ghost-inclusive, x padded
+ *   dist[i]   = base[i * DIST_SIZE + gi],  DIST_SIZE = arr_nx*arr_ny*arr_nz
+ *   fields    = one float per gi;  node map = one uint32 per gi
+ *   node code = orientation | scratch | param | type  (geo_encoder.py:365-382)
+ */
+#ifndef SLF_B200_H_
+#define SLF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLF_ABI_VERSION 1
+
+/* error codes (negative; positive values are cudaError_t) */
+#define SLF_EINVAL      (-1)   /* bad argument / unsupported configuration          */
+#define SLF_ENODEVICE   (-2)   /* no CUDA device: there is no CPU fallback           */
+#define SLF_EUNSUPPORTED (-3)  /* feature of the reference that is out of scope      */
+#define SLF_ENCCL       (-4)
+
+/* lattices: sailfish/sym.py:61 (D2Q9), :312 (D3Q19), :409 (D3Q27) */
+enum { SLF_D2Q9 = 0, SLF_D3Q19 = 1, SLF_D3Q27 = 2 };
+/* collision models: templates/relaxation.mako:99 (BGK), relaxation_mrt.mako:31 (MRT) */
+enum { SLF_BGK = 0, SLF_MRT = 1 };
+/* --access_pattern, lb_base.py:61-65 */
+enum { SLF_AB = 0, SLF_AA = 1 };
+
+/* Node classes understood by the kernels (sailfish/node_type.py).  type_id[] in
+ * SlfParams holds the per-run remapped id (geo_encoder.py:83-91) of each class,
+ * or SLF_NT_ABSENT when the class does not occur in the subdomain. */
+enum {
+  SLF_NT_FLUID = 0,             /* node_type.py:87  _NTFluid              */
+  SLF_NT_GHOST,                 /* :94  _NTGhost (excluded)               */
+  SLF_NT_UNUSED,                /* :99  _NTUnused (excluded)              */
+  SLF_NT_PROPAGATION_ONLY,      /* :104 _NTPropagationOnly                */
+  SLF_NT_FULLBB_WALL,           /* :148 NTFullBBWall                      */
+  SLF_NT_HALFBB_WALL,           /* :117 NTHalfBBWall                      */
+  SLF_NT_EQUILIBRIUM_VELOCITY,  /* :246 NTEquilibriumVelocity             */
+  SLF_NT_EQUILIBRIUM_DENSITY,   /* :200 NTEquilibriumDensity              */
+  SLF_NT_REGULARIZED_VELOCITY,  /* :269 NTRegularizedVelocity             */
+  SLF_NT_REGULARIZED_DENSITY,   /* :211 NTRegularizedDensity              */
+  SLF_NT_DO_NOTHING,            /* :296 NTDoNothing                       */
+  SLF_NT_COUNT
+};
+#define SLF_NT_ABSENT 0xfffffffeu   /* geo_encoder.py:44-50 */
+
+/* CollideAndPropagate `options` bits, templates/kernel_common.mako:507-508 */
+#define SLF_OPTION_SAVE_MACRO_FIELDS 1
+#define SLF_OPTION_BULK              2
+
+/* Faces, sailfish/subdomain.py SubdomainSpec.{X_LOW..Z_HIGH} */
+enum { SLF_X_LOW = 0, SLF_X_HIGH = 1, SLF_Y_LOW = 2, SLF_Y_HIGH = 3, SLF_Z_LOW = 4, SLF_Z_HIGH = 5 };
+
+/*
+ * Everything the reference bakes into the generated source as literals
+ * (codegen.py:195-204 _build_context -> lb_base.py:120-137, lb_single.py:52-70,
+ * subdomain_runner.py:182-248, geo_encoder.py:341-363), as one POD.
+ */
+typedef struct SlfParams {
+  uint32_t struct_bytes;        /* sizeof(SlfParams): ABI check                         */
+  int32_t  lattice;             /* SLF_D2Q9 | SLF_D3Q19 | SLF_D3Q27   (ctx['grid'])      */
+  int32_t  model;               /* SLF_BGK | SLF_MRT                  (ctx['model'])     */
+  int32_t  access_pattern;      /* SLF_AB | SLF_AA                                      */
+  int32_t  lat_nx, lat_ny, lat_nz;   /* ghost-inclusive lattice (lat_nz = 1 in 2-D)     */
+  int32_t  arr_nx, arr_ny, arr_nz;   /* in-memory size, x padded to --mem_alignment     */
+  int32_t  periodic[3];         /* ctx['block_periodicity']                             */
+  int32_t  bits_type;           /* nt_misc_shift                                        */
+  int32_t  bits_param;          /* nt_param_shift                                       */
+  int32_t  bits_scratch;        /* nt_scratch_shift                                     */
+  uint32_t type_id[SLF_NT_COUNT];
+  int32_t  use_link_tags;       /* --nouse_link_tags clears it (lb_base.py:91-97)       */
+  int32_t  relaxation_enabled;  /* config.relaxation_enabled (regtest/subdomains)     */
+  int32_t  propagation_enabled;
+  int32_t  force_enabled;       /* LBForcedSim.add_body_force, Guo scheme only          */
+  int32_t  reserved0;
+  double   visc;                /* --visc; tau = (6 visc + 1) / 2  (sym.py:847)          */
+  double   accel[3];            /* body acceleration (sym_force.py:72-119, accel=True)  */
+  int32_t  num_node_params;     /* len(ctx['node_params'])                              */
+  int32_t  reserved1;
+  const double *node_params;    /* host pointer, copied by slf_plan_create              */
+} SlfParams;
+
+typedef struct SlfPlan SlfPlan;
+
+/* ---- device / memory: backend_cuda.py:52-191 ------------------------------------ */
+int  slf_abi_version(void);
+const char *slf_last_error(void);
+int  slf_device_count(int *count);
+int  slf_init(int device);                                   /* CUDABackend.__init__ :52-107 */
+int  slf_device_info(char *name, int name_len, uint64_t *total_mem, int *sm_count);
+int  slf_malloc(uint64_t bytes, uint64_t *dptr);             /* alloc_buf :132-154           */
+int  slf_free(uint64_t dptr);
+int  slf_memset(uint64_t dptr, int value, uint64_t bytes, uint64_t stream);
+int  slf_host_alloc(uint64_t bytes, void **hptr);            /* alloc_async_host_buf :156    */
+int  slf_host_free(void *hptr);
+int  slf_memcpy_h2d(uint64_t dptr, const void *hptr, uint64_t bytes);                 /* to_buf :161     */
+int  slf_memcpy_d2h(void *hptr, uint64_t dptr, uint64_t bytes);                       /* from_buf :174   */
+int  slf_memcpy_h2d_async(uint64_t dptr, const void *hptr, uint64_t bytes, uint64_t stream); /* :187 */
+int  slf_memcpy_d2h_async(void *hptr, uint64_t dptr, uint64_t bytes, uint64_t stream);       /* :190 */
+int  slf_memcpy_d2d_async(uint64_t dst, uint64_t src, uint64_t bytes, uint64_t stream);
+int  slf_sync(void);                                         /* sync :294                    */
+int  slf_stream_create(uint64_t *stream, int high_priority); /* make_stream :297             */
+int  slf_stream_destroy(uint64_t stream);
+int  slf_stream_sync(uint64_t stream);
+int  slf_stream_wait_event(uint64_t stream, uint64_t event);
+int  slf_event_create(uint64_t *event, int timing);          /* make_event :300-308          */
+int  slf_event_destroy(uint64_t event);
+int  slf_event_record(uint64_t event, uint64_t stream);
+int  slf_event_sync(uint64_t event);
+int  slf_event_elapsed_ms(uint64_t start, uint64_t end, float *ms);
+
+/* ---- plan: replaces BlockCodeGenerator.get_code + backend.build (codegen.py:104,
+ *      backend_cuda.py:193-218): no source is generated, the context becomes data ---- */
+int  slf_plan_create(const SlfParams *params, SlfPlan **plan);
+int  slf_plan_destroy(SlfPlan *plan);
+/* number of kernels this library has launched since slf_init (bench `gpu_launches`) */
+uint64_t slf_launch_count(void);
+
+/* ---- kernels (names are the reference's, kernel-name contract in SURVEY.md 8b) ---- */
+
+/* SetInitialConditions(dist, ivx, ivy[, ivz], irho, map)  lb_single_fluid.mako:101-127 */
+int  slf_set_initial_conditions(SlfPlan *plan, uint64_t dist, uint64_t vx, uint64_t vy,
+                                uint64_t vz, uint64_t rho, uint64_t map, uint64_t stream);
+
+/* CollideAndPropagate(map, dist_in, dist_out, rho, vx, vy[, vz], options, iteration)
+ * lb_single_fluid.mako:161-229.  z_begin/z_end select a slab of gz planes
+ * [z_begin, z_end) (2-D: gy rows); pass 0, -1 for the whole subdomain.  This replaces
+ * the reference's bulk/boundary block lists (kernel_common.mako:245-457). */
+int  slf_collide_and_propagate(SlfPlan *plan, uint64_t map, uint64_t dist_in, uint64_t dist_out,
+                               uint64_t rho, uint64_t vx, uint64_t vy, uint64_t vz,
+                               int options, uint32_t iteration,
+                               int z_begin, int z_end, uint64_t stream);
+
+/* PrepareMacroFields(map, dist, rho, options, iteration)  lb_single_fluid.mako:129-159 */
+int  slf_prepare_macro_fields(SlfPlan *plan, uint64_t map, uint64_t dist, uint64_t rho,
+                              int options, uint32_t iteration, uint64_t stream);
+
+/* ApplyPeriodicBoundaryConditions[WithSwap](dist, axis)  kernel_utils.mako:295-384 */
+int  slf_apply_periodic_boundary_conditions(SlfPlan *plan, uint64_t dist, int axis,
+                                            int with_swap, uint64_t stream);
+
+/* Collect/DistributeContinuousData[WithSwap](dist, face, base_gx, base_other, max_lx,
+ * max_other, buffer)  kernel_utils.mako:526-794.  2-D: base_other is ignored and
+ * max_other must be 1 (the reference's 2-D signature has no such arguments; its
+ * max_lx = ndists * nx is passed here as max_lx = nx). */
+int  slf_collect_continuous_data(SlfPlan *plan, uint64_t dist, int face, int base_gx,
+                                 int base_other, int max_lx, int max_other, uint64_t buffer,
+                                 int with_swap, uint64_t stream);
+int  slf_distribute_continuous_data(SlfPlan *plan, uint64_t dist, int face, int base_gx,
+                                    int base_other, int max_lx, int max_other, uint64_t buffer,
+                                    int with_swap, uint64_t stream);
+/* Collect/DistributeSparseData(idx_array, dist, buffer, max_idx)  kernel_utils.mako:796-836 */
+int  slf_collect_sparse_data(SlfPlan *plan, uint64_t idx_array, uint64_t dist, uint64_t buffer,
+                             int max_idx, uint64_t stream);
+int  slf_distribute_sparse_data(SlfPlan *plan, uint64_t idx_array, uint64_t dist, uint64_t buffer,
+                                int max_idx, uint64_t stream);
+
+/* ---- z-split halo exchange between the GPUs of one box -------------------------------
+ * Replaces SubdomainRunner._send_dists/_recv_dists + ZMQ connectors
+ * (subdomain_runner.py:1064-1139, connector.py:73-117) for conn_axis = z:
+ * one call posts both faces' messages.  Device-to-device, no host staging.
+ * `peer_*` are the neighbour's dist base pointers mapped into this process
+ * (cudaIpc or same-process peer access); 0 = no neighbour on that side.
+ * Parity of `iteration` (value AFTER the step, like sim.iteration in step():960-974)
+ * selects the AA variant (ghost layer -> neighbour's first real layer, or first real
+ * layer opposite slots -> neighbour's ghost layer). */
+int  slf_halo_push_z(SlfPlan *plan, uint64_t dist, uint64_t peer_low, uint64_t peer_high,
+                     SlfPlan *peer_low_plan_like, uint32_t iteration_after_step, uint64_t stream);
+
+/* CUDA IPC handles for the above (backend_cuda.py:122-126 wraps them but never calls them) */
+int  slf_ipc_get_handle(uint64_t dptr, void *handle64);      /* 64 bytes */
+int  slf_ipc_open_handle(const void *handle64, uint64_t *dptr);
+int  slf_ipc_close_handle(uint64_t dptr);
+int  slf_enable_peer_access(int peer_device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* SLF_B200_H_ */

@@ -1,0 +1,676 @@
+/*
+ * lbm_oracle.c -- CPU restatement of the reference's collide-and-propagate path.
+ *
+ * THIS IS TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may build, load or call it.  The product
+ * (sailfish_b200/, libslf_b200.so) never does and has no CPU fallback.
+ *
+ * Why a restatement: the reference has no compiled kernel source -- its kernels
+ * are Mako templates rendered and nvcc-JITed at run time through pycuda
+ * (sailfish/backend_cuda.py:193-218); neither Mako, pycuda nor a GPU exist in the
+ * build container, and `--backends=dummy` is a no-op (backend_dummy.py:31-38).
+ * The control flow below follows the templates line by line; the closed-form
+ * expressions are restated from sailfish/sym*.py.
+ *
+ * Parity pinning (see DESIGN.md "Oracle"):
+ *   - every formula is checked against tests/golden/formulas.npz, produced by
+ *     lambdifying the reference's own SymPy expressions (tools/gen_golden.py);
+ *   - whole steps are checked against tests/golden/steps_*.npz, produced by
+ *     tools/ref_stepper.py whose arithmetic is the reference's SymPy objects and
+ *     whose geometry is the reference's own encoded node map;
+ *   - streaming/halo/PBC are checked against the literal known-answer vectors of
+ *     regtest/subdomains/{2d,3d}_propagation.py.
+ *
+ * Built twice: -DREAL=float (parity target, the reference computes in fp32) and
+ * -DREAL=double (error budgeting).  OpenMP over the outermost axis is used for the
+ * CPU baseline timing only.
+ *
+ * Reference map (execution order inside CollideAndPropagate,
+ * templates/models/lb_single_fluid.mako:161-229):
+ *   local_indices / load_node_type   kernel_common.mako:83-115, :191-201
+ *   getDist                          geo_helpers.mako:225-276
+ *   getMacro                         boundary.mako:465-507 (+ :418-459, :267-319)
+ *   precollisionBoundaryConditions   boundary.mako:784-878
+ *   relaxate -> BGK_relaxate0        relaxation.mako:99-181, relaxation_common.mako
+ *            -> MS_relaxate          relaxation_mrt.mako:31-97
+ *   postcollisionBoundaryConditions  boundary.mako:670-683 (HalfBB :653-666)
+ *   save_macro_fields                kernel_common.mako:213-240
+ *   propagate                        propagation.mako:384-421 (+ :12-60 bounds)
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/slf_b200.h"
+
+#ifndef REAL
+#define REAL float
+#endif
+
+#define MAXQ 27
+
+typedef struct Lat {
+  int Q, D;
+  int e[MAXQ][3];
+  double w[MAXQ];
+  int opp[MAXQ];
+  int dir2vec[7];      /* direction number 1..2D -> slot */
+  int has_mrt;
+  int M[MAXQ][MAXQ];   /* orthogonal integer moment basis (sym.py:1044) */
+  double Mnorm[MAXQ];
+  double rates[MAXQ];  /* -1 -> 1/tau */
+  int i_mx, i_my, i_mz;
+} Lat;
+
+static const int E_D2Q9[9][3] = {{0,0,0},{1,0,0},{0,1,0},{-1,0,0},{0,-1,0},{1,1,0},{-1,1,0},{-1,-1,0},{1,-1,0}};
+static const int E_D3Q27[27][3] = {
+  {0,0,0},{1,0,0},{-1,0,0},{0,1,0},{0,-1,0},{0,0,1},{0,0,-1},
+  {1,1,0},{-1,1,0},{1,-1,0},{-1,-1,0},{0,1,1},{0,-1,1},{0,1,-1},{0,-1,-1},
+  {1,0,1},{-1,0,1},{1,0,-1},{-1,0,-1},
+  {1,1,1},{1,1,-1},{1,-1,1},{1,-1,-1},{-1,1,1},{-1,1,-1},{-1,-1,1},{-1,-1,-1}};
+
+static Lat g_lat[3];
+static int g_lat_ready = 0;
+
+/* Gram-Schmidt with integer rescaling, sym.py:918-942. Uses long double rationals
+ * via brute force: the bases are tiny so exact fractions are done with int64. */
+static long long gcdll(long long a, long long b) { if (a < 0) a = -a; if (b < 0) b = -b; while (b) { long long t = a % b; a = b; b = t; } return a; }
+
+static void orthogonalize(int Q, long long rows[MAXQ][MAXQ], int out[MAXQ][MAXQ]) {
+  /* keep vectors as integer numerators with a common positive denominator */
+  static long long num[MAXQ][MAXQ];
+  for (int k = 0; k < Q; k++) {
+    long long v[MAXQ], den = 1;
+    for (int i = 0; i < Q; i++) v[i] = rows[k][i];
+    for (int j = 0; j < k; j++) {
+      long long uu = 0, uv = 0;
+      for (int i = 0; i < Q; i++) { uu += num[j][i] * num[j][i]; uv += num[j][i] * v[i]; }
+      /* v <- v - (uv/(den*uu)) u  with v = v/den : v*uu - uv*u over den*uu */
+      for (int i = 0; i < Q; i++) v[i] = v[i] * uu - uv * num[j][i];
+      den *= uu;
+      long long g = 0;
+      for (int i = 0; i < Q; i++) g = gcdll(g, v[i]);
+      g = gcdll(g, den);
+      if (g > 1) { for (int i = 0; i < Q; i++) v[i] /= g; den /= g; }
+    }
+    long long g = 0;
+    for (int i = 0; i < Q; i++) g = gcdll(g, v[i]);
+    if (g > 1) for (int i = 0; i < Q; i++) v[i] /= g;
+    for (int i = 0; i < Q; i++) { num[k][i] = v[i]; out[k][i] = (int)v[i]; }
+  }
+}
+
+static void lat_finish(Lat *L) {
+  for (int i = 0; i < L->Q; i++)
+    for (int j = 0; j < L->Q; j++)
+      if (L->e[i][0] == -L->e[j][0] && L->e[i][1] == -L->e[j][1] && L->e[i][2] == -L->e[j][2]) L->opp[i] = j;
+  int d = 1;
+  for (int i = 0; i < L->Q; i++) {
+    int n2 = L->e[i][0]*L->e[i][0] + L->e[i][1]*L->e[i][1] + L->e[i][2]*L->e[i][2];
+    if (n2 == 1) L->dir2vec[d++] = i;
+  }
+}
+
+static void lat_init(void) {
+  if (g_lat_ready) return;
+  /* D2Q9, sym.py:61-95 */
+  Lat *L = &g_lat[SLF_D2Q9];
+  memset(L, 0, sizeof(*L));
+  L->Q = 9; L->D = 2;
+  for (int i = 0; i < 9; i++) for (int d = 0; d < 3; d++) L->e[i][d] = E_D2Q9[i][d];
+  L->w[0] = 4.0/9; for (int i = 1; i < 5; i++) L->w[i] = 1.0/9; for (int i = 5; i < 9; i++) L->w[i] = 1.0/36;
+  lat_finish(L);
+  {
+    long long rows[MAXQ][MAXQ];
+    for (int i = 0; i < 9; i++) {
+      long long x = L->e[i][0], y = L->e[i][1], sq = x*x + y*y;
+      rows[0][i] = 1; rows[1][i] = sq; rows[2][i] = sq*sq; rows[3][i] = x; rows[4][i] = x*sq;
+      rows[5][i] = y; rows[6][i] = y*sq; rows[7][i] = x*x - y*y; rows[8][i] = x*y;
+    }
+    orthogonalize(9, rows, L->M);
+    const double r[9] = {0, 1.63, 1.14, 0, 1.9, 0, 1.9, -1, -1};   /* sym.py:83 */
+    for (int i = 0; i < 9; i++) L->rates[i] = r[i];
+    L->has_mrt = 1; L->i_mx = 3; L->i_my = 5; L->i_mz = -1;
+  }
+  /* D3Q19 (first 19 vectors of the D3Q27 list), sym.py:312-358 */
+  L = &g_lat[SLF_D3Q19];
+  memset(L, 0, sizeof(*L));
+  L->Q = 19; L->D = 3;
+  for (int i = 0; i < 19; i++) for (int d = 0; d < 3; d++) L->e[i][d] = E_D3Q27[i][d];
+  L->w[0] = 1.0/3; for (int i = 1; i < 7; i++) L->w[i] = 1.0/18; for (int i = 7; i < 19; i++) L->w[i] = 1.0/36;
+  lat_finish(L);
+  {
+    long long rows[MAXQ][MAXQ];
+    for (int i = 0; i < 19; i++) {
+      long long x = L->e[i][0], y = L->e[i][1], z = L->e[i][2], sq = x*x + y*y + z*z;
+      rows[0][i] = 1; rows[1][i] = sq; rows[2][i] = sq*sq;
+      rows[3][i] = x; rows[4][i] = x*sq; rows[5][i] = y; rows[6][i] = y*sq; rows[7][i] = z; rows[8][i] = z*sq;
+      rows[9][i] = 3*x*x - sq; rows[10][i] = (3*sq - 5)*(3*x*x - sq);
+      rows[11][i] = y*y - z*z; rows[12][i] = (3*sq - 5)*(y*y - z*z);
+      rows[13][i] = x*y; rows[14][i] = y*z; rows[15][i] = x*z;
+      rows[16][i] = (y*y - z*z)*x; rows[17][i] = (z*z - x*x)*y; rows[18][i] = (x*x - y*y)*z;
+    }
+    orthogonalize(19, rows, L->M);
+    const double r[19] = {0.0, 1.19, 1.4, 0.0, 1.2, 0.0, 1.2, 0.0, 1.2, -1, 1.4, -1, 1.4, -1, -1, -1, 1.98, 1.98, 1.98};
+    for (int i = 0; i < 19; i++) L->rates[i] = r[i];   /* sym.py:334-335 */
+    L->has_mrt = 1; L->i_mx = 3; L->i_my = 5; L->i_mz = 7;
+  }
+  /* D3Q27, sym.py:409-428 (BGK only) */
+  L = &g_lat[SLF_D3Q27];
+  memset(L, 0, sizeof(*L));
+  L->Q = 27; L->D = 3;
+  for (int i = 0; i < 27; i++) for (int d = 0; d < 3; d++) L->e[i][d] = E_D3Q27[i][d];
+  L->w[0] = 8.0/27; for (int i = 1; i < 7; i++) L->w[i] = 2.0/27; for (int i = 7; i < 19; i++) L->w[i] = 1.0/54;
+  for (int i = 19; i < 27; i++) L->w[i] = 1.0/216;
+  lat_finish(L);
+  for (int l = 0; l < 3; l++)
+    for (int k = 0; k < g_lat[l].Q; k++) {
+      double s = 0; for (int i = 0; i < g_lat[l].Q; i++) s += (double)g_lat[l].M[k][i] * g_lat[l].M[k][i];
+      g_lat[l].Mnorm[k] = s;
+    }
+  g_lat_ready = 1;
+}
+
+/* introspection for tests */
+int orc_lattice_info(int lattice, int *Q, int *D, int *e, double *w, int *opp, int *M) {
+  lat_init();
+  if (lattice < 0 || lattice > 2) return SLF_EINVAL;
+  const Lat *L = &g_lat[lattice];
+  *Q = L->Q; *D = L->D;
+  for (int i = 0; i < L->Q; i++) {
+    for (int d = 0; d < 3; d++) e[3*i + d] = L->e[i][d];
+    w[i] = L->w[i]; opp[i] = L->opp[i];
+    for (int j = 0; j < L->Q; j++) M[i*L->Q + j] = L->M[i][j];
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+typedef struct Ctx {
+  const SlfParams *P;
+  const Lat *L;
+  int nx, ny, nz, ax, ay, az;
+  long long DS;
+  long long stride[3];
+  uint32_t tmask; int oshift, pshift; uint32_t pmask;
+  REAL omega;        /* (float)(1/tau), relaxation.mako:133 */
+  REAL tau;
+  REAL visc;
+  REAL a[3];
+  int forced;
+  REAL rates[MAXQ];
+} Ctx;
+
+static int ctx_init(Ctx *C, const SlfParams *P) {
+  lat_init();
+  if (!P || P->struct_bytes != sizeof(SlfParams)) return SLF_EINVAL;
+  if (P->lattice < 0 || P->lattice > 2) return SLF_EINVAL;
+  C->P = P; C->L = &g_lat[P->lattice];
+  if (P->model == SLF_MRT && !C->L->has_mrt) return SLF_EUNSUPPORTED;
+  C->nx = P->lat_nx; C->ny = P->lat_ny; C->nz = C->L->D == 3 ? P->lat_nz : 1;
+  C->ax = P->arr_nx; C->ay = P->arr_ny; C->az = C->L->D == 3 ? P->arr_nz : 1;
+  C->DS = (long long)C->ax * C->ay * C->az;
+  C->stride[0] = 1; C->stride[1] = C->ax; C->stride[2] = (long long)C->ax * C->ay;
+  C->tmask = (1u << P->bits_type) - 1u;
+  C->pshift = P->bits_type; C->pmask = (1u << P->bits_param) - 1u;
+  C->oshift = P->bits_type + P->bits_param + P->bits_scratch;
+  double tau = (6.0 * P->visc + 1.0) / 2.0;     /* sym.py:847-848 */
+  C->tau = (REAL)tau;
+  C->omega = (REAL)(1.0 / tau);
+  C->visc = (REAL)P->visc;
+  C->forced = P->force_enabled;
+  for (int d = 0; d < 3; d++) C->a[d] = (REAL)P->accel[d];
+  /* relaxation_mrt.mako:44-46 evaluates inv_tau = 1/(0.5 + 3 visc) in REAL */
+  REAL inv_tau = (REAL)1.0 / ((REAL)0.5 + (REAL)3.0 * C->visc);
+  for (int k = 0; k < C->L->Q; k++) C->rates[k] = C->L->rates[k] < 0 ? inv_tau : (REAL)C->L->rates[k];
+  return 0;
+}
+
+static inline int nclass(const Ctx *C, uint32_t type) {
+  for (int k = 0; k < SLF_NT_COUNT; k++) if (C->P->type_id[k] == type) return k;
+  return -1;
+}
+
+/* f^eq, sym_equilibrium.py:90-120: w_i (rho + rho0 * horner(3 e.v + 4.5 (e.v)^2 - 1.5 v.v)), rho0 = rho */
+static inline void feq_all(const Lat *L, REAL rho, const REAL *v, REAL *out) {
+  REAL vv = 0;
+  for (int d = 0; d < L->D; d++) vv += v[d] * v[d];
+  for (int i = 0; i < L->Q; i++) {
+    REAL ev = 0;
+    for (int d = 0; d < L->D; d++) ev += (REAL)L->e[i][d] * v[d];
+    REAL h = (REAL)3.0 * ev + (REAL)4.5 * ev * ev - (REAL)1.5 * vv;
+    out[i] = (REAL)L->w[i] * (rho + rho * h);
+  }
+}
+
+static inline void fill_missing_with_opposite(const Lat *L, int orient, REAL *f) {
+  /* boundary.mako:418-422 with sym.get_missing_dists (sym.py:534-543) */
+  const int *n = L->e[L->dir2vec[orient]];
+  for (int i = 0; i < L->Q; i++) {
+    int sp = 0; for (int d = 0; d < L->D; d++) sp += L->e[i][d] * n[d];
+    if (sp > 0) f[i] = f[L->opp[i]];
+  }
+}
+
+static inline void bounce_back(const Lat *L, REAL *f) {   /* boundary.mako:255-264 */
+  for (int i = 0; i < L->Q; i++) { int j = L->opp[i]; if (i < j) { REAL t = f[i]; f[i] = f[j]; f[j] = t; } }
+}
+
+/* MS_relaxate, relaxation_mrt.mako:31-97 */
+static inline void mrt_relax(const Ctx *C, int cls, REAL *f, REAL *v) {
+  const Lat *L = C->L; const int Q = L->Q, D = L->D;
+  REAL m[MAXQ], meq[MAXQ];
+  for (int k = 0; k < Q; k++) { REAL s = 0; for (int i = 0; i < Q; i++) if (L->M[k][i]) s += (REAL)L->M[k][i] * f[i]; m[k] = s; }
+  const int im[3] = {L->i_mx, L->i_my, L->i_mz};
+  if (C->forced) for (int d = 0; d < D; d++) m[im[d]] += (REAL)0.5 * C->a[d];   /* fluid_momentum :11-28 */
+  REAL rho = m[0], mx = m[im[0]], my = m[im[1]], mz = D == 3 ? m[im[2]] : 0;
+  for (int k = 0; k < Q; k++) meq[k] = 0;
+  if (C->P->lattice == SLF_D2Q9) {               /* sym.py:122-149 */
+    meq[1] = (REAL)-2.0 * rho + (REAL)3.0 * (mx*mx + my*my);
+    meq[2] = rho - (REAL)3.0 * (mx*mx + my*my);
+    meq[4] = -mx; meq[6] = -my;
+    meq[7] = mx*mx - my*my; meq[8] = mx*my;
+  } else {                                        /* D3Q19, sym.py:384-400 */
+    REAL ir = (REAL)1.0 / rho, m2 = mx*mx + my*my + mz*mz;
+    meq[1] = (REAL)-11.0 * rho + (REAL)19.0 * ir * m2;
+    meq[2] = (REAL)(-475.0/63.0) * ir * m2;
+    meq[4] = (REAL)(-2.0/3.0) * mx; meq[6] = (REAL)(-2.0/3.0) * my; meq[8] = (REAL)(-2.0/3.0) * mz;
+    meq[9] = ir * ((REAL)2.0*mx*mx - (my*my + mz*mz));
+    meq[11] = ir * (my*my - mz*mz);
+    meq[13] = ir * mx*my; meq[14] = ir * my*mz; meq[15] = ir * mx*mz;
+  }
+  if (cls == SLF_NT_EQUILIBRIUM_VELOCITY || cls == SLF_NT_EQUILIBRIUM_DENSITY)   /* :59-77 */
+    for (int k = 0; k < Q; k++) if (L->rates[k] != 0) m[k] = meq[k];
+  for (int k = 0; k < Q; k++) if (L->rates[k] != 0) m[k] -= C->rates[k] * (m[k] - meq[k]);
+  if (C->forced) for (int d = 0; d < D; d++) m[im[d]] += (REAL)0.5 * C->a[d];
+  for (int k = 0; k < Q; k++) m[k] = m[k] / (REAL)L->Mnorm[k];
+  for (int i = 0; i < Q; i++) { REAL s = 0; for (int k = 0; k < Q; k++) if (L->M[k][i]) s += (REAL)L->M[k][i] * m[k]; f[i] = s; }
+  if (C->forced) for (int d = 0; d < D; d++) v[d] += (REAL)0.5 * C->a[d];       /* fluid_output_velocity */
+}
+
+/* BGK_relaxate0, relaxation.mako:99-181 + relaxation_common.mako:56-64,110-149,208-237 */
+static inline void bgk_relax(const Ctx *C, REAL rho, REAL *f, REAL *v) {
+  const Lat *L = C->L; const int Q = L->Q, D = L->D;
+  REAL v0[3] = {0, 0, 0}, feq[MAXQ];
+  for (int d = 0; d < D; d++) v0[d] = C->forced ? v[d] + (REAL)0.5 * C->a[d] : v[d];
+  feq_all(L, rho, v0, feq);
+  for (int i = 0; i < Q; i++) f[i] += C->omega * (feq[i] - f[i]);
+  if (C->forced) {
+    /* Guo, sym_force.py:121-160: pref = rho/cs^2 (1 - 1/(2 tau)) */
+    REAL pref = rho * (REAL)3.0 * ((REAL)1.0 - (REAL)1.0 / ((REAL)2.0 * C->tau));
+    for (int i = 0; i < Q; i++) {
+      REAL ev = 0; for (int d = 0; d < D; d++) ev += (REAL)L->e[i][d] * v0[d];
+      REAL s = 0;
+      for (int d = 0; d < D; d++) s += ((REAL)L->e[i][d] - v0[d] + (REAL)3.0 * ev * (REAL)L->e[i][d]) * C->a[d];
+      f[i] += pref * (REAL)L->w[i] * s;
+    }
+    for (int d = 0; d < D; d++) v[d] += (REAL)0.5 * C->a[d];
+  }
+}
+
+static inline int in_bounds_target(const Ctx *C, const int *e, int x, int y, int z) {
+  /* prop_bnd, propagation.mako:36-41: positive component needs coord < lim-1, negative coord > 0 */
+  const int c[3] = {x, y, z}, lim[3] = {C->nx, C->ny, C->nz};
+  for (int d = 0; d < C->L->D; d++) {
+    if (e[d] > 0 && !(c[d] < lim[d] - 1)) return 0;
+    if (e[d] < 0 && !(c[d] > 0)) return 0;
+  }
+  return 1;
+}
+
+int orc_collide_and_propagate(const SlfParams *P, const uint32_t *map, const REAL *din, REAL *dout,
+                              REAL *orho, REAL *ovx, REAL *ovy, REAL *ovz,
+                              int options, uint32_t iteration, int z_begin, int z_end) {
+  Ctx Cs; int rc = ctx_init(&Cs, P); if (rc) return rc;
+  const Ctx *C = &Cs; const Lat *L = C->L; const int Q = L->Q, D = L->D;
+  const long long DS = C->DS;
+  REAL *ov[3] = {ovx, ovy, ovz};
+  const int aa = P->access_pattern == SLF_AA;
+  const int odd = aa && (iteration & 1);
+  const int outer_n = D == 3 ? C->nz : C->ny;
+  if (z_end < 0) z_end = outer_n;
+  long long off[MAXQ];
+  for (int i = 0; i < Q; i++) off[i] = L->e[i][0] + C->stride[1] * L->e[i][1] + C->stride[2] * L->e[i][2];
+
+#pragma omp parallel for schedule(static)
+  for (int o = z_begin; o < z_end; o++) {
+    const int y0 = D == 3 ? 0 : o, y1 = D == 3 ? C->ny : o + 1, z = D == 3 ? o : 0;
+    for (int y = y0; y < y1; y++)
+    for (int x = 0; x < C->nx; x++) {
+      const long long gi = x + C->stride[1] * y + C->stride[2] * z;
+      const uint32_t code = map[gi];
+      const uint32_t type = code & C->tmask;
+      const int cls = nclass(C, type);
+      if (cls == SLF_NT_GHOST || cls == SLF_NT_UNUSED) continue;      /* isExcludedNode */
+      if (cls == SLF_NT_PROPAGATION_ONLY) continue;                   /* nothing but barriers */
+      if (cls < 0) continue;
+      const int orient = (int)(code >> C->oshift);
+      REAL f[MAXQ], rho, v[3] = {0, 0, 0};
+      /* getDist */
+      if (!odd) for (int i = 0; i < Q; i++) f[i] = din[gi + DS * i];
+      else      for (int i = 0; i < Q; i++) f[i] = din[gi - off[i] + DS * L->opp[i]];
+      /* getMacro */
+      const int standard = (cls == SLF_NT_FLUID || cls == SLF_NT_FULLBB_WALL || cls == SLF_NT_HALFBB_WALL ||
+                            cls == SLF_NT_DO_NOTHING);
+      const int vel_bc = (cls == SLF_NT_EQUILIBRIUM_VELOCITY || cls == SLF_NT_REGULARIZED_VELOCITY);
+      const int den_bc = (cls == SLF_NT_EQUILIBRIUM_DENSITY || cls == SLF_NT_REGULARIZED_DENSITY);
+      if (standard || orient == 0) {
+        rho = 0; for (int i = 0; i < Q; i++) rho += f[i];
+        for (int d = 0; d < D; d++) { REAL s = 0; for (int i = 0; i < Q; i++) s += (REAL)L->e[i][d] * f[i]; v[d] = s / rho; }
+      } else if (vel_bc) {
+        const int pidx = (int)((code >> C->pshift) & C->pmask);
+        fill_missing_with_opposite(L, orient, f);
+        rho = 0; for (int i = 0; i < Q; i++) rho += f[i];
+        const int *n = L->e[L->dir2vec[orient]];
+        REAL nv = 0;
+        for (int d = 0; d < D; d++) { v[d] = (REAL)P->node_params[pidx + d]; nv += (REAL)n[d] * v[d]; }
+        rho = rho / ((REAL)1.0 - nv);                                  /* sym.py:627 */
+      } else { /* den_bc */
+        const int pidx = (int)((code >> C->pshift) & C->pmask);
+        fill_missing_with_opposite(L, orient, f);
+        rho = 0; for (int i = 0; i < Q; i++) rho += f[i];
+        const REAL par_rho = (REAL)P->node_params[pidx];
+        const int *n = L->e[L->dir2vec[orient]];
+        for (int d = 0; d < D; d++) v[d] = (REAL)(-n[d]) * (rho - par_rho) / par_rho;   /* sym.py:666-680 */
+        rho = par_rho;
+      }
+      /* precollisionBoundaryConditions */
+      if (cls == SLF_NT_FULLBB_WALL) {
+        bounce_back(L, f);
+      } else if (cls == SLF_NT_EQUILIBRIUM_VELOCITY || cls == SLF_NT_EQUILIBRIUM_DENSITY) {
+        feq_all(L, rho, v, f);
+      } else if (cls == SLF_NT_REGULARIZED_VELOCITY || cls == SLF_NT_REGULARIZED_DENSITY) {
+        if (orient == 0) {
+          bounce_back(L, f);                                           /* boundary.mako:336-338 */
+        } else {
+          REAL feq[MAXQ]; feq_all(L, rho, v, feq);
+          const int *n = L->e[L->dir2vec[orient]];
+          for (int i = 0; i < Q; i++) {                                 /* noneq_bb, sym.py:750-766 */
+            int sp = 0; for (int d = 0; d < D; d++) sp += L->e[i][d] * n[d];
+            if (sp > 0) f[i] = f[L->opp[i]] - feq[L->opp[i]] + feq[i];
+          }
+          REAL flux[3][3];
+          for (int a = 0; a < D; a++) for (int b = 0; b < D; b++) {     /* boundary.mako:298-304 */
+            REAL s = 0; for (int i = 0; i < Q; i++) s += (REAL)(L->e[i][a] * L->e[i][b]) * f[i];
+            REAL eq = a == b ? rho * (v[a]*v[a] + (REAL)(1.0/3.0)) : rho * v[a] * v[b];
+            flux[a][b] = s - eq;
+          }
+          for (int i = 0; i < Q; i++) {                                 /* sym.py:882-891 */
+            REAL s = 0;
+            for (int a = 0; a < D; a++) for (int b = 0; b < D; b++)
+              s += flux[a][b] * ((REAL)(L->e[i][a] * L->e[i][b]) - (a == b ? (REAL)(1.0/3.0) : (REAL)0));
+            REAL t = feq[i] + (REAL)L->w[i] * (REAL)4.5 * s;
+            f[i] = t > (REAL)1e-7 ? t : (REAL)1e-7;
+          }
+        }
+      } else if (cls == SLF_NT_DO_NOTHING && aa) {                      /* boundary.mako:862-877 */
+        if (orient != 0) {
+          const int *n = L->e[L->dir2vec[orient]];
+          for (int i = 0; i < Q; i++) {
+            int sp = 0; for (int d = 0; d < D; d++) sp += L->e[i][d] * n[d];
+            if (sp <= 0) continue;
+            if (odd) dout[gi + DS * i] = f[i];
+            else     dout[gi + off[L->opp[i]] + DS * L->opp[i]] = f[i];
+          }
+        }
+      }
+      /* relaxate */
+      const int wet = (cls == SLF_NT_FLUID || cls == SLF_NT_HALFBB_WALL || vel_bc || den_bc || cls == SLF_NT_DO_NOTHING);
+      if (wet && P->relaxation_enabled) {
+        if (P->model == SLF_MRT) mrt_relax(C, cls, f, v);
+        else bgk_relax(C, rho, f, v);
+      }
+      /* postcollisionBoundaryConditions: half-way bounce-back, boundary.mako:653-683 */
+      if (cls == SLF_NT_HALFBB_WALL) {
+        for (int i = 1; i < Q; i++) {
+          int missing;   /* slot whose data is undefined; f[name] is written into it */
+          int name;
+          if (P->use_link_tags) {
+            if (orient & (1 << (i - 1))) continue;   /* link i points to a fluid node */
+            name = i; missing = L->opp[i];
+          } else {
+            if (orient == 0) break;
+            const int *n = L->e[L->dir2vec[orient]];
+            int sp = 0; for (int d = 0; d < D; d++) sp += L->e[i][d] * n[d];
+            if (sp <= 0) continue;
+            missing = i; name = L->opp[i];
+          }
+          if (!aa || odd) dout[gi + DS * missing] = f[name];
+          else dout[gi + off[L->opp[missing]] + DS * L->opp[missing]] = f[name];
+        }
+      }
+      /* save_macro_fields */
+      if ((options & SLF_OPTION_SAVE_MACRO_FIELDS) && wet) {
+        orho[gi] = rho;
+        for (int d = 0; d < D; d++) ov[d][gi] = v[d];
+      }
+      /* propagate */
+      if (!P->propagation_enabled) {
+        for (int i = 0; i < Q; i++) dout[gi + DS * i] = f[i];
+      } else if (aa && !odd) {
+        for (int i = 0; i < Q; i++) dout[gi + DS * L->opp[i]] = f[i];
+      } else {
+        for (int i = 0; i < Q; i++)
+          if (in_bounds_target(C, L->e[i], x, y, z)) dout[gi + off[i] + DS * i] = f[i];
+      }
+    }
+  }
+  return 0;
+}
+
+/* SetInitialConditions, lb_single_fluid.mako:101-127: every node with gx < lat_nx, no type test */
+int orc_set_initial_conditions(const SlfParams *P, REAL *dist, const REAL *ivx, const REAL *ivy,
+                               const REAL *ivz, const REAL *irho, const uint32_t *map) {
+  (void)map;
+  Ctx Cs; int rc = ctx_init(&Cs, P); if (rc) return rc;
+  const Ctx *C = &Cs; const Lat *L = C->L;
+  for (int z = 0; z < C->nz; z++) for (int y = 0; y < C->ny; y++) for (int x = 0; x < C->nx; x++) {
+    long long gi = x + C->stride[1] * y + C->stride[2] * z;
+    REAL v[3], feq[MAXQ]; v[0] = ivx[gi]; v[1] = ivy[gi]; v[2] = L->D == 3 ? ivz[gi] : (REAL)0;
+    feq_all(L, irho[gi], v, feq);
+    for (int i = 0; i < L->Q; i++) dist[gi + C->DS * i] = feq[i];
+  }
+  return 0;
+}
+
+/* PrepareMacroFields, lb_single_fluid.mako:129-159 (density only) */
+int orc_prepare_macro_fields(const SlfParams *P, const uint32_t *map, const REAL *din, REAL *orho,
+                             int options, uint32_t iteration) {
+  (void)options;
+  Ctx Cs; int rc = ctx_init(&Cs, P); if (rc) return rc;
+  const Ctx *C = &Cs; const Lat *L = C->L; const int Q = L->Q;
+  const int odd = P->access_pattern == SLF_AA && (iteration & 1);
+  for (int z = 0; z < C->nz; z++) for (int y = 0; y < C->ny; y++) for (int x = 0; x < C->nx; x++) {
+    long long gi = x + C->stride[1] * y + C->stride[2] * z;
+    int cls = nclass(C, map[gi] & C->tmask);
+    if (cls < 0 || cls == SLF_NT_GHOST || cls == SLF_NT_UNUSED || cls == SLF_NT_PROPAGATION_ONLY) continue;
+    REAL rho = 0;
+    for (int i = 0; i < Q; i++) {
+      long long off = L->e[i][0] + C->stride[1] * L->e[i][1] + C->stride[2] * L->e[i][2];
+      rho += odd ? din[gi - off + C->DS * L->opp[i]] : din[gi + C->DS * i];
+    }
+    orho[gi] = rho;
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------
+ * ApplyPeriodicBoundaryConditions[WithSwap], kernel_utils.mako:19-384.
+ * The template generates one condition chain per population at render time; here the
+ * same rules are evaluated at run time from (basis, block_periodicity, bnd_limits).
+ * ------------------------------------------------------------------------------------ */
+static inline long long gidx(const Ctx *C, const int *c) { return c[0] + C->stride[1] * c[1] + C->stride[2] * c[2]; }
+
+/* make_cond(i), kernel_utils.mako:120-171 */
+static int pbc_make_cond(const Ctx *C, int axis, int opposite, const int *e, const int *oth, int nother,
+                         const int *idx, const int *maxd) {
+  const int *per = C->P->periodic;
+  if (opposite) {
+    for (int k = 0; k < nother; k++) if (!(idx[k] >= 1 && idx[k] <= maxd[k])) return 0;
+    return 1;
+  }
+  if (C->L->D == 2) {
+    int c = e[1 - axis];
+    if (c == 1) return idx[0] > 1 && idx[0] <= maxd[0];
+    if (c == -1) return idx[0] < maxd[0] && idx[0] >= 1;
+    return 1;
+  }
+  for (int k = 0; k < 2; k++) {
+    int c = e[oth[k]];
+    int both = per[axis] && per[oth[k]];
+    if (c == 1) { if (!(idx[k] > 1)) return 0; if (both && !(idx[k] <= maxd[k])) return 0; }
+    else if (c == -1) { if (!(idx[k] < maxd[k])) return 0; if (both && !(idx[k] >= 1)) return 0; }
+  }
+  return 1;
+}
+
+/* handle_corners, kernel_utils.mako:32-118.  Returns 1 and fills `tgt` with the node the
+ * value must be copied to when one of the generated conditions matches (first match wins). */
+static int pbc_corner_target(const Ctx *C, int axis, int opposite, const int *e, const int *oth, int nother,
+                             const int *idx, int axis_target, int *tgt) {
+  const int *per = C->P->periodic; const int lim[3] = {C->nx, C->ny, C->nz};
+  /* entry 0: corner nodes */
+  {
+    int ncond = 0, ok = 1, t[3] = {0, 0, 0};
+    t[axis] = axis_target;
+    for (int k = 0; k < nother; k++) {
+      int oa = oth[k], c = e[oa];
+      if (c == 0 || !per[oa]) { t[oa] = idx[k]; continue; }
+      if (c == 1) { int shift = opposite ? 2 : 1; ncond++; if (idx[k] != lim[oa] - shift) ok = 0; t[oa] = opposite ? 0 : 1; }
+      else { int shift = opposite ? 1 : 0; ncond++; if (idx[k] != shift) ok = 0; t[oa] = lim[oa] - (opposite ? 1 : 2); }
+    }
+    if (ncond > 0 && ok) { tgt[0] = t[0]; tgt[1] = t[1]; tgt[2] = t[2]; return 1; }
+  }
+  /* edge entries: only for vectors with three non-zero components (D3Q27) */
+  if (abs(e[0]) + abs(e[1]) + abs(e[2]) == 3) {
+    for (int k = 0; k < 2; k++) {
+      int oa = oth[k], ob = oth[1 - k], id_ = idx[k], id2 = idx[1 - k];
+      int ok = 1, t[3] = {0, 0, 0};
+      t[axis] = axis_target;
+      if (e[oa] == 1) { int shift = opposite ? 2 : 1, start = opposite ? 1 : 2; if (!(id_ >= start && id_ < lim[oa] - shift)) ok = 0; }
+      else { int shift = opposite ? 1 : 2; if (!(id_ < lim[oa] - shift && id_ >= 1)) ok = 0; }
+      t[oa] = id_;
+      if (e[ob] == 1) { int shift = opposite ? 2 : 1; if (id2 != lim[ob] - shift) ok = 0; t[ob] = opposite ? 0 : 1; }
+      else { int shift = opposite ? 1 : 0; if (id2 != shift) ok = 0; t[ob] = lim[ob] - (opposite ? 1 : 2); }
+      if (ok) { tgt[0] = t[0]; tgt[1] = t[1]; tgt[2] = t[2]; return 1; }
+    }
+  }
+  return 0;
+}
+
+int orc_apply_periodic_boundary_conditions(const SlfParams *P, REAL *dist, int axis, int with_swap) {
+  Ctx Cs; int rc = ctx_init(&Cs, P); if (rc) return rc;
+  const Ctx *C = &Cs; const Lat *L = C->L; const int D = L->D, Q = L->Q;
+  if (axis < 0 || axis >= D) return D == 2 && axis == 2 ? 0 : SLF_EINVAL;
+  const int lim[3] = {C->nx, C->ny, C->nz};
+  int oth[2], nother = D - 1;
+  if (D == 2) { oth[0] = 1 - axis; oth[1] = 2; }
+  else { const int oa[3][2] = {{1, 2}, {0, 2}, {0, 1}}; oth[0] = oa[axis][0]; oth[1] = oa[axis][1]; }
+  const int maxd[2] = {lim[oth[0]] - 2, D == 3 ? lim[oth[1]] - 2 : 0};
+  const long long offset = with_swap ? -C->stride[axis] : C->stride[axis];
+  const int n1 = lim[oth[0]], n2 = D == 3 ? lim[oth[1]] : 1;
+  for (int i2 = 0; i2 < n2; i2++) for (int i1 = 0; i1 < n1; i1++) {
+    const int idx[2] = {i1, i2};
+    if (with_swap && D == 3) { if (i1 >= lim[oth[0]] - 1 || i2 >= lim[oth[1]] - 1 || i1 < 1 || i2 < 1) continue; }
+    int cl[3] = {0, 0, 0}, ch[3] = {0, 0, 0};
+    cl[oth[0]] = ch[oth[0]] = i1; if (D == 3) cl[oth[1]] = ch[oth[1]] = i2;
+    cl[axis] = with_swap ? 1 : 0;
+    ch[axis] = with_swap ? lim[axis] - 1 : lim[axis] - 2;
+    const long long gi_low = gidx(C, cl), gi_high = gidx(C, ch);
+    /* low -> high: populations with e[axis] == -1 */
+    REAL val[MAXQ];
+    for (int i = 1; i < Q; i++) if (L->e[i][axis] == -1) { int j = with_swap ? L->opp[i] : i; val[i] = dist[gi_low + C->DS * j]; }
+    for (int i = 1; i < Q; i++) if (L->e[i][axis] == -1) {
+      const int j = with_swap ? L->opp[i] : i; const REAL fv = val[i];
+      const int n2e = L->e[i][0]*L->e[i][0] + L->e[i][1]*L->e[i][1] + L->e[i][2]*L->e[i][2];
+      if (!isfinite(fv)) continue;
+      if (n2e > 1) {
+        int main_ok = pbc_make_cond(C, axis, with_swap, L->e[i], oth, nother, idx, maxd);
+        if (main_ok) dist[gi_high + C->DS * j] = fv;
+        if (with_swap || !main_ok) {
+          int tgt[3];
+          if (pbc_corner_target(C, axis, with_swap, L->e[i], oth, nother, idx, with_swap ? lim[axis] - 1 : lim[axis] - 2, tgt))
+            dist[gidx(C, tgt) + C->DS * j] = fv;
+        }
+      } else {
+        dist[gi_high + C->DS * j] = fv;
+      }
+    }
+    /* high -> low: populations with e[axis] == +1 */
+    for (int i = 1; i < Q; i++) if (L->e[i][axis] == 1) { int j = with_swap ? L->opp[i] : i; val[i] = dist[gi_high + offset + C->DS * j]; }
+    for (int i = 1; i < Q; i++) if (L->e[i][axis] == 1) {
+      const int j = with_swap ? L->opp[i] : i; const REAL fv = val[i];
+      const int n2e = L->e[i][0]*L->e[i][0] + L->e[i][1]*L->e[i][1] + L->e[i][2]*L->e[i][2];
+      if (!isfinite(fv)) continue;
+      if (n2e > 1) {
+        int main_ok = pbc_make_cond(C, axis, with_swap, L->e[i], oth, nother, idx, maxd);
+        if (main_ok) dist[gi_low + offset + C->DS * j] = fv;
+        if (with_swap || !main_ok) {
+          int tgt[3];
+          if (pbc_corner_target(C, axis, with_swap, L->e[i], oth, nother, idx, with_swap ? 0 : 1, tgt))
+            dist[gidx(C, tgt) + C->DS * j] = fv;
+        }
+      } else {
+        dist[gi_low + offset + C->DS * j] = fv;
+      }
+    }
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------
+ * Collect/DistributeContinuousData[WithSwap], kernel_utils.mako:476-794.
+ * Buffer layout [dist][other][x]; `face` >= 2 (y/z faces).  In 2-D pass max_other = 1.
+ * ------------------------------------------------------------------------------------ */
+static int face_dists(const Lat *L, int face, int *out) {
+  /* sym.get_interblock_dists(grid, face_to_normal(face)), sym.py:829-845 */
+  int axis = face / 2, sgn = (face & 1) ? 1 : -1, n = 0;
+  for (int i = 0; i < L->Q; i++) if (L->e[i][axis] * sgn >= 1) out[n++] = i;
+  return n;
+}
+
+static int face_layer(const Ctx *C, int face, int which) {
+  /* which: 0 lat_linear, 1 lat_linear_macro, 2 lat_linear_dist, 3 lat_linear_with_swap
+   * subdomain_runner.py:488-510 (envelope 1) */
+  const int lim[3] = {C->nx, C->ny, C->nz}; int axis = face / 2, hi = face & 1, n = lim[axis];
+  switch (which) {
+    case 0: return hi ? n - 1 : 0;
+    case 1: return hi ? n - 2 : 1;
+    case 2: return hi ? 1 : n - 2;
+    default: return hi ? 0 : n - 1;
+  }
+}
+
+static int xfer(const SlfParams *P, REAL *dist, int face, int base_gx, int base_other, int max_lx,
+                int max_other, REAL *buffer, int with_swap, int distribute) {
+  Ctx Cs; int rc = ctx_init(&Cs, P); if (rc) return rc;
+  const Ctx *C = &Cs; const Lat *L = C->L;
+  if (face < 2 || face >= 2 * L->D) return SLF_EINVAL;
+  int dl[MAXQ], nd = face_dists(L, face, dl);
+  int layer = face_layer(C, face, distribute ? (with_swap ? 3 : 2) : (with_swap ? 1 : 0));
+  int axis = face / 2;
+  if (L->D == 2) max_other = 1;
+  for (int k = 0; k < nd; k++) for (int o = 0; o < max_other; o++) for (int x = 0; x < max_lx; x++) {
+    int c[3] = {base_gx + x, 0, 0};
+    if (L->D == 2) c[1] = layer;
+    else if (axis == 1) { c[1] = layer; c[2] = base_other + o; }
+    else { c[1] = base_other + o; c[2] = layer; }
+    int slot = with_swap ? L->opp[dl[k]] : dl[k];
+    long long di = gidx(C, c) + C->DS * slot;
+    long long bi = ((long long)k * max_other + o) * max_lx + x;
+    if (distribute) dist[di] = buffer[bi]; else buffer[bi] = dist[di];
+  }
+  return 0;
+}
+
+int orc_collect_continuous_data(const SlfParams *P, const REAL *dist, int face, int base_gx, int base_other,
+                                int max_lx, int max_other, REAL *buffer, int with_swap) {
+  return xfer(P, (REAL *)dist, face, base_gx, base_other, max_lx, max_other, buffer, with_swap, 0);
+}
+int orc_distribute_continuous_data(const SlfParams *P, REAL *dist, int face, int base_gx, int base_other,
+                                   int max_lx, int max_other, const REAL *buffer, int with_swap) {
+  return xfer(P, dist, face, base_gx, base_other, max_lx, max_other, (REAL *)buffer, with_swap, 1);
+}
+
+int orc_sizeof_real(void) { return (int)sizeof(REAL); }

@@ -1,0 +1,147 @@
+"""ctypes wrapper of the CPU oracle (oracle/lbm_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  The product package never
+imports this module.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS = {}
+
+
+def build(force=False):
+    """Compiles liboracle_f32.so / liboracle_f64.so with gcc (Makefile in this dir)."""
+    args = ['make', '-C', _HERE, '-s']
+    if force:
+        args.append('-B')
+    subprocess.check_call(args)
+
+
+def _lib(dtype):
+    dtype = np.dtype(dtype)
+    key = 'f32' if dtype == np.float32 else 'f64'
+    if key not in _LIBS:
+        path = os.path.join(_HERE, 'liboracle_%s.so' % key)
+        if not os.path.exists(path):
+            build()
+        _LIBS[key] = ctypes.CDLL(path)
+        assert _LIBS[key].orc_sizeof_real() == dtype.itemsize
+    return _LIBS[key]
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _chk(rc, what):
+    if rc != 0:
+        raise RuntimeError('oracle %s failed with code %d' % (what, rc))
+
+
+def collide_and_propagate(params, node_map, dist_in, dist_out, rho, v, options, iteration,
+                          z_begin=0, z_end=-1):
+    """One CollideAndPropagate launch (lb_single_fluid.mako:161-229).  For the AA
+    pattern pass the same array as dist_in and dist_out."""
+    lib = _lib(dist_in.dtype)
+    vz = v[2] if len(v) > 2 else None
+    _chk(lib.orc_collide_and_propagate(
+        ctypes.byref(params), _p(node_map), _p(dist_in), _p(dist_out), _p(rho), _p(v[0]), _p(v[1]),
+        _p(vz), ctypes.c_int(options), ctypes.c_uint32(iteration), ctypes.c_int(z_begin),
+        ctypes.c_int(z_end)), 'collide_and_propagate')
+
+
+def set_initial_conditions(params, dist, v, rho, node_map):
+    lib = _lib(dist.dtype)
+    vz = v[2] if len(v) > 2 else None
+    _chk(lib.orc_set_initial_conditions(ctypes.byref(params), _p(dist), _p(v[0]), _p(v[1]), _p(vz),
+                                        _p(rho), _p(node_map)), 'set_initial_conditions')
+
+
+def prepare_macro_fields(params, node_map, dist, rho, options, iteration):
+    lib = _lib(dist.dtype)
+    _chk(lib.orc_prepare_macro_fields(ctypes.byref(params), _p(node_map), _p(dist), _p(rho),
+                                      ctypes.c_int(options), ctypes.c_uint32(iteration)), 'prepare_macro')
+
+
+def apply_pbc(params, dist, axis, with_swap):
+    lib = _lib(dist.dtype)
+    _chk(lib.orc_apply_periodic_boundary_conditions(ctypes.byref(params), _p(dist), ctypes.c_int(axis),
+                                                    ctypes.c_int(int(with_swap))), 'apply_pbc')
+
+
+def collect(params, dist, face, base_gx, base_other, max_lx, max_other, buf, with_swap):
+    lib = _lib(dist.dtype)
+    _chk(lib.orc_collect_continuous_data(ctypes.byref(params), _p(dist), face, base_gx, base_other,
+                                         max_lx, max_other, _p(buf), int(with_swap)), 'collect')
+
+
+def distribute(params, dist, face, base_gx, base_other, max_lx, max_other, buf, with_swap):
+    lib = _lib(dist.dtype)
+    _chk(lib.orc_distribute_continuous_data(ctypes.byref(params), _p(dist), face, base_gx, base_other,
+                                            max_lx, max_other, _p(buf), int(with_swap)), 'distribute')
+
+
+def lattice_info(lattice_id):
+    lib = _lib(np.float32)
+    Q, D = ctypes.c_int(), ctypes.c_int()
+    e = np.zeros(27 * 3, np.int32)
+    w = np.zeros(27, np.float64)
+    opp = np.zeros(27, np.int32)
+    M = np.zeros(27 * 27, np.int32)
+    _chk(lib.orc_lattice_info(lattice_id, ctypes.byref(Q), ctypes.byref(D), _p(e), _p(w), _p(opp), _p(M)),
+         'lattice_info')
+    q = Q.value
+    return dict(Q=q, D=D.value, e=e[:3 * q].reshape(q, 3), w=w[:q], opp=opp[:q], M=M[:q * q].reshape(q, q))
+
+
+class Simulation(object):
+    """Drives the oracle the way SubdomainRunner.step() drives the kernels
+    (subdomain_runner.py:960-1058) for a single subdomain: CollideAndPropagate on the
+    whole domain, then the per-axis PBC kernels (lb_single.py:153-185,
+    subdomain_runner.py:984-1009)."""
+
+    def __init__(self, params, node_map, rho, v, dtype=np.float32):
+        self.p = params
+        self.dtype = np.dtype(dtype)
+        self.map = np.ascontiguousarray(node_map, dtype=np.uint32)
+        n = params.dist_size
+        self.rho = np.ascontiguousarray(rho, dtype=self.dtype).reshape(-1).copy()
+        self.v = [np.ascontiguousarray(c, dtype=self.dtype).reshape(-1).copy() for c in v]
+        self.dist_a = np.zeros(params.Q * n, dtype=self.dtype)
+        self.dist_b = np.zeros(params.Q * n, dtype=self.dtype) if params.access_pattern == 0 else None
+        self.iteration = 0
+        set_initial_conditions(params, self.dist_a, self.v, self.rho, self.map)
+        if self.dist_b is not None:
+            set_initial_conditions(params, self.dist_b, self.v, self.rho, self.map)
+
+    def current_dist(self):
+        """Array holding the latest populations (AB ping-pong, lb_single.py:105-106)."""
+        if self.dist_b is None or (self.iteration & 1) == 0:
+            return self.dist_a
+        return self.dist_b
+
+    def step(self, save_macro=False):
+        it = self.iteration
+        if self.dist_b is None:
+            din = dout = self.dist_a
+        elif (it & 1) == 0:
+            din, dout = self.dist_a, self.dist_b
+        else:
+            din, dout = self.dist_b, self.dist_a
+        collide_and_propagate(self.p, self.map, din, dout, self.rho, self.v,
+                              1 if save_macro else 0, it)
+        aa = self.dist_b is None
+        for axis in range(self.p.dim):
+            if self.p.periodic[axis]:
+                # _apply_pbc: base = 1 - (iteration & 1); AA even steps use the WithSwap kernel
+                apply_pbc(self.p, dout, axis, with_swap=(aa and (it & 1) == 0))
+        self.iteration += 1
+
+    def run(self, steps, save_last=True):
+        for k in range(steps):
+            self.step(save_macro=(save_last and k == steps - 1))

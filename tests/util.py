@@ -1,0 +1,53 @@
+"""Shared helpers for the test-suite (fixtures -> SlfParams, oracle runs, norms)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+from sailfish_b200 import params as P  # noqa: E402
+
+
+def load_case(name):
+    return np.load(os.path.join(GOLD, 'steps_%s.npz' % name))
+
+
+def params_from_case(c, access_pattern=None):
+    type_ids = {str(n): int(i) for n, i in zip(c['type_names'], c['type_ids'])}
+    accel = [float(a) for a in c['accel']]
+    return P.make_params(
+        str(c['grid']), str(c['model']), access_pattern or str(c['access_pattern']),
+        [int(x) for x in c['lat']], [int(x) for x in c['arr']], [int(x) for x in c['periodic']],
+        [int(x) for x in c['bits']], type_ids, [float(x) for x in c['node_params']],
+        float(c['visc']), accel, use_link_tags=bool(c['use_link_tags']))
+
+
+def real_mask(c):
+    """Boolean mask (array shape) of the non-ghost, non-padding nodes."""
+    lat = [int(x) for x in c['lat']]
+    shape = c['map'].shape
+    m = np.zeros(shape, bool)
+    if len(shape) == 3:
+        m[1:lat[2] - 1, 1:lat[1] - 1, 1:lat[0] - 1] = True
+    else:
+        m[1:lat[1] - 1, 1:lat[0] - 1] = True
+    return m
+
+
+def rel_linf(a, b):
+    """||a-b||_inf / ||b||_inf over finite entries of b (the parity metric of
+    SURVEY.md section 7 'Hard parts')."""
+    ok = np.isfinite(b)
+    d = np.abs(a[ok] - b[ok])
+    if d.size == 0:
+        return 0.0
+    scale = np.max(np.abs(b[ok]))
+    return float(np.max(d) / scale) if scale > 0 else float(np.max(d))
+
+
+CASES = ['ldc2d_bgk', 'ldc2d_mrt', 'ldc3d_bgk', 'ldc3d_mrt', 'ldc3d_q27', 'poi3d_press_mrt',
+         'poi3d_force_bgk', 'poi3d_force_mrt', 'box3d_bgk', 'box3d_q27', 'box2d_bgk']

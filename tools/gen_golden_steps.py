@@ -1,0 +1,139 @@
+"""Geometry + whole-step golden fixtures (see tools/gen_golden.py).  Build container only."""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_harness  # noqa: E402
+import numpy as np  # noqa: E402
+from ref_stepper import RefStepper  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+
+
+def _periodic_box_classes():
+    """All-fluid periodic box with a smooth initial field (the bandwidth microbenchmark
+    of SURVEY.md 8d), written against the reference API."""
+    from sailfish.subdomain import Subdomain2D, Subdomain3D
+    from sailfish.lb_single import LBFluidSim
+
+    class Box3D(Subdomain3D):
+        def boundary_conditions(self, hx, hy, hz):
+            pass
+
+        def initial_conditions(self, sim, hx, hy, hz):
+            sim.rho[:] = 1.0 + 1e-3 * np.sin(2 * np.pi * hx / self.gx) * np.cos(2 * np.pi * hz / self.gz)
+            sim.vx[:] = 0.05 * np.sin(2 * np.pi * hy / self.gy)
+            sim.vy[:] = 0.03 * np.cos(2 * np.pi * hz / self.gz)
+            sim.vz[:] = 0.02 * np.sin(2 * np.pi * (hx + hy) / self.gx)
+
+    class BoxSim3D(LBFluidSim):
+        subdomain = Box3D
+
+        @classmethod
+        def update_defaults(cls, defaults):
+            defaults.update({'lat_nx': 10, 'lat_ny': 9, 'lat_nz': 8, 'grid': 'D3Q19',
+                             'periodic_x': True, 'periodic_y': True, 'periodic_z': True})
+
+    class Box2D(Subdomain2D):
+        def boundary_conditions(self, hx, hy):
+            pass
+
+        def initial_conditions(self, sim, hx, hy):
+            sim.rho[:] = 1.0 + 1e-3 * np.sin(2 * np.pi * hx / self.gx)
+            sim.vx[:] = 0.05 * np.sin(2 * np.pi * hy / self.gy)
+            sim.vy[:] = 0.03 * np.cos(2 * np.pi * hx / self.gx)
+
+    class BoxSim2D(LBFluidSim):
+        subdomain = Box2D
+
+        @classmethod
+        def update_defaults(cls, defaults):
+            defaults.update({'lat_nx': 12, 'lat_ny': 10, 'grid': 'D2Q9',
+                             'periodic_x': True, 'periodic_y': True})
+    return BoxSim2D, BoxSim3D
+
+
+def _cases():
+    ldc2 = ref_harness.load_example('examples/ldc_2d.py').LDCSim
+    ldc3 = ref_harness.load_example('examples/ldc_3d.py').LDCSim
+    poi3 = ref_harness.load_example('examples/poiseuille_3d.py')
+    poi2 = ref_harness.load_example('examples/poiseuille.py')
+    from sailfish.geo import EqualSubdomainsGeometry3D
+    box2, box3 = _periodic_box_classes()
+    c = []
+    for ap in ('AB', 'AA'):
+        c.append(('ldc2d_bgk_' + ap, ldc2, None, ['--lat_nx=16', '--lat_ny=14', '--visc=0.05', '--access_pattern=' + ap], 20))
+        c.append(('ldc2d_mrt_' + ap, ldc2, None, ['--lat_nx=16', '--lat_ny=14', '--visc=0.05', '--model=mrt', '--access_pattern=' + ap], 20))
+        c.append(('ldc3d_bgk_' + ap, ldc3, None, ['--lat_nx=12', '--lat_ny=10', '--lat_nz=11', '--visc=0.04', '--access_pattern=' + ap], 20))
+        c.append(('ldc3d_mrt_' + ap, ldc3, None, ['--lat_nx=12', '--lat_ny=10', '--lat_nz=11', '--visc=0.04', '--model=mrt', '--access_pattern=' + ap], 20))
+        c.append(('ldc3d_q27_' + ap, ldc3, None, ['--lat_nx=10', '--lat_ny=10', '--lat_nz=9', '--visc=0.04', '--grid=D3Q27', '--access_pattern=' + ap], 16))
+        c.append(('poi3d_press_mrt_' + ap, poi3.PoiseuilleSim, EqualSubdomainsGeometry3D,
+                  ['--grid=D3Q19', '--lat_nx=12', '--lat_ny=12', '--lat_nz=16', '--flow_direction=z', '--drive=pressure',
+                   '--stationary', '--model=mrt', '--visc=0.1', '--access_pattern=' + ap], 20))
+        c.append(('poi3d_force_bgk_' + ap, poi3.PoiseuilleSim, EqualSubdomainsGeometry3D,
+                  ['--grid=D3Q19', '--lat_nx=14', '--lat_ny=12', '--lat_nz=12', '--flow_direction=x', '--drive=force',
+                   '--visc=0.1', '--access_pattern=' + ap], 20))
+        c.append(('poi3d_force_mrt_' + ap, poi3.PoiseuilleSim, EqualSubdomainsGeometry3D,
+                  ['--grid=D3Q19', '--lat_nx=12', '--lat_ny=12', '--lat_nz=14', '--flow_direction=z', '--drive=force',
+                   '--model=mrt', '--visc=0.1', '--access_pattern=' + ap], 20))
+        c.append(('box3d_bgk_' + ap, box3, None, ['--visc=0.02', '--access_pattern=' + ap], 12))
+        c.append(('box3d_q27_' + ap, box3, None, ['--visc=0.02', '--grid=D3Q27', '--access_pattern=' + ap], 12))
+        c.append(('box2d_bgk_' + ap, box2, None, ['--visc=0.02', '--access_pattern=' + ap], 12))
+    return c, poi2
+
+
+def pack_ctx(ctx):
+    remap = ctx['type_id_remap']
+    names = sorted(c.__name__ for c in ctx['node_types'])
+    ids = [int(remap[c.id]) for c in sorted(ctx['node_types'], key=lambda c: c.__name__)]
+    accel = np.zeros(3)
+    forces = ctx.get('forces')
+    if forces is not None and getattr(forces, 'numeric', None):
+        a = forces.numeric[0][True]
+        accel[:len(a)] = a
+    dim = ctx['grid'].dim
+    return dict(
+        grid=ctx['grid'].__name__, model=ctx['model'], access_pattern=ctx['access_pattern'],
+        lat=np.array([ctx['lat_nx'], ctx['lat_ny'], ctx['lat_nz'] if dim == 3 else 1]),
+        arr=np.array([ctx['arr_nx'], ctx['arr_ny'], ctx['arr_nz'] if dim == 3 else 1]),
+        periodic=np.array([int(bool(x)) for x in ctx['block_periodicity']]),
+        bits=np.array([ctx['nt_misc_shift'], ctx['nt_param_shift'], ctx['nt_scratch_shift']]),
+        type_names=np.array(names), type_ids=np.array(ids),
+        node_params=np.array([float(x) for x in ctx['node_params']] or [0.0]),
+        visc=np.float64(ctx['visc']), tau=np.float64(ctx['tau']), accel=accel,
+        use_link_tags=np.int32(bool(ctx.get('use_link_tags', True))))
+
+
+def main(what):
+    cases, _ = _cases()
+    for name, cls, geo, args, steps in cases:
+        cfg, runners = ref_harness.make_runners(cls, geo, args=args)
+        r = runners[0]
+        ctx = ref_harness.context_of(r)
+        out = pack_ctx(ctx)
+        out['map'] = r._subdomain.encoded_map().astype(np.uint32)
+        sim = r._sim
+        rho0 = r.field_base(sim.rho).astype(np.float64)
+        v0 = [r.field_base(c).astype(np.float64) for c in sim.v]
+        out['rho0'] = rho0
+        out['v0'] = np.array(v0)
+        out['fluid_map'] = r._subdomain.fluid_map()
+        if 'steps' in what:
+            st = RefStepper(r, ctx)
+            st.set_initial_conditions(rho0, v0)
+            for k in range(steps):
+                st.step(save_macro=(k == steps - 1))
+            out['steps'] = np.int32(steps)
+            out['dist'] = st.current_dist().copy()
+            out['rho'] = st.rho
+            out['v'] = np.array(st.v)
+            # mass over real fluid nodes, for the record
+            print('%-22s steps=%d  rho[min,max]=%.6f %.6f  max|v|=%.4e' % (
+                name, steps, np.nanmin(st.rho[np.isfinite(st.rho)]), np.nanmax(st.rho[np.isfinite(st.rho)]),
+                max(np.nanmax(np.abs(c[np.isfinite(c)])) for c in st.v)))
+        np.savez_compressed(os.path.join(GOLD, 'steps_%s.npz' % name), **out)
+
+
+if __name__ == '__main__':
+    main(sys.argv[1:] or ['geometry', 'steps'])
