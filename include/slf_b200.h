@@ -179,17 +179,27 @@ int  slf_collect_sparse_data(SlfPlan *plan, uint64_t idx_array, uint64_t dist, u
 int  slf_distribute_sparse_data(SlfPlan *plan, uint64_t idx_array, uint64_t dist, uint64_t buffer,
                                 int max_idx, uint64_t stream);
 
-/* ---- z-split halo exchange between the GPUs of one box -------------------------------
- * Replaces SubdomainRunner._send_dists/_recv_dists + ZMQ connectors
- * (subdomain_runner.py:1064-1139, connector.py:73-117) for conn_axis = z:
- * one call posts both faces' messages.  Device-to-device, no host staging.
- * `peer_*` are the neighbour's dist base pointers mapped into this process
- * (cudaIpc or same-process peer access); 0 = no neighbour on that side.
- * Parity of `iteration` (value AFTER the step, like sim.iteration in step():960-974)
- * selects the AA variant (ghost layer -> neighbour's first real layer, or first real
- * layer opposite slots -> neighbour's ghost layer). */
-int  slf_halo_push_z(SlfPlan *plan, uint64_t dist, uint64_t peer_low, uint64_t peer_high,
-                     SlfPlan *peer_low_plan_like, uint32_t iteration_after_step, uint64_t stream);
+/* ---- halo exchange between the GPUs of one box (subdomains split along the outermost
+ * axis: conn_axis = z in 3-D, y in 2-D) -------------------------------------------------
+ * Replaces SubdomainRunner._send_dists/_recv_dists + the collect/distribute kernels + the
+ * ZeroMQ connectors (subdomain_runner.py:1064-1139, kernel_utils.mako:526-794,
+ * connector.py:73-117): the |dists| planes of a face message are contiguous in the SoA
+ * lattice, so one kernel copies them from this GPU's lattice straight into the
+ * neighbour's lattice through a peer-mapped pointer (no pack, no host staging).
+ *   face        local face the populations leave through (SLF_Z_LOW/HIGH; 2-D: SLF_Y_*)
+ *   peer_dist   neighbour's dist base, mapped here (slf_ipc_open_handle / peer access)
+ *   peer_lat_n, peer_arr_n   neighbour's lattice / array extent along the split axis
+ *   with_swap   1 after an AA even (in-place) step: first real layer, opposite slots ->
+ *               neighbour's ghost layer; 0 after AB / AA-odd steps: ghost layer, natural
+ *               slots -> neighbour's first real layer (the reference's WithSwap variants).
+ */
+int  slf_halo_push(SlfPlan *plan, uint64_t dist, int face, uint64_t peer_dist, int peer_lat_n,
+                   int peer_arr_n, int with_swap, uint64_t stream);
+/* Stream-ordered counting semaphores in device memory for cross-GPU ordering of the pushes:
+ * signal = system-scope fence + atomic increment of `sem` (may be a peer pointer);
+ * wait   = spin until *sem > *consumed, then ++*consumed (both local uint32). */
+int  slf_sem_signal(uint64_t sem, uint64_t stream);
+int  slf_sem_wait(uint64_t sem, uint64_t consumed, uint64_t stream);
 
 /* CUDA IPC handles for the above (backend_cuda.py:122-126 wraps them but never calls them) */
 int  slf_ipc_get_handle(uint64_t dptr, void *handle64);      /* 64 bytes */

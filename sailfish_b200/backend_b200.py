@@ -1,0 +1,431 @@
+"""``backend_b200`` -- the sailfish compute backend for NVIDIA B200 (sm_100a).
+
+Drop-in for the reference's backend duck type (sailfish/backend_cuda.py:34-332): same
+method names, argument meaning and error behaviour, but instead of JIT-compiling a
+Mako-rendered source with pycuda it binds the prebuilt ``libslf_b200.so`` (C ABI in
+include/slf_b200.h) through ctypes.  ``build()`` receives the serialised code-generation
+context (see ``sailfish_b200.plugin``) and turns it into a plan; ``get_kernel()`` maps the
+reference's kernel *names* and positional argument lists to C entry points.
+
+There is no CPU fallback: a missing library or a missing CUDA device raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from sailfish_b200 import params as P
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libslf_b200.so')
+
+_u64 = ctypes.c_uint64
+_i = ctypes.c_int
+_u32 = ctypes.c_uint32
+_vp = ctypes.c_void_p
+
+# name -> (argtypes) ; every function returns int except where noted
+_PROTOTYPES = {
+    'slf_device_count': [ctypes.POINTER(_i)],
+    'slf_init': [_i],
+    'slf_device_info': [ctypes.c_char_p, _i, ctypes.POINTER(_u64), ctypes.POINTER(_i)],
+    'slf_malloc': [_u64, ctypes.POINTER(_u64)],
+    'slf_free': [_u64],
+    'slf_memset': [_u64, _i, _u64, _u64],
+    'slf_host_alloc': [_u64, ctypes.POINTER(_vp)],
+    'slf_host_free': [_vp],
+    'slf_memcpy_h2d': [_u64, _vp, _u64],
+    'slf_memcpy_d2h': [_vp, _u64, _u64],
+    'slf_memcpy_h2d_async': [_u64, _vp, _u64, _u64],
+    'slf_memcpy_d2h_async': [_vp, _u64, _u64, _u64],
+    'slf_memcpy_d2d_async': [_u64, _u64, _u64, _u64],
+    'slf_sync': [],
+    'slf_stream_create': [ctypes.POINTER(_u64), _i],
+    'slf_stream_destroy': [_u64],
+    'slf_stream_sync': [_u64],
+    'slf_stream_wait_event': [_u64, _u64],
+    'slf_event_create': [ctypes.POINTER(_u64), _i],
+    'slf_event_destroy': [_u64],
+    'slf_event_record': [_u64, _u64],
+    'slf_event_sync': [_u64],
+    'slf_event_elapsed_ms': [_u64, _u64, ctypes.POINTER(ctypes.c_float)],
+    'slf_plan_create': [ctypes.POINTER(P.SlfParams), ctypes.POINTER(_vp)],
+    'slf_plan_destroy': [_vp],
+    'slf_set_initial_conditions': [_vp, _u64, _u64, _u64, _u64, _u64, _u64, _u64],
+    'slf_collide_and_propagate': [_vp, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _i, _u32, _i, _i, _u64],
+    'slf_prepare_macro_fields': [_vp, _u64, _u64, _u64, _i, _u32, _u64],
+    'slf_apply_periodic_boundary_conditions': [_vp, _u64, _i, _i, _u64],
+    'slf_collect_continuous_data': [_vp, _u64, _i, _i, _i, _i, _i, _u64, _i, _u64],
+    'slf_distribute_continuous_data': [_vp, _u64, _i, _i, _i, _i, _i, _u64, _i, _u64],
+    'slf_collect_sparse_data': [_vp, _u64, _u64, _u64, _i, _u64],
+    'slf_distribute_sparse_data': [_vp, _u64, _u64, _u64, _i, _u64],
+    'slf_halo_push': [_vp, _u64, _i, _u64, _i, _i, _i, _u64],
+    'slf_sem_signal': [_u64, _u64],
+    'slf_sem_wait': [_u64, _u64, _u64],
+    'slf_ipc_get_handle': [_u64, _vp],
+    'slf_ipc_open_handle': [_vp, ctypes.POINTER(_u64)],
+    'slf_ipc_close_handle': [_u64],
+    'slf_enable_peer_access': [_i],
+}
+_SPECIAL = {
+    'slf_abi_version': ([], _i),
+    'slf_last_error': ([], ctypes.c_char_p),
+    'slf_launch_count': ([], _u64),
+}
+EXPORTED_SYMBOLS = sorted(list(_PROTOTYPES) + list(_SPECIAL))
+
+
+class B200Error(RuntimeError):
+    """Raised for any failing libslf_b200 call (the reference raises pycuda errors)."""
+
+
+class Lib(object):
+    """Thin checked wrapper over the C ABI."""
+
+    def __init__(self, path=LIB_PATH):
+        if not os.path.exists(path):
+            raise B200Error(
+                '%s not found: build it with `python -m sailfish_b200.build` '
+                '(there is no CPU fallback for the B200 backend)' % path)
+        self.path = path
+        self.cdll = ctypes.CDLL(path)
+        for name, argtypes in _PROTOTYPES.items():
+            fn = getattr(self.cdll, name)
+            fn.argtypes = argtypes
+            fn.restype = _i
+        for name, (argtypes, restype) in _SPECIAL.items():
+            fn = getattr(self.cdll, name)
+            fn.argtypes = argtypes
+            fn.restype = restype
+        if self.cdll.slf_abi_version() != 1:
+            raise B200Error('ABI version mismatch')
+
+    def call(self, name, *args):
+        rc = getattr(self.cdll, name)(*args)
+        if rc != 0:
+            msg = self.cdll.slf_last_error()
+            raise B200Error('%s failed (%d): %s' % (name, rc, msg.decode() if msg else ''))
+
+    def launch_count(self):
+        return int(self.cdll.slf_launch_count())
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = Lib()
+    return _LIB
+
+
+class Stream(object):
+    def __init__(self, high_priority=False):
+        h = _u64()
+        lib().call('slf_stream_create', ctypes.byref(h), int(high_priority))
+        self.handle = h.value
+
+    def synchronize(self):
+        lib().call('slf_stream_sync', self.handle)
+
+    def wait_for_event(self, ev):
+        lib().call('slf_stream_wait_event', self.handle, ev.handle)
+
+
+class Event(object):
+    """backend_cuda.py:300-308: recorded immediately on creation."""
+
+    def __init__(self, stream=None, timing=False):
+        h = _u64()
+        lib().call('slf_event_create', ctypes.byref(h), int(timing))
+        self.handle = h.value
+        self.record(stream)
+
+    def record(self, stream=None):
+        lib().call('slf_event_record', self.handle, stream.handle if stream is not None else 0)
+
+    def synchronize(self):
+        lib().call('slf_event_sync', self.handle)
+
+    def time_since(self, other):
+        ms = ctypes.c_float()
+        lib().call('slf_event_elapsed_ms', other.handle, self.handle, ctypes.byref(ms))
+        return ms.value
+
+    def time_till(self, other):
+        return other.time_since(self)
+
+
+def _stream_handle(stream):
+    return stream.handle if stream is not None else 0
+
+
+class DeviceBuffer(int):
+    """A device pointer (an int, so it can be passed wherever pycuda passed a
+    DeviceAllocation) that remembers its size."""
+    def __new__(cls, ptr, nbytes):
+        obj = int.__new__(cls, ptr)
+        obj.nbytes = nbytes
+        return obj
+
+
+class Kernel(object):
+    """What get_kernel() returns: a bound C entry point + its translated arguments."""
+
+    def __init__(self, backend, name, args, needs_iteration):
+        self.backend = backend
+        self.name = name
+        self.args = list(args)
+        self.needs_iteration = needs_iteration
+        self.iteration = 0
+
+    def _ptr(self, a):
+        return int(a)
+
+    def launch(self, grid, stream):
+        b, l, plan, s = self.backend, lib(), self.backend._plan, _stream_handle(stream)
+        a = self.args
+        n = self.name
+        dim = b._dim
+        if plan is None:
+            raise B200Error('kernel %s launched before build()' % n)
+        if n == 'CollideAndPropagate':
+            # map, dist_in, dist_out, rho, vx, vy[, vz], options  (lb_single.py:96-151)
+            if dim == 3:
+                m, din, dout, rho, vx, vy, vz, options = a[:8]
+            else:
+                m, din, dout, rho, vx, vy, options = a[:7]
+                vz = 0
+            options = int(options)
+            z0, z1 = b._region_for(options)
+            if z0 == z1:
+                return
+            l.call('slf_collide_and_propagate', plan, int(m), int(din), int(dout), int(rho), int(vx),
+                   int(vy), int(vz), options, self.iteration, z0, z1, s)
+        elif n == 'SetInitialConditions':
+            # dist, ivx, ivy[, ivz], irho, map  (lb_single.py:72-94)
+            if dim == 3:
+                dist, vx, vy, vz, rho, m = a[:6]
+            else:
+                dist, vx, vy, rho, m = a[:5]
+                vz = 0
+            l.call('slf_set_initial_conditions', plan, int(dist), int(vx), int(vy), int(vz), int(rho), int(m), s)
+        elif n == 'PrepareMacroFields':
+            m, dist, rho, options = a[:4]
+            l.call('slf_prepare_macro_fields', plan, int(m), int(dist), int(rho), int(options), self.iteration, s)
+        elif n in ('ApplyPeriodicBoundaryConditions', 'ApplyPeriodicBoundaryConditionsWithSwap'):
+            dist, axis = a[:2]
+            l.call('slf_apply_periodic_boundary_conditions', plan, int(dist), int(axis),
+                   int(n.endswith('WithSwap')), s)
+        elif n in ('CollectContinuousData', 'CollectContinuousDataWithSwap',
+                   'DistributeContinuousData', 'DistributeContinuousDataWithSwap'):
+            swap = int(n.endswith('WithSwap'))
+            fn = 'slf_collect_continuous_data' if n.startswith('Collect') else 'slf_distribute_continuous_data'
+            if dim == 3:
+                dist, face, base_gx, base_other, max_lx, max_other, buf = a[:7]
+                ndists = b._face_ndists()
+                l.call(fn, plan, int(dist), int(face), int(base_gx), int(base_other), int(max_lx),
+                       int(max_other) // ndists, int(buf), swap, s)
+            else:
+                dist, face, base_gx, max_lx, buf = a[:5]
+                ndists = b._face_ndists()
+                l.call(fn, plan, int(dist), int(face), int(base_gx), 0, int(max_lx) // ndists, 1, int(buf), swap, s)
+        elif n in ('CollectSparseData', 'DistributeSparseData'):
+            idx, dist, buf, max_idx = a[:4]
+            fn = 'slf_collect_sparse_data' if n.startswith('Collect') else 'slf_distribute_sparse_data'
+            l.call(fn, plan, int(idx), int(dist), int(buf), int(max_idx), s)
+        else:
+            raise B200Error('kernel %r is outside the B200 hot path (SURVEY.md section 8)' % n)
+
+
+class B200Backend(object):
+    """The reference backend contract (backend_cuda.py), on libslf_b200."""
+    name = 'b200'
+    FatalError = B200Error
+
+    @classmethod
+    def devices_count(cls):
+        n = _i()
+        lib().call('slf_device_count', ctypes.byref(n))
+        return n.value
+
+    @classmethod
+    def add_options(cls, group):
+        return 0
+
+    def __init__(self, options=None, gpu_id=0):
+        self.options = options
+        self.gpu_id = gpu_id
+        self._lib = lib()
+        self._lib.call('slf_init', int(gpu_id))   # raises when there is no device
+        self._plan = None
+        self._params = None
+        self._dim = 3
+        self._buffers = {}          # device ptr -> host ndarray (alloc_buf(like=...))
+        self._iteration_kernels = []
+        self._default_stream = None
+        # connected faces along the outermost axis (set by the runner glue); used to
+        # translate the reference's bulk/boundary launches into slabs
+        self.boundary_layers = 1
+        self.split_enabled = False
+
+    # -- information ---------------------------------------------------------------
+    @property
+    def info(self):
+        name = ctypes.create_string_buffer(128)
+        mem, sms = _u64(), _i()
+        self._lib.call('slf_device_info', name, 128, ctypes.byref(mem), ctypes.byref(sms))
+        return '%s / %d SMs / %d MiB' % (name.value.decode(), sms.value, mem.value >> 20)
+
+    @property
+    def total_memory(self):
+        mem = _u64()
+        self._lib.call('slf_device_info', None, 0, ctypes.byref(mem), None)
+        return mem.value
+
+    @property
+    def supports_printf(self):
+        return False
+
+    def get_defines(self):
+        """backend_cuda.py:310-322: symbols consumed by the templates; kept for the context."""
+        return {'shared_var': '__shared__', 'kernel': '__global__', 'global_ptr': '',
+                'const_ptr': 'const', 'device_func': '__device__', 'const_var': '__constant__',
+                'warp_size': 32, 'supports_shuffle': True, 'backend': 'b200'}
+
+    # -- memory --------------------------------------------------------------------
+    def alloc_buf(self, size=None, like=None, wrap_in_array=False):
+        if like is not None:
+            # backend_cuda.py:132-154: size from the first stride, remember the base array
+            if like.base is not None and isinstance(like.base, np.ndarray) and like.base.size >= like.size:
+                host = like.base
+            else:
+                host = like
+            nbytes = int(like.shape[0] * like.strides[0]) if like.ndim > 0 else int(like.nbytes)
+            nbytes = max(nbytes, int(host.nbytes))
+        else:
+            host = None
+            nbytes = int(size)
+        ptr = _u64()
+        self._lib.call('slf_malloc', nbytes, ctypes.byref(ptr))
+        buf = DeviceBuffer(ptr.value, nbytes)
+        if host is not None:
+            self._buffers[int(buf)] = host
+            self.to_buf(buf)
+        else:
+            self._lib.call('slf_memset', int(buf), 0, nbytes, 0)
+            self._lib.call('slf_sync')
+        return buf
+
+    def alloc_async_host_buf(self, shape, dtype):
+        """Pinned, zero-filled host array (backend_cuda.py:156-159)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape))
+        hp = _vp()
+        self._lib.call('slf_host_alloc', max(n * dtype.itemsize, 4), ctypes.byref(hp))
+        cbuf = (ctypes.c_byte * max(n * dtype.itemsize, 4)).from_address(hp.value)
+        arr = np.frombuffer(cbuf, dtype=dtype, count=n).reshape(shape)
+        return arr
+
+    def _host_of(self, buf, given):
+        if given is not None:
+            return given
+        return self._buffers[int(buf)]
+
+    def to_buf(self, buf, source=None):
+        h = np.ascontiguousarray(self._host_of(buf, source))
+        self._lib.call('slf_memcpy_h2d', int(buf), h.ctypes.data_as(_vp), int(h.nbytes))
+
+    def from_buf(self, buf, target=None):
+        h = self._host_of(buf, target)
+        assert h.flags.c_contiguous
+        self._lib.call('slf_memcpy_d2h', h.ctypes.data_as(_vp), int(buf), int(h.nbytes))
+
+    def to_buf_async(self, buf, stream=None):
+        h = self._buffers[int(buf)]
+        self._lib.call('slf_memcpy_h2d_async', int(buf), h.ctypes.data_as(_vp), int(h.nbytes), _stream_handle(stream))
+
+    def from_buf_async(self, buf, stream=None):
+        h = self._buffers[int(buf)]
+        self._lib.call('slf_memcpy_d2h_async', h.ctypes.data_as(_vp), int(buf), int(h.nbytes), _stream_handle(stream))
+
+    # -- code ----------------------------------------------------------------------
+    def build(self, source):
+        """``source`` is an SlfParams (self-contained host) or the reference's context
+        serialised by sailfish_b200.plugin (a dict)."""
+        if isinstance(source, P.SlfParams):
+            params = source
+        elif isinstance(source, dict):
+            params = P.from_context(source)
+        else:
+            raise B200Error('backend_b200.build() expects the code-generation context, '
+                            'not rendered source text (got %s)' % type(source).__name__)
+        plan = _vp()
+        self._lib.call('slf_plan_create', ctypes.byref(params), ctypes.byref(plan))
+        self._plan = plan
+        self._params = params
+        self._dim = params.dim
+        return plan
+
+    def _face_ndists(self):
+        return {0: 3, 1: 5, 2: 9}[self._params.lattice]
+
+    def _region_for(self, options):
+        """Maps the reference's bulk/boundary launches (options bit 1,
+        kernel_common.mako:130-134) onto slabs.  Without a split the single launch covers
+        the subdomain.  With a split the 'boundary' launch takes everything and the 'bulk'
+        launch nothing: same result, the runner's overlap degenerates (the self-contained
+        runner in this package uses explicit slabs instead)."""
+        if not self.split_enabled:
+            return 0, -1
+        if options & P.OPTION_BULK:
+            return 0, 0
+        return 0, -1
+
+    def get_kernel(self, prog, name, block, args, args_format, shared=0, needs_iteration=False,
+                   more_shared=False):
+        k = Kernel(self, name, args, needs_iteration)
+        if needs_iteration:
+            self._iteration_kernels.append(k)
+        return k
+
+    def set_iteration(self, it):
+        for k in self._iteration_kernels:
+            k.iteration = int(it)
+
+    def run_kernel(self, kernel, grid_size, stream=None):
+        kernel.launch(grid_size, stream)
+
+    def get_reduction_kernel(self, *a, **kw):
+        raise B200Error('reduction kernels (flow statistics) are outside the B200 hot path')
+
+    def get_array(self, buf):
+        raise B200Error('GPUArray views are outside the B200 hot path')
+
+    # -- streams / events ------------------------------------------------------------
+    def sync(self):
+        self._lib.call('slf_sync')
+
+    def make_stream(self, high_priority=False):
+        return Stream(high_priority)
+
+    def make_event(self, stream, timing=False):
+        return Event(stream, timing)
+
+    def sync_stream(self, *streams):
+        for s in streams:
+            s.synchronize()
+
+    def ipc_handle(self, buf):
+        h = ctypes.create_string_buffer(64)
+        self._lib.call('slf_ipc_get_handle', int(buf), h)
+        return h.raw
+
+    def ipc_handle_wrap(self, handle):
+        ptr = _u64()
+        self._lib.call('slf_ipc_open_handle', ctypes.create_string_buffer(handle, 64), ctypes.byref(ptr))
+        return DeviceBuffer(ptr.value, 0)
+
+
+backend = B200Backend

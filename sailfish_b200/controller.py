@@ -1,0 +1,189 @@
+"""``LBSimulationController``: mirror of sailfish/controller.py:272-830 for one box.
+
+Same constructor and ``run()`` contract as the reference (lb_class, lb_geo, default_config;
+command-line flags contributed by every class in ``lb_class.mro()`` and by the geometry
+class).  Process model: one process per GPU.  Launched plainly it drives every subdomain
+from this process (round-robin over the visible GPUs -- the reference's ``gpus[i % n]``
+rule, master.py:106-117); under ``torchrun`` (WORLD_SIZE > 1) rank r owns subdomain r and
+the ranks exchange CUDA-IPC handles once at start-up, after which all halo traffic is
+GPU-to-GPU.  The reference's cluster/PBS/execnet/ZeroMQ control plane is out of scope.
+"""
+import ctypes
+import os
+import sys
+import time
+
+import numpy as np
+
+from sailfish_b200 import backend_b200 as bk
+from sailfish_b200 import config as cfgmod
+from sailfish_b200.geo import LBGeometry2D, LBGeometry3D
+from sailfish_b200.subdomain_runner import HaloLink, SubdomainRunner, LBOutput
+
+_u64 = ctypes.c_uint64
+
+
+class LBSimulationController(object):
+    def __init__(self, lb_class, lb_geo=None, default_config=None):
+        self._lb_class = lb_class
+        self.dim = lb_class.subdomain.dim
+        if lb_geo is None:
+            lb_geo = LBGeometry2D if self.dim == 2 else LBGeometry3D
+        self._lb_geo = lb_geo
+        self._parser = cfgmod.LBConfigParser()
+        g = self._parser.add_group('Runtime mode settings')
+        g.add_argument('--mode', type=str, choices=['batch', 'benchmark'], default='batch')
+        g.add_argument('--every', type=int, default=100, help='save results every N iterations')
+        g.add_argument('--from', dest='from_', type=int, default=0)
+        g.add_argument('--max_iters', type=int, default=0, help='number of iterations to run (0 = run nothing)')
+        g.add_argument('--output', type=str, default='', help='base name of the .npz output files')
+        g.add_argument('--seed', type=int, default=int(time.time()))
+        g.add_argument('--gpus', type=int, nargs='+', default=[0])
+        g.add_argument('--quiet', action='store_true', default=False)
+        g.add_argument('--perf_stats_every', type=int, default=1000)
+        g.add_argument('--debug_single_process', action='store_true', default=True)
+        g.add_argument('--precision', type=str, choices=['single'], default='single')
+        g.add_argument('--mem_alignment', type=int, default=32)
+        g.add_argument('--block_size', type=int, default=64, help='accepted for compatibility; unused')
+        g = self._parser.add_group('Simulation-specific settings')
+        for base in lb_class.mro():
+            if 'add_options' in base.__dict__:
+                base.add_options(g, self.dim)
+        g = self._parser.add_group('Geometry settings')
+        lb_geo.add_options(g)
+        defaults = {}
+        lb_class.update_defaults(defaults)
+        self._parser.set_defaults(defaults)
+        if default_config is not None:
+            self._parser.set_defaults(default_config)
+        self.runners = []
+
+    # -- set-up --------------------------------------------------------------------------------
+    def _make_specs(self):
+        cfg = self.config
+        self.geo = self._lb_geo(cfg)
+        specs = self.geo.subdomains()
+        axis = self.dim - 1
+        per = [bool(getattr(cfg, 'periodic_' + a, False)) for a in 'xyz'[:self.dim]]
+        n = len(specs)
+        for s in specs:
+            for a in range(self.dim):
+                if per[a] and (a != axis or n == 1):
+                    s.enable_local_periodicity(a)     # controller.py:155-269 (local periodicity)
+        lo_face, hi_face = 2 * axis, 2 * axis + 1
+        for i, s in enumerate(specs):
+            if i + 1 < n:
+                s.connect(hi_face, i + 1)
+                specs[i + 1].connect(lo_face, i)
+        if n > 1 and per[axis]:
+            specs[-1].connect(hi_face, 0)
+            specs[0].connect(lo_face, n - 1)
+        return specs
+
+    def _distributed(self):
+        ws = int(os.environ.get('WORLD_SIZE', '1'))
+        return ws > 1, int(os.environ.get('RANK', '0')), ws, int(os.environ.get('LOCAL_RANK', '0'))
+
+    def setup(self, args=None):
+        self.config = self._parser.parse(list(args or []))
+        self._lb_class.modify_config(self.config)
+        np.random.seed(self.config.seed)
+        specs = self._make_specs()
+        self.specs = specs
+        dist_mode, rank, ws, local_rank = self._distributed()
+        if dist_mode:
+            if len(specs) != ws:
+                raise ValueError('torchrun world size %d != --subdomains %d' % (ws, len(specs)))
+            mine = [specs[rank]]
+            devices = {specs[rank].id: local_rank}
+        else:
+            mine = specs
+            ngpu = max(1, bk.B200Backend.devices_count())
+            gpus = [g for g in self.config.gpus if g < ngpu] or [0]
+            devices = dict((s.id, gpus[i % len(gpus)]) for i, s in enumerate(specs))
+        if len(set(devices.values())) > 1:
+            raise NotImplementedError('one process drives one GPU; use torchrun for multi-GPU runs')
+        self.runners = []
+        for s in mine:
+            sim = self._lb_class(self.config)
+            r = SubdomainRunner(sim, s, output=LBOutput(self.config, s.id), device=devices[s.id])
+            r.initialize()
+            self.runners.append(r)
+        self._link(dist_mode, rank, ws)
+        return self
+
+    def _link(self, dist_mode, rank, ws):
+        """Exchanges lattice/semaphore addresses between neighbours: plain pointers inside one
+        process, CUDA IPC handles (backend_cuda.py:122-126 wraps them, never uses them) across
+        ranks."""
+        axis = self.dim - 1
+        infos = {}
+        for r in self.runners:
+            d = r._dev
+            infos[r._spec.id] = dict(dist_a=int(d.d_dist_a), dist_b=int(d.d_dist_b) if d.d_dist_b else 0,
+                                     lat_n=r._lat_size[0], arr_n=r._physical_size[0], sems=int(r._sems))
+        remote = {}
+        if dist_mode:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                dist.init_process_group('gloo')
+            mine = self.runners[0]
+            be = mine.backend
+            payload = dict(id=mine._spec.id, lat_n=mine._lat_size[0], arr_n=mine._physical_size[0],
+                           dist_a=be.ipc_handle(mine._dev.d_dist_a),
+                           dist_b=be.ipc_handle(mine._dev.d_dist_b) if mine._dev.d_dist_b else None,
+                           sems=be.ipc_handle(mine._sems))
+            gathered = [None] * ws
+            dist.all_gather_object(gathered, payload)
+            needed = set(mine._spec._face_conn.values())
+            for g in gathered:
+                if g['id'] in needed and g['id'] != mine._spec.id:
+                    remote[g['id']] = dict(
+                        dist_a=int(be.ipc_handle_wrap(g['dist_a'])),
+                        dist_b=int(be.ipc_handle_wrap(g['dist_b'])) if g['dist_b'] else 0,
+                        lat_n=g['lat_n'], arr_n=g['arr_n'], sems=int(be.ipc_handle_wrap(g['sems'])))
+            self._dist = dist
+        for r in self.runners:
+            for face, other in r._spec._face_conn.items():
+                if face // 2 != axis:
+                    continue
+                info = infos.get(other) or remote[other]
+                side = face & 1
+                # the neighbour receives through its opposite side: signal that semaphore
+                peer_ready = info['sems'] + 4 * (1 - side)
+                sp = r.sem_ptrs()
+                r.add_link(HaloLink(face, info['dist_a'], info['dist_b'], info['lat_n'], info['arr_n'],
+                                    peer_ready, sp['ready'][side], sp['consumed'][side]))
+
+    # -- running -------------------------------------------------------------------------------
+    def barrier(self):
+        if getattr(self, '_dist', None) is not None:
+            self._dist.barrier()
+
+    def run_steps(self, n):
+        for _ in range(n):
+            for r in self.runners:
+                r.step(False)
+
+    def sync(self):
+        for r in self.runners:
+            r.sync()
+
+    def run(self, ignore_cmdline=False):
+        self.setup([] if ignore_cmdline else sys.argv[1:])
+        cfg = self.config
+        if cfg.max_iters <= 0:
+            return self
+        t0 = time.time()
+        done = False
+        while not done:
+            flags = [r.main_step() for r in self.runners]
+            done = all(flags)
+        self.sync()
+        self.barrier()
+        dt = time.time() - t0
+        if not cfg.quiet:
+            nodes = sum(r.num_fluid_nodes for r in self.runners)
+            print('Simulation completed after %d iterations: %.2f MLUPS (local subdomains)'
+                  % (cfg.max_iters, nodes * cfg.max_iters / dt * 1e-6))
+        return self

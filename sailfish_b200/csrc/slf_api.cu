@@ -1,0 +1,439 @@
+// slf_api.cu -- C ABI of libslf_b200.so (see include/slf_b200.h for the contract and the
+// reference interface each entry point replaces).
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "slf_kernels.cuh"
+
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+static int g_device = -1;
+
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_OK(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail((int)e_, std::string(#expr) + ": " + cudaGetErrorString(e_));              \
+  } while (0)
+#define LAUNCH_OK(name)                                                                       \
+  do {                                                                                        \
+    cudaError_t e_ = cudaGetLastError();                                                      \
+    if (e_ != cudaSuccess) return fail((int)e_, std::string(name) + ": " + cudaGetErrorString(e_)); \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                       \
+  } while (0)
+
+struct SlfPlan {
+  SlfParams hp;
+  DevParams dp;
+  float *d_node_params = nullptr;
+  int Q = 0, D = 0;
+};
+
+extern "C" {
+
+int slf_abi_version(void) { return SLF_ABI_VERSION; }
+const char *slf_last_error(void) { return g_err.c_str(); }
+uint64_t slf_launch_count(void) { return g_launches.load(); }
+
+int slf_device_count(int *count) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { *count = 0; return fail(SLF_ENODEVICE, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); }
+  *count = n;
+  return 0;
+}
+
+int slf_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(SLF_ENODEVICE, "no CUDA device available; libslf_b200 has no CPU fallback");
+  if (device < 0 || device >= n) return fail(SLF_EINVAL, "device index out of range");
+  CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(SLF_EUNSUPPORTED, "libslf_b200 is built for sm_100a (B200) only");
+  CUDA_OK(cudaFree(0));
+  g_device = device;
+  return 0;
+}
+
+int slf_device_info(char *name, int name_len, uint64_t *total_mem, int *sm_count) {
+  cudaDeviceProp prop;
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  if (name && name_len > 0) { strncpy(name, prop.name, name_len - 1); name[name_len - 1] = 0; }
+  if (total_mem) *total_mem = prop.totalGlobalMem;
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  return 0;
+}
+
+int slf_malloc(uint64_t bytes, uint64_t *dptr) {
+  void *p = nullptr;
+  CUDA_OK(cudaMalloc(&p, bytes ? bytes : 4));
+  *dptr = (uint64_t)p;
+  return 0;
+}
+int slf_free(uint64_t dptr) { CUDA_OK(cudaFree((void *)dptr)); return 0; }
+int slf_memset(uint64_t dptr, int value, uint64_t bytes, uint64_t stream) {
+  CUDA_OK(cudaMemsetAsync((void *)dptr, value, bytes, (cudaStream_t)stream));
+  return 0;
+}
+int slf_host_alloc(uint64_t bytes, void **hptr) {
+  CUDA_OK(cudaHostAlloc(hptr, bytes ? bytes : 4, cudaHostAllocDefault));
+  memset(*hptr, 0, bytes);
+  return 0;
+}
+int slf_host_free(void *hptr) { CUDA_OK(cudaFreeHost(hptr)); return 0; }
+int slf_memcpy_h2d(uint64_t dptr, const void *hptr, uint64_t bytes) {
+  CUDA_OK(cudaMemcpy((void *)dptr, hptr, bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+int slf_memcpy_d2h(void *hptr, uint64_t dptr, uint64_t bytes) {
+  CUDA_OK(cudaMemcpy(hptr, (const void *)dptr, bytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int slf_memcpy_h2d_async(uint64_t dptr, const void *hptr, uint64_t bytes, uint64_t stream) {
+  CUDA_OK(cudaMemcpyAsync((void *)dptr, hptr, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return 0;
+}
+int slf_memcpy_d2h_async(void *hptr, uint64_t dptr, uint64_t bytes, uint64_t stream) {
+  CUDA_OK(cudaMemcpyAsync(hptr, (const void *)dptr, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return 0;
+}
+int slf_memcpy_d2d_async(uint64_t dst, uint64_t src, uint64_t bytes, uint64_t stream) {
+  CUDA_OK(cudaMemcpyAsync((void *)dst, (const void *)src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+int slf_sync(void) { CUDA_OK(cudaDeviceSynchronize()); return 0; }
+int slf_stream_create(uint64_t *stream, int high_priority) {
+  cudaStream_t s;
+  int lo = 0, hi = 0;
+  CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  CUDA_OK(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high_priority ? hi : lo));
+  *stream = (uint64_t)s;
+  return 0;
+}
+int slf_stream_destroy(uint64_t stream) { CUDA_OK(cudaStreamDestroy((cudaStream_t)stream)); return 0; }
+int slf_stream_sync(uint64_t stream) { CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream)); return 0; }
+int slf_stream_wait_event(uint64_t stream, uint64_t event) {
+  CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0));
+  return 0;
+}
+int slf_event_create(uint64_t *event, int timing) {
+  cudaEvent_t e;
+  CUDA_OK(cudaEventCreateWithFlags(&e, timing ? cudaEventDefault : cudaEventDisableTiming));
+  *event = (uint64_t)e;
+  return 0;
+}
+int slf_event_destroy(uint64_t event) { CUDA_OK(cudaEventDestroy((cudaEvent_t)event)); return 0; }
+int slf_event_record(uint64_t event, uint64_t stream) {
+  CUDA_OK(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream));
+  return 0;
+}
+int slf_event_sync(uint64_t event) { CUDA_OK(cudaEventSynchronize((cudaEvent_t)event)); return 0; }
+int slf_event_elapsed_ms(uint64_t start, uint64_t end, float *ms) {
+  CUDA_OK(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)end));
+  return 0;
+}
+
+// ---- plan ------------------------------------------------------------------------------
+int slf_plan_create(const SlfParams *p, SlfPlan **out) {
+  if (!p || !out) return fail(SLF_EINVAL, "null argument");
+  if (p->struct_bytes != sizeof(SlfParams))
+    return fail(SLF_EINVAL, "SlfParams size mismatch (ABI): got " + std::to_string(p->struct_bytes) +
+                                ", expected " + std::to_string(sizeof(SlfParams)));
+  if (p->lattice < SLF_D2Q9 || p->lattice > SLF_D3Q27) return fail(SLF_EINVAL, "unknown lattice");
+  if (p->model != SLF_BGK && p->model != SLF_MRT) return fail(SLF_EINVAL, "unknown model");
+  if (p->model == SLF_MRT && p->lattice == SLF_D3Q27)
+    return fail(SLF_EUNSUPPORTED, "D3Q27 has no MRT basis in the reference (sym.py:409-428)");
+  if (p->access_pattern != SLF_AB && p->access_pattern != SLF_AA) return fail(SLF_EINVAL, "unknown access pattern");
+  if (p->lat_nx < 3 || p->lat_ny < 3 || p->arr_nx < p->lat_nx || p->arr_ny < p->lat_ny)
+    return fail(SLF_EINVAL, "bad lattice/array size");
+  if (p->bits_type < 1 || p->bits_type + p->bits_param + p->bits_scratch > 31)
+    return fail(SLF_EINVAL, "bad node-code bit layout");
+  if (p->type_id[SLF_NT_FLUID] == SLF_NT_ABSENT) return fail(SLF_EINVAL, "fluid type id missing");
+  if (!(p->visc > 0.0)) return fail(SLF_EINVAL, "viscosity must be positive");
+  SlfPlan *pl = new SlfPlan();
+  pl->hp = *p;
+  pl->hp.node_params = nullptr;
+  const int D = p->lattice == SLF_D2Q9 ? 2 : 3;
+  pl->D = D;
+  pl->Q = p->lattice == SLF_D2Q9 ? 9 : (p->lattice == SLF_D3Q19 ? 19 : 27);
+  DevParams &d = pl->dp;
+  memset(&d, 0, sizeof(d));
+  d.nx = p->lat_nx; d.ny = p->lat_ny; d.nz = D == 3 ? p->lat_nz : 1;
+  d.ax = p->arr_nx; d.ay = p->arr_ny; d.az = D == 3 ? p->arr_nz : 1;
+  if (D == 3 && (d.nz < 3 || d.az < d.nz)) { delete pl; return fail(SLF_EINVAL, "bad z size"); }
+  d.DS = (long long)d.ax * d.ay * d.az;
+  d.sy = d.ax; d.sz = (long long)d.ax * d.ay;
+  d.tmask = (1u << p->bits_type) - 1u;
+  d.pmask = (1u << p->bits_param) - 1u;
+  d.pshift = p->bits_type;
+  d.oshift = p->bits_type + p->bits_param + p->bits_scratch;
+  for (int k = 0; k < SLF_NT_COUNT; k++) d.tid[k] = p->type_id[k];
+  const double tau = (6.0 * p->visc + 1.0) / 2.0;            // sym.py:847-848
+  d.tau = (float)tau;
+  d.omega = (float)(1.0 / tau);
+  const float viscf = (float)p->visc;
+  d.inv_tau_mrt = 1.0f / (0.5f + 3.0f * viscf);
+  d.guo_pref = 3.0f * (1.0f - 1.0f / (2.0f * d.tau));
+  d.forced = p->force_enabled ? 1 : 0;
+  for (int k = 0; k < 3; k++) d.a[k] = p->force_enabled ? (float)p->accel[k] : 0.f;
+  d.relax = p->relaxation_enabled; d.prop = p->propagation_enabled; d.use_tags = p->use_link_tags;
+  const int np = p->num_node_params > 0 ? p->num_node_params : 0;
+  std::vector<float> h(np + 4, 0.f);
+  for (int k = 0; k < np; k++) h[k] = (float)p->node_params[k];
+  cudaError_t e = cudaMalloc((void **)&pl->d_node_params, h.size() * sizeof(float));
+  if (e != cudaSuccess) { delete pl; return fail((int)e, std::string("cudaMalloc(node_params): ") + cudaGetErrorString(e)); }
+  e = cudaMemcpy(pl->d_node_params, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(pl->d_node_params); delete pl; return fail((int)e, cudaGetErrorString(e)); }
+  d.node_params = pl->d_node_params;
+  *out = pl;
+  return 0;
+}
+
+int slf_plan_destroy(SlfPlan *plan) {
+  if (!plan) return 0;
+  if (plan->d_node_params) cudaFree(plan->d_node_params);
+  delete plan;
+  return 0;
+}
+
+}  // extern "C"
+
+// ---- dispatch helpers --------------------------------------------------------------------
+template <class L, int MODEL, int MODE, bool SAVE>
+static int launch_collide(SlfPlan *pl, const uint32_t *map, const float *din, float *dout, float *rho,
+                          float *vx, float *vy, float *vz, long long gi0, long long gi1, cudaStream_t s) {
+  const long long n = gi1 - gi0;
+  if (n <= 0) return 0;
+  {
+    const int bs = 256;
+    const long long nb = (n + bs - 1) / bs;
+    collide_bulk<L, MODEL, MODE, SAVE><<<(unsigned)nb, bs, 0, s>>>(pl->dp, map, din, dout, rho, vx, vy, vz, gi0, gi1);
+    LAUNCH_OK("collide_bulk");
+  }
+  {
+    const int bs = 128;
+    const long long nb = (n + bs - 1) / bs;
+    collide_boundary<L, MODEL, MODE, SAVE><<<(unsigned)nb, bs, 0, s>>>(pl->dp, map, din, dout, rho, vx, vy, vz, gi0, gi1);
+    LAUNCH_OK("collide_boundary");
+  }
+  return 0;
+}
+
+template <class L, int MODEL>
+static int dispatch_mode(SlfPlan *pl, int mode, bool save, const uint32_t *map, const float *din, float *dout,
+                         float *rho, float *vx, float *vy, float *vz, long long gi0, long long gi1,
+                         cudaStream_t s) {
+#define SLF_CASE(M)                                                                                     \
+  case M:                                                                                               \
+    return save ? launch_collide<L, MODEL, M, true>(pl, map, din, dout, rho, vx, vy, vz, gi0, gi1, s)   \
+                : launch_collide<L, MODEL, M, false>(pl, map, din, dout, rho, vx, vy, vz, gi0, gi1, s);
+  switch (mode) {
+    SLF_CASE(MODE_AB)
+    SLF_CASE(MODE_AA_EVEN)
+    SLF_CASE(MODE_AA_ODD)
+  }
+#undef SLF_CASE
+  return fail(SLF_EINVAL, "bad mode");
+}
+
+extern "C" {
+
+int slf_collide_and_propagate(SlfPlan *pl, uint64_t map, uint64_t dist_in, uint64_t dist_out, uint64_t rho,
+                              uint64_t vx, uint64_t vy, uint64_t vz, int options, uint32_t iteration,
+                              int z_begin, int z_end, uint64_t stream) {
+  if (!pl) return fail(SLF_EINVAL, "null plan");
+  const DevParams &d = pl->dp;
+  const int outer = pl->D == 3 ? d.nz : d.ny;
+  if (z_end < 0) z_end = outer;
+  if (z_begin < 0 || z_end > outer || z_begin > z_end) return fail(SLF_EINVAL, "bad slab range");
+  const long long slab = pl->D == 3 ? d.sz : d.sy;
+  const long long gi0 = slab * z_begin, gi1 = slab * z_end;
+  int mode;
+  if (pl->hp.access_pattern == SLF_AB) {
+    mode = MODE_AB;
+    if (dist_in == dist_out) return fail(SLF_EINVAL, "AB access pattern needs two distinct lattices");
+  } else {
+    mode = (iteration & 1) ? MODE_AA_ODD : MODE_AA_EVEN;
+    if (dist_in != dist_out) return fail(SLF_EINVAL, "AA access pattern works in place (dist_in == dist_out)");
+  }
+  const bool save = (options & SLF_OPTION_SAVE_MACRO_FIELDS) != 0;
+  if (save && (!rho || !vx || !vy || (pl->D == 3 && !vz))) return fail(SLF_EINVAL, "macro fields requested but null");
+  const uint32_t *m = (const uint32_t *)map;
+  const float *din = (const float *)dist_in;
+  float *dout = (float *)dist_out, *r = (float *)rho, *x = (float *)vx, *y = (float *)vy, *z = (float *)vz;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int model = pl->hp.model;
+  switch (pl->hp.lattice) {
+    case SLF_D2Q9:
+      return model == SLF_MRT ? dispatch_mode<D2Q9, SLF_MRT>(pl, mode, save, m, din, dout, r, x, y, z, gi0, gi1, s)
+                              : dispatch_mode<D2Q9, SLF_BGK>(pl, mode, save, m, din, dout, r, x, y, z, gi0, gi1, s);
+    case SLF_D3Q19:
+      return model == SLF_MRT ? dispatch_mode<D3Q19, SLF_MRT>(pl, mode, save, m, din, dout, r, x, y, z, gi0, gi1, s)
+                              : dispatch_mode<D3Q19, SLF_BGK>(pl, mode, save, m, din, dout, r, x, y, z, gi0, gi1, s);
+    case SLF_D3Q27:
+      return dispatch_mode<D3Q27, SLF_BGK>(pl, mode, save, m, din, dout, r, x, y, z, gi0, gi1, s);
+  }
+  return fail(SLF_EINVAL, "bad lattice");
+}
+
+#define SLF_LATTICE_SWITCH(pl, CALL)            \
+  switch ((pl)->hp.lattice) {                    \
+    case SLF_D2Q9: { using L = D2Q9; CALL; } break;   \
+    case SLF_D3Q19: { using L = D3Q19; CALL; } break; \
+    case SLF_D3Q27: { using L = D3Q27; CALL; } break; \
+  }
+
+int slf_set_initial_conditions(SlfPlan *pl, uint64_t dist, uint64_t vx, uint64_t vy, uint64_t vz, uint64_t rho,
+                               uint64_t map, uint64_t stream) {
+  (void)map;
+  if (!pl) return fail(SLF_EINVAL, "null plan");
+  const int bs = 256;
+  const unsigned nb = (unsigned)((pl->dp.DS + bs - 1) / bs);
+  cudaStream_t s = (cudaStream_t)stream;
+  SLF_LATTICE_SWITCH(pl, (set_initial_conditions<L><<<nb, bs, 0, s>>>(pl->dp, (float *)dist, (const float *)vx,
+                                                                      (const float *)vy, (const float *)vz,
+                                                                      (const float *)rho)));
+  LAUNCH_OK("set_initial_conditions");
+  return 0;
+}
+
+int slf_prepare_macro_fields(SlfPlan *pl, uint64_t map, uint64_t dist, uint64_t rho, int options,
+                             uint32_t iteration, uint64_t stream) {
+  (void)options;
+  if (!pl) return fail(SLF_EINVAL, "null plan");
+  const int bs = 256;
+  const unsigned nb = (unsigned)((pl->dp.DS + bs - 1) / bs);
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool odd = pl->hp.access_pattern == SLF_AA && (iteration & 1);
+  if (odd) {
+    SLF_LATTICE_SWITCH(pl, (prepare_macro_fields<L, MODE_AA_ODD><<<nb, bs, 0, s>>>(
+                               pl->dp, (const uint32_t *)map, (const float *)dist, (float *)rho)));
+  } else {
+    SLF_LATTICE_SWITCH(pl, (prepare_macro_fields<L, MODE_AB><<<nb, bs, 0, s>>>(
+                               pl->dp, (const uint32_t *)map, (const float *)dist, (float *)rho)));
+  }
+  LAUNCH_OK("prepare_macro_fields");
+  return 0;
+}
+
+int slf_apply_periodic_boundary_conditions(SlfPlan *pl, uint64_t dist, int axis, int with_swap, uint64_t stream) {
+  if (!pl) return fail(SLF_EINVAL, "null plan");
+  if (axis == 2 && pl->D == 2) return 0;   // the reference prepares a z kernel in 2-D and never runs it
+  if (axis < 0 || axis >= pl->D) return fail(SLF_EINVAL, "bad axis");
+  const DevParams &d = pl->dp;
+  const int lim[3] = {d.nx, d.ny, d.nz};
+  int o0, o1;
+  if (pl->D == 2) { o0 = 1 - axis; o1 = 2; } else { o0 = axis == 0 ? 1 : 0; o1 = axis == 2 ? 1 : 2; }
+  const int n1 = lim[o0], n2 = pl->D == 3 ? lim[o1] : 1;
+  dim3 grid((n1 + 127) / 128, n2);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int *per = pl->hp.periodic;
+  if (with_swap) {
+    SLF_LATTICE_SWITCH(pl, (apply_pbc<L, true><<<grid, 128, 0, s>>>(d, (float *)dist, axis, per[0], per[1], per[2])));
+  } else {
+    SLF_LATTICE_SWITCH(pl, (apply_pbc<L, false><<<grid, 128, 0, s>>>(d, (float *)dist, axis, per[0], per[1], per[2])));
+  }
+  LAUNCH_OK("apply_pbc");
+  return 0;
+}
+
+static int face_ndists(const SlfPlan *pl, int face) {
+  // |{i: e_i . n >= 1}|
+  if (pl->hp.lattice == SLF_D2Q9) return 3;
+  if (pl->hp.lattice == SLF_D3Q19) return 5;
+  (void)face;
+  return 9;
+}
+
+static int xfer(SlfPlan *pl, uint64_t dist, int face, int base_gx, int base_other, int max_lx, int max_other,
+                uint64_t buffer, int with_swap, bool distribute, uint64_t stream) {
+  if (!pl) return fail(SLF_EINVAL, "null plan");
+  if (face < 2 || face >= 2 * pl->D) return fail(SLF_EINVAL, "continuous transfers are for y/z faces");
+  if (pl->D == 2) max_other = 1;
+  if (max_lx <= 0 || max_other <= 0) return 0;
+  dim3 grid((max_lx + 127) / 128, max_other, face_ndists(pl, face));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (distribute) {
+    SLF_LATTICE_SWITCH(pl, (xfer_continuous<L, true><<<grid, 128, 0, s>>>(pl->dp, (float *)dist, face, base_gx, base_other,
+                                                                       max_lx, max_other, (float *)buffer, with_swap)));
+  } else {
+    SLF_LATTICE_SWITCH(pl, (xfer_continuous<L, false><<<grid, 128, 0, s>>>(pl->dp, (float *)dist, face, base_gx, base_other,
+                                                                        max_lx, max_other, (float *)buffer, with_swap)));
+  }
+  LAUNCH_OK("xfer_continuous");
+  return 0;
+}
+
+int slf_collect_continuous_data(SlfPlan *pl, uint64_t dist, int face, int base_gx, int base_other, int max_lx,
+                                int max_other, uint64_t buffer, int with_swap, uint64_t stream) {
+  return xfer(pl, dist, face, base_gx, base_other, max_lx, max_other, buffer, with_swap, false, stream);
+}
+int slf_distribute_continuous_data(SlfPlan *pl, uint64_t dist, int face, int base_gx, int base_other, int max_lx,
+                                   int max_other, uint64_t buffer, int with_swap, uint64_t stream) {
+  return xfer(pl, dist, face, base_gx, base_other, max_lx, max_other, buffer, with_swap, true, stream);
+}
+
+int slf_collect_sparse_data(SlfPlan *pl, uint64_t idx_array, uint64_t dist, uint64_t buffer, int max_idx,
+                            uint64_t stream) {
+  if (!pl) return fail(SLF_EINVAL, "null plan");
+  if (max_idx <= 0) return 0;
+  xfer_sparse<false><<<(max_idx + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      (const uint32_t *)idx_array, (float *)dist, (float *)buffer, max_idx,
+      (unsigned long long)pl->dp.DS * pl->Q);
+  LAUNCH_OK("collect_sparse");
+  return 0;
+}
+int slf_distribute_sparse_data(SlfPlan *pl, uint64_t idx_array, uint64_t dist, uint64_t buffer, int max_idx,
+                               uint64_t stream) {
+  if (!pl) return fail(SLF_EINVAL, "null plan");
+  if (max_idx <= 0) return 0;
+  xfer_sparse<true><<<(max_idx + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      (const uint32_t *)idx_array, (float *)dist, (float *)buffer, max_idx,
+      (unsigned long long)pl->dp.DS * pl->Q);
+  LAUNCH_OK("distribute_sparse");
+  return 0;
+}
+
+// ---- peer access ---------------------------------------------------------------------------
+int slf_ipc_get_handle(uint64_t dptr, void *handle64) {
+  cudaIpcMemHandle_t h;
+  CUDA_OK(cudaIpcGetMemHandle(&h, (void *)dptr));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+int slf_ipc_open_handle(const void *handle64, uint64_t *dptr) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void *p = nullptr;
+  CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *dptr = (uint64_t)p;
+  return 0;
+}
+int slf_ipc_close_handle(uint64_t dptr) { CUDA_OK(cudaIpcCloseMemHandle((void *)dptr)); return 0; }
+int slf_enable_peer_access(int peer_device) {
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+  CUDA_OK(e);
+  return 0;
+}
+
+}  // extern "C"
+
+#include "slf_halo.cuh"

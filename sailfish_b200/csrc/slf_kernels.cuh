@@ -1,0 +1,485 @@
+// slf_kernels.cuh -- the kernels behind the reference's kernel names.
+//
+//   collide_bulk     : CollideAndPropagate for plain fluid nodes (the 97+% case).  No
+//                      branches on node type beyond "is it fluid"; this is the kernel the
+//                      roofline is quoted on.
+//   collide_boundary : CollideAndPropagate for every other active node (walls, velocity /
+//                      density / do-nothing nodes).  Same arithmetic as the reference's
+//                      generic path, orientation handled with run-time normals.
+//   The two kernels touch disjoint memory (each node owns the Q addresses it reads and
+//   writes in the AA pattern; in AB the target slots of different nodes never coincide),
+//   so they may run in either order or concurrently.
+#pragma once
+#include "slf_device.cuh"
+
+template <class L>
+__device__ __forceinline__ int node_class(const DevParams &P, uint32_t type) {
+#pragma unroll
+  for (int k = 0; k < SLF_NT_COUNT; k++)
+    if (P.tid[k] == type) return k;
+  return -1;
+}
+
+// ----------------------------------------------------------------------------------------
+// Bulk kernel.  gi range [gi0, gi1) is a contiguous run of nodes (whole z-slabs).
+// ----------------------------------------------------------------------------------------
+template <class L, int MODEL, int MODE, bool SAVE>
+__global__ void __launch_bounds__(256)
+collide_bulk(const DevParams P, const uint32_t *__restrict__ map, const float *din, float *dout,
+             float *__restrict__ orho, float *__restrict__ ovx, float *__restrict__ ovy,
+             float *__restrict__ ovz, long long gi0, long long gi1) {
+  const long long gi = gi0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= gi1) return;
+  const uint32_t code = map[gi];
+  if ((code & P.tmask) != P.tid[SLF_NT_FLUID]) return;
+
+  float f[L::Q];
+  load_node<L, MODE>(P, din, gi, f);
+
+  float rho, v[3];
+  moments<L>(f, rho, v);
+  const float inv = 1.0f / rho;
+  v[0] *= inv; v[1] *= inv; v[2] *= inv;
+
+  if (P.relax) {
+    if (MODEL == SLF_MRT) collide_mrt<L, false>(P, v, f);
+    else collide_bgk<L>(P, rho, v, f);
+  }
+  if (SAVE) {
+    orho[gi] = rho; ovx[gi] = v[0]; ovy[gi] = v[1];
+    if (L::D == 3) ovz[gi] = v[2];
+  }
+  if (!P.prop) {
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) dout[gi + P.DS * i] = f[i];
+  } else if (MODE == MODE_AA_EVEN) {
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) dout[gi + P.DS * L::opp(i)] = f[i];
+  } else {
+    // A fluid node is never on the outermost layer (that layer is always ghost,
+    // subdomain.py:952-977), so every target is inside the array: the bounds tests of
+    // propagation.mako:36-41 are vacuous here and live in the boundary kernel only.
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) dout[gi + noff<L>(P, i) + P.DS * i] = f[i];
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// Boundary kernel: all active non-fluid nodes.
+// ----------------------------------------------------------------------------------------
+template <class L>
+__device__ __forceinline__ int edotn(int i, int n0, int n1, int n2) {
+  return L::ex(i) * n0 + L::ey(i) * n1 + L::ez(i) * n2;
+}
+
+template <class L, int MODEL, int MODE, bool SAVE>
+__global__ void __launch_bounds__(128)
+collide_boundary(const DevParams P, const uint32_t *__restrict__ map, const float *din, float *dout,
+                 float *__restrict__ orho, float *__restrict__ ovx, float *__restrict__ ovy,
+                 float *__restrict__ ovz, long long gi0, long long gi1) {
+  const long long gi = gi0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= gi1) return;
+  const uint32_t code = map[gi];
+  const uint32_t type = code & P.tmask;
+  if (type == P.tid[SLF_NT_FLUID]) return;
+  const int cls = node_class<L>(P, type);
+  if (cls < 0 || cls == SLF_NT_GHOST || cls == SLF_NT_UNUSED || cls == SLF_NT_PROPAGATION_ONLY) return;
+  const int x = (int)(gi % P.ax);
+  const long long t = gi / P.ax;
+  const int y = (int)(t % P.ay), z = (int)(t / P.ay);
+  if (x >= P.nx) return;
+  const int orient = (int)(code >> P.oshift);
+  constexpr bool ODD = MODE == MODE_AA_ODD;
+  constexpr bool AA = MODE != MODE_AB;
+
+  float f[L::Q];
+  load_node<L, MODE>(P, din, gi, f);
+
+  // inward normal of the node (primary orientation); zero when unknown
+  int n0 = 0, n1 = 0, n2 = 0;
+  const bool tagged = (cls == SLF_NT_HALFBB_WALL) && P.use_tags;
+  if (orient > 0 && orient <= 2 * L::D && !tagged) {
+#pragma unroll
+    for (int d = 1; d <= 2 * L::D; d++)
+      if (orient == d) { n0 = L::ex(L::dir2vec(d)); n1 = L::ey(L::dir2vec(d)); n2 = L::ez(L::dir2vec(d)); }
+  }
+  const bool vel_bc = cls == SLF_NT_EQUILIBRIUM_VELOCITY || cls == SLF_NT_REGULARIZED_VELOCITY;
+  const bool den_bc = cls == SLF_NT_EQUILIBRIUM_DENSITY || cls == SLF_NT_REGULARIZED_DENSITY;
+  const bool standard = !(vel_bc || den_bc);
+
+  float rho, v[3];
+  if (standard || orient == 0) {
+    moments<L>(f, rho, v);
+    v[0] /= rho; v[1] /= rho; v[2] /= rho;
+  } else {
+    const int pidx = (int)((code >> P.pshift) & P.pmask);
+#pragma unroll
+    for (int i = 0; i < L::Q; i++)            // fill missing with opposite, boundary.mako:418-422
+      if (edotn<L>(i, n0, n1, n2) > 0) f[i] = f[L::opp(i)];
+    float j[3];
+    moments<L>(f, rho, j);
+    if (vel_bc) {
+      v[0] = P.node_params[pidx]; v[1] = P.node_params[pidx + 1];
+      v[2] = L::D == 3 ? P.node_params[pidx + 2] : 0.f;
+      const float nv = (float)n0 * v[0] + (float)n1 * v[1] + (float)n2 * v[2];
+      rho = rho / (1.0f - nv);                // sym.py:627
+    } else {
+      const float par_rho = P.node_params[pidx];
+      const float s = (rho - par_rho) / par_rho;   // sym.py:666-680
+      v[0] = (float)(-n0) * s; v[1] = (float)(-n1) * s; v[2] = (float)(-n2) * s;
+      rho = par_rho;
+    }
+  }
+
+  // pre-collision boundary conditions
+  if (cls == SLF_NT_FULLBB_WALL) {
+#pragma unroll
+    for (int i = 0; i < L::Q; i++)
+      if (i < L::opp(i)) { const float tmp = f[i]; f[i] = f[L::opp(i)]; f[L::opp(i)] = tmp; }
+  } else if (cls == SLF_NT_EQUILIBRIUM_VELOCITY || cls == SLF_NT_EQUILIBRIUM_DENSITY) {
+    equilibrium<L>(rho, v, f);
+  } else if (cls == SLF_NT_REGULARIZED_VELOCITY || cls == SLF_NT_REGULARIZED_DENSITY) {
+    if (orient == 0) {
+#pragma unroll
+      for (int i = 0; i < L::Q; i++)
+        if (i < L::opp(i)) { const float tmp = f[i]; f[i] = f[L::opp(i)]; f[L::opp(i)] = tmp; }
+    } else {
+      float feq[L::Q];
+      equilibrium<L>(rho, v, feq);
+#pragma unroll
+      for (int i = 0; i < L::Q; i++)          // non-equilibrium bounce-back, sym.py:750-766
+        if (edotn<L>(i, n0, n1, n2) > 0) f[i] = f[L::opp(i)] - feq[L::opp(i)] + feq[i];
+      // Pi^neq = sum e e f - (rho v v + rho cs^2 I), boundary.mako:298-304
+      float pxx = 0.f, pyy = 0.f, pzz = 0.f, pxy = 0.f, pxz = 0.f, pyz = 0.f;
+#pragma unroll
+      for (int i = 0; i < L::Q; i++) {
+        if (L::ex(i) * L::ex(i)) pxx += f[i];
+        if (L::ey(i) * L::ey(i)) pyy += f[i];
+        if (L::ez(i) * L::ez(i)) pzz += f[i];
+        if (L::ex(i) * L::ey(i) == 1) pxy += f[i]; else if (L::ex(i) * L::ey(i) == -1) pxy -= f[i];
+        if (L::ex(i) * L::ez(i) == 1) pxz += f[i]; else if (L::ex(i) * L::ez(i) == -1) pxz -= f[i];
+        if (L::ey(i) * L::ez(i) == 1) pyz += f[i]; else if (L::ey(i) * L::ez(i) == -1) pyz -= f[i];
+      }
+      const float third = (float)(1.0 / 3.0);
+      pxx -= rho * (v[0] * v[0] + third); pyy -= rho * (v[1] * v[1] + third);
+      pzz -= L::D == 3 ? rho * (v[2] * v[2] + third) : 0.f;
+      pxy -= rho * v[0] * v[1]; pxz -= rho * v[0] * v[2]; pyz -= rho * v[1] * v[2];
+#pragma unroll
+      for (int i = 0; i < L::Q; i++) {        // regularisation, sym.py:882-891
+        float s = pxx * ((float)(L::ex(i) * L::ex(i)) - third) + pyy * ((float)(L::ey(i) * L::ey(i)) - third);
+        if (L::D == 3) s += pzz * ((float)(L::ez(i) * L::ez(i)) - third);
+        s += 2.0f * pxy * (float)(L::ex(i) * L::ey(i));
+        if (L::D == 3) s += 2.0f * (pxz * (float)(L::ex(i) * L::ez(i)) + pyz * (float)(L::ey(i) * L::ez(i)));
+        f[i] = fmaxf(1e-7f, feq[i] + L::w(i) * 4.5f * s);
+      }
+    }
+  } else if (cls == SLF_NT_DO_NOTHING && AA && orient != 0) {   // boundary.mako:862-877
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) {
+      if (edotn<L>(i, n0, n1, n2) > 0) {
+        if (ODD) dout[gi + P.DS * i] = f[i];
+        else dout[gi + noff<L>(P, L::opp(i)) + P.DS * L::opp(i)] = f[i];
+      }
+    }
+  }
+
+  const bool wet = cls == SLF_NT_HALFBB_WALL || vel_bc || den_bc || cls == SLF_NT_DO_NOTHING;
+  if (wet && P.relax) {
+    if (MODEL == SLF_MRT) {
+      if (cls == SLF_NT_EQUILIBRIUM_VELOCITY || cls == SLF_NT_EQUILIBRIUM_DENSITY) collide_mrt<L, true>(P, v, f);
+      else collide_mrt<L, false>(P, v, f);
+    } else {
+      collide_bgk<L>(P, rho, v, f);
+    }
+  }
+
+  if (cls == SLF_NT_HALFBB_WALL) {            // boundary.mako:653-683
+#pragma unroll
+    for (int i = 1; i < L::Q; i++) {
+      bool hit; int missing, name;
+      if (P.use_tags) { hit = (orient & (1 << (i - 1))) == 0; name = i; missing = L::opp(i); }
+      else { hit = orient != 0 && edotn<L>(i, n0, n1, n2) > 0; missing = i; name = L::opp(i); }
+      if (hit) {
+        // `name`/`missing` are compile-time per branch: resolve through a tiny switch
+        float val = 0.f;
+#pragma unroll
+        for (int k = 0; k < L::Q; k++) if (k == name) val = f[k];
+        if (!AA || ODD) dout[gi + P.DS * missing] = val;
+        else {
+          long long off = 0; int slot = 0;
+#pragma unroll
+          for (int k = 0; k < L::Q; k++) if (k == missing) { off = noff<L>(P, L::opp(k)); slot = L::opp(k); }
+          dout[gi + off + P.DS * slot] = val;
+        }
+      }
+    }
+  }
+
+  if (SAVE && wet) {
+    orho[gi] = rho; ovx[gi] = v[0]; ovy[gi] = v[1];
+    if (L::D == 3) ovz[gi] = v[2];
+  }
+
+  if (!P.prop) {
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) dout[gi + P.DS * i] = f[i];
+  } else if (MODE == MODE_AA_EVEN) {
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) dout[gi + P.DS * L::opp(i)] = f[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) {
+      bool ok = true;                          // prop_bnd, propagation.mako:36-41
+      if (L::ex(i) > 0) ok = ok && x < P.nx - 1; else if (L::ex(i) < 0) ok = ok && x > 0;
+      if (L::ey(i) > 0) ok = ok && y < P.ny - 1; else if (L::ey(i) < 0) ok = ok && y > 0;
+      if (L::D == 3) { if (L::ez(i) > 0) ok = ok && z < P.nz - 1; else if (L::ez(i) < 0) ok = ok && z > 0; }
+      if (ok) dout[gi + noff<L>(P, i) + P.DS * i] = f[i];
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// SetInitialConditions (lb_single_fluid.mako:101-127): every node with gx < lat_nx.
+// ----------------------------------------------------------------------------------------
+template <class L>
+__global__ void __launch_bounds__(256)
+set_initial_conditions(const DevParams P, float *__restrict__ dist, const float *__restrict__ ivx,
+                       const float *__restrict__ ivy, const float *__restrict__ ivz,
+                       const float *__restrict__ irho) {
+  const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= P.DS) return;
+  const int x = (int)(gi % P.ax);
+  const long long t = gi / P.ax;
+  const int y = (int)(t % P.ay), z = (int)(t / P.ay);
+  if (x >= P.nx || y >= P.ny || z >= P.nz) return;
+  float v[3] = {ivx[gi], ivy[gi], L::D == 3 ? ivz[gi] : 0.f};
+  float feq[L::Q];
+  equilibrium<L>(irho[gi], v, feq);
+#pragma unroll
+  for (int i = 0; i < L::Q; i++) dist[gi + P.DS * i] = feq[i];
+}
+
+// PrepareMacroFields (lb_single_fluid.mako:129-159): density only.
+template <class L, int MODE>
+__global__ void __launch_bounds__(256)
+prepare_macro_fields(const DevParams P, const uint32_t *__restrict__ map, const float *__restrict__ din,
+                     float *__restrict__ orho) {
+  const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= P.DS) return;
+  const int cls = node_class<L>(P, map[gi] & P.tmask);
+  if (cls < 0 || cls == SLF_NT_GHOST || cls == SLF_NT_UNUSED || cls == SLF_NT_PROPAGATION_ONLY) return;
+  if ((int)(gi % P.ax) >= P.nx) return;
+  float f[L::Q];
+  load_node<L, MODE>(P, din, gi, f);
+  float rho = 0.f;
+#pragma unroll
+  for (int i = 0; i < L::Q; i++) rho += f[i];
+  orho[gi] = rho;
+}
+
+// ----------------------------------------------------------------------------------------
+// ApplyPeriodicBoundaryConditions[WithSwap] (kernel_utils.mako:19-384).  One thread per
+// face position; the per-population conditions the template prints at render time are
+// evaluated here from (basis, periodicity, lattice size).
+// ----------------------------------------------------------------------------------------
+template <class L>
+__device__ __forceinline__ long long gidx3(const DevParams &P, int c0, int c1, int c2) {
+  return (long long)c0 + P.sy * c1 + P.sz * c2;
+}
+
+template <class L, bool SWAP>
+__device__ __forceinline__ bool pbc_main_cond(int axis, int i, const int (&per)[3], const int (&oth)[2],
+                                              const int (&idx)[2], const int (&maxd)[2]) {
+  const int e[3] = {L::ex(i), L::ey(i), L::ez(i)};
+  if (SWAP) {
+    bool ok = idx[0] >= 1 && idx[0] <= maxd[0];
+    if (L::D == 3) ok = ok && idx[1] >= 1 && idx[1] <= maxd[1];
+    return ok;
+  }
+  if (L::D == 2) {
+    const int c = e[1 - axis];
+    if (c == 1) return idx[0] > 1 && idx[0] <= maxd[0];
+    if (c == -1) return idx[0] < maxd[0] && idx[0] >= 1;
+    return true;
+  }
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const int c = e[oth[k]];
+    const bool both = per[axis] && per[oth[k]];
+    if (c == 1) { ok = ok && idx[k] > 1; if (both) ok = ok && idx[k] <= maxd[k]; }
+    else if (c == -1) { ok = ok && idx[k] < maxd[k]; if (both) ok = ok && idx[k] >= 1; }
+  }
+  return ok;
+}
+
+template <class L, bool SWAP>
+__device__ __forceinline__ bool pbc_corner(int axis, int i, const int (&per)[3], const int (&lim)[3],
+                                           const int (&oth)[2], const int (&idx)[2], int axis_target,
+                                           int (&tgt)[3]) {
+  const int e[3] = {L::ex(i), L::ey(i), L::ez(i)};
+  constexpr int nother = L::D - 1;
+  {
+    int ncond = 0; bool ok = true; int t[3] = {0, 0, 0};
+    t[axis] = axis_target;
+#pragma unroll
+    for (int k = 0; k < nother; k++) {
+      const int oa = oth[k], c = e[oa];
+      if (c == 0 || !per[oa]) { t[oa] = idx[k]; continue; }
+      if (c == 1) { const int shift = SWAP ? 2 : 1; ncond++; ok = ok && idx[k] == lim[oa] - shift; t[oa] = SWAP ? 0 : 1; }
+      else { const int shift = SWAP ? 1 : 0; ncond++; ok = ok && idx[k] == shift; t[oa] = lim[oa] - (SWAP ? 1 : 2); }
+    }
+    if (ncond > 0 && ok) { tgt[0] = t[0]; tgt[1] = t[1]; tgt[2] = t[2]; return true; }
+  }
+  if (L::D == 3 && e[0] * e[0] + e[1] * e[1] + e[2] * e[2] == 3) {
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const int oa = oth[k], ob = oth[1 - k], id_ = idx[k], id2 = idx[1 - k];
+      bool ok = true; int t[3] = {0, 0, 0};
+      t[axis] = axis_target;
+      if (e[oa] == 1) { const int shift = SWAP ? 2 : 1, start = SWAP ? 1 : 2; ok = ok && id_ >= start && id_ < lim[oa] - shift; }
+      else { const int shift = SWAP ? 1 : 2; ok = ok && id_ < lim[oa] - shift && id_ >= 1; }
+      t[oa] = id_;
+      if (e[ob] == 1) { const int shift = SWAP ? 2 : 1; ok = ok && id2 == lim[ob] - shift; t[ob] = SWAP ? 0 : 1; }
+      else { const int shift = SWAP ? 1 : 0; ok = ok && id2 == shift; t[ob] = lim[ob] - (SWAP ? 1 : 2); }
+      if (ok) { tgt[0] = t[0]; tgt[1] = t[1]; tgt[2] = t[2]; return true; }
+    }
+  }
+  return false;
+}
+
+template <class L, bool SWAP>
+__global__ void __launch_bounds__(128)
+apply_pbc(const DevParams P, float *dist, int axis, int per0, int per1, int per2) {
+  const int lim[3] = {P.nx, P.ny, P.nz};
+  const int per[3] = {per0, per1, per2};
+  int oth[2];
+  if (L::D == 2) { oth[0] = 1 - axis; oth[1] = 2; }
+  else { oth[0] = axis == 0 ? 1 : 0; oth[1] = axis == 2 ? 1 : 2; }
+  const int n1 = lim[oth[0]], n2 = L::D == 3 ? lim[oth[1]] : 1;
+  const int i1 = blockIdx.x * blockDim.x + threadIdx.x, i2 = blockIdx.y;
+  if (i1 >= n1 || i2 >= n2) return;
+  const int idx[2] = {i1, i2};
+  const int maxd[2] = {lim[oth[0]] - 2, L::D == 3 ? lim[oth[1]] - 2 : 0};
+  if (SWAP && L::D == 3) { if (i1 >= lim[oth[0]] - 1 || i2 >= lim[oth[1]] - 1 || i1 < 1 || i2 < 1) return; }
+  const long long stride = axis == 0 ? 1 : (axis == 1 ? P.sy : P.sz);
+  const long long offset = SWAP ? -stride : stride;
+  int cl[3] = {0, 0, 0}, ch[3] = {0, 0, 0};
+  cl[oth[0]] = ch[oth[0]] = i1;
+  if (L::D == 3) cl[oth[1]] = ch[oth[1]] = i2;
+  cl[axis] = SWAP ? 1 : 0;
+  ch[axis] = SWAP ? lim[axis] - 1 : lim[axis] - 2;
+  const long long gi_low = gidx3<L>(P, cl[0], cl[1], cl[2]), gi_high = gidx3<L>(P, ch[0], ch[1], ch[2]);
+  float val[L::Q];
+  const int ea_tab[3] = {0, 0, 0}; (void)ea_tab;
+  // low -> high
+#pragma unroll
+  for (int i = 1; i < L::Q; i++) {
+    const int ea = axis == 0 ? L::ex(i) : (axis == 1 ? L::ey(i) : L::ez(i));
+    if (ea == -1) val[i] = dist[gi_low + P.DS * (SWAP ? L::opp(i) : i)];
+  }
+#pragma unroll
+  for (int i = 1; i < L::Q; i++) {
+    const int ea = axis == 0 ? L::ex(i) : (axis == 1 ? L::ey(i) : L::ez(i));
+    if (ea != -1) continue;
+    const int j = SWAP ? L::opp(i) : i;
+    const float fv = val[i];
+    if (!isfinite(fv)) continue;
+    const int n2e = L::ex(i) * L::ex(i) + L::ey(i) * L::ey(i) + L::ez(i) * L::ez(i);
+    if (n2e > 1) {
+      const bool main_ok = pbc_main_cond<L, SWAP>(axis, i, per, oth, idx, maxd);
+      if (main_ok) dist[gi_high + P.DS * j] = fv;
+      if (SWAP || !main_ok) {
+        int tgt[3];
+        if (pbc_corner<L, SWAP>(axis, i, per, lim, oth, idx, SWAP ? lim[axis] - 1 : lim[axis] - 2, tgt))
+          dist[gidx3<L>(P, tgt[0], tgt[1], tgt[2]) + P.DS * j] = fv;
+      }
+    } else {
+      dist[gi_high + P.DS * j] = fv;
+    }
+  }
+  // high -> low
+#pragma unroll
+  for (int i = 1; i < L::Q; i++) {
+    const int ea = axis == 0 ? L::ex(i) : (axis == 1 ? L::ey(i) : L::ez(i));
+    if (ea == 1) val[i] = dist[gi_high + offset + P.DS * (SWAP ? L::opp(i) : i)];
+  }
+#pragma unroll
+  for (int i = 1; i < L::Q; i++) {
+    const int ea = axis == 0 ? L::ex(i) : (axis == 1 ? L::ey(i) : L::ez(i));
+    if (ea != 1) continue;
+    const int j = SWAP ? L::opp(i) : i;
+    const float fv = val[i];
+    if (!isfinite(fv)) continue;
+    const int n2e = L::ex(i) * L::ex(i) + L::ey(i) * L::ey(i) + L::ez(i) * L::ez(i);
+    if (n2e > 1) {
+      const bool main_ok = pbc_main_cond<L, SWAP>(axis, i, per, oth, idx, maxd);
+      if (main_ok) dist[gi_low + offset + P.DS * j] = fv;
+      if (SWAP || !main_ok) {
+        int tgt[3];
+        if (pbc_corner<L, SWAP>(axis, i, per, lim, oth, idx, SWAP ? 0 : 1, tgt))
+          dist[gidx3<L>(P, tgt[0], tgt[1], tgt[2]) + P.DS * j] = fv;
+      }
+    } else {
+      dist[gi_low + offset + P.DS * j] = fv;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// Collect/DistributeContinuousData[WithSwap] (kernel_utils.mako:476-794); buffer layout
+// [dist][other][x].  grid = (ceil(max_lx/128), max_other, ndists).
+// ----------------------------------------------------------------------------------------
+template <class L>
+__device__ __forceinline__ int face_slot(int face, int k) {
+  // k-th population with e[axis] * sign >= 1  (sym.get_interblock_dists, sym.py:829-845)
+  const int axis = face >> 1, sgn = (face & 1) ? 1 : -1;
+  int n = 0, out = -1;
+#pragma unroll
+  for (int i = 0; i < L::Q; i++) {
+    const int ea = axis == 0 ? L::ex(i) : (axis == 1 ? L::ey(i) : L::ez(i));
+    if (ea * sgn >= 1) { if (n == k) out = i; n++; }
+  }
+  return out;
+}
+
+template <class L>
+__device__ __forceinline__ int opp_rt(int i) {
+  int o = 0;
+#pragma unroll
+  for (int k = 0; k < L::Q; k++) if (k == i) o = L::opp(k);
+  return o;
+}
+
+template <class L, bool DISTRIBUTE>
+__global__ void __launch_bounds__(128)
+xfer_continuous(const DevParams P, float *dist, int face, int base_gx, int base_other, int max_lx,
+                int max_other, float *buffer, int with_swap) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int o = blockIdx.y, k = blockIdx.z;
+  if (x >= max_lx || o >= max_other) return;
+  const int lim[3] = {P.nx, P.ny, P.nz};
+  const int axis = face >> 1, hi = face & 1, n = lim[axis];
+  int layer;
+  if (!DISTRIBUTE) layer = with_swap ? (hi ? n - 2 : 1) : (hi ? n - 1 : 0);    // lat_linear_macro / lat_linear
+  else layer = with_swap ? (hi ? 0 : n - 1) : (hi ? 1 : n - 2);               // lat_linear_with_swap / _dist
+  int c0 = base_gx + x, c1, c2 = 0;
+  if (L::D == 2) c1 = layer;
+  else if (axis == 1) { c1 = layer; c2 = base_other + o; }
+  else { c1 = base_other + o; c2 = layer; }
+  int slot = face_slot<L>(face, k);
+  if (with_swap) slot = opp_rt<L>(slot);
+  const long long di = gidx3<L>(P, c0, c1, c2) + P.DS * slot;
+  const long long bi = ((long long)k * max_other + o) * max_lx + x;
+  if (DISTRIBUTE) dist[di] = buffer[bi]; else buffer[bi] = dist[di];
+}
+
+template <bool DISTRIBUTE>
+__global__ void xfer_sparse(const uint32_t *__restrict__ idx_array, float *dist, float *buffer, int max_idx,
+                            unsigned long long limit) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= max_idx) return;
+  const uint32_t gi = idx_array[idx];
+  if (gi == 0xffffffffu || gi >= limit) return;
+  if (DISTRIBUTE) dist[gi] = buffer[idx]; else buffer[idx] = dist[gi];
+}

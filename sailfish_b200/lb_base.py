@@ -1,0 +1,104 @@
+"""Model base classes: mirror of sailfish/lb_base.py (LBSim :30-302, LBForcedSim :305-394)
+for the single-fluid hot path."""
+from collections import namedtuple
+
+import numpy as np
+
+from sailfish_b200 import lattice
+
+ScalarField = namedtuple('ScalarField', 'name')
+VectorField = namedtuple('VectorField', 'name')
+
+
+class LBSim(object):
+    subdomain = None
+    subdomain_runner = None
+    nonlocality = 0
+
+    @classmethod
+    def add_options(cls, group, dim):
+        """lb_base.py:54-100 (options that reach the kernels)."""
+        grids = [n for n in lattice.KNOWN if lattice.get(n).dim == dim]
+        group.add_argument('--grid', help='LB grid', type=str, choices=grids, default=grids[0])
+        group.add_argument('--access_pattern', type=str, default='AB', choices=('AB', 'AA'),
+                           help='AB: two lattice copies; AA: single copy, in-place updates')
+        group.add_argument('--node_addressing', type=str, default='direct', choices=('direct',),
+                           help='only direct (dense) addressing is on the B200 hot path')
+        group.add_argument('--nouse_link_tags', action='store_false', dest='use_link_tags', default=True)
+
+    @classmethod
+    def modify_config(cls, config):
+        pass
+
+    @classmethod
+    def update_defaults(cls, defaults):
+        pass
+
+    def __init__(self, config):
+        self.config = config
+        self.iteration = 0
+        self.need_sync_flag = False
+        self.need_fields_flag = False
+        self.grid = lattice.get(config.grid)
+        self.grids = [self.grid]
+
+    @property
+    def dim(self):
+        return self.grid.dim
+
+    @classmethod
+    def fields(cls):
+        return []
+
+    def need_output(self):
+        """lb_base.py:222-231."""
+        if self.config.output_required:
+            return ((self.iteration + 1) % self.config.every) == 0 and self.config.from_ <= self.iteration
+        return False
+
+    def need_sync_fields(self):
+        """lb_base.py:233-252."""
+        need_sync = self.need_sync_flag or self.need_output()
+        need_fields = self.need_fields_flag or need_sync
+        self.need_fields_flag = False
+        self.need_sync_flag = False
+        return need_sync, need_fields
+
+    def before_main_loop(self, runner):
+        pass
+
+    def after_step(self, runner):
+        pass
+
+    def after_main_loop(self, runner):
+        pass
+
+    def body_acceleration(self):
+        return None
+
+
+class LBForcedSim(LBSim):
+    """Body forces (lb_base.py:305-394).  Only constant accelerations on grid 0 with the Guo
+    scheme are on the hot path (force-driven Poiseuille)."""
+
+    def __init__(self, config):
+        super(LBForcedSim, self).__init__(config)
+        self._forces = {}
+
+    @classmethod
+    def add_options(cls, group, dim):
+        group.add_argument('--force_implementation', type=str, choices=['guo'], default='guo')
+
+    def add_body_force(self, force, grid=0, accel=True):
+        dim = self.grid.dim
+        assert len(force) == dim
+        if grid != 0 or not accel:
+            raise ValueError('B200 hot path: constant accelerations on grid 0 only')
+        cur = self._forces.setdefault(0, np.zeros(dim, np.float64))
+        self._forces[0] = cur + np.float64(force)
+
+    def body_acceleration(self):
+        if 0 not in self._forces:
+            return None
+        a = self._forces[0]
+        return [float(x) for x in a] + [0.0] * (3 - len(a))
