@@ -137,6 +137,13 @@ int  slf_event_elapsed_ms(uint64_t start, uint64_t end, float *ms);
  *      backend_cuda.py:193-218): no source is generated, the context becomes data ---- */
 int  slf_plan_create(const SlfParams *params, SlfPlan **plan);
 int  slf_plan_destroy(SlfPlan *plan);
+/* Binds a node map (device pointer to the uint32 array the kernels receive as `map`) to the
+ * plan and derives, once, what the reference re-reads every step: 1-bit masks of the plain
+ * fluid and full-bounce-back nodes for the bulk kernel and the sorted list of the remaining
+ * active nodes for the boundary kernel.  Launches with a different / unbound map pointer fall
+ * back to kernels that decode the map per node.  Call again after the map is modified
+ * (Subdomain.update_node -> backend.to_buf, subdomain.py:564-591); map = 0 unbinds. */
+int  slf_plan_bind_map(SlfPlan *plan, uint64_t map);
 /* number of kernels this library has launched since slf_init (bench `gpu_launches`) */
 uint64_t slf_launch_count(void);
 

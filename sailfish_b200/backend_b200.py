@@ -51,6 +51,7 @@ _PROTOTYPES = {
     'slf_event_elapsed_ms': [_u64, _u64, ctypes.POINTER(ctypes.c_float)],
     'slf_plan_create': [ctypes.POINTER(P.SlfParams), ctypes.POINTER(_vp)],
     'slf_plan_destroy': [_vp],
+    'slf_plan_bind_map': [_vp, _u64],
     'slf_set_initial_conditions': [_vp, _u64, _u64, _u64, _u64, _u64, _u64, _u64],
     'slf_collide_and_propagate': [_vp, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _i, _u32, _i, _i, _u64],
     'slf_prepare_macro_fields': [_vp, _u64, _u64, _u64, _i, _u32, _u64],
@@ -198,6 +199,9 @@ class Kernel(object):
                 m, din, dout, rho, vx, vy, options = a[:7]
                 vz = 0
             options = int(options)
+            if b._bound_map != int(m):
+                l.call('slf_plan_bind_map', plan, int(m))
+                b._bound_map = int(m)
             z0, z1 = b._region_for(options)
             if z0 == z1:
                 return
@@ -261,6 +265,7 @@ class B200Backend(object):
         self._lib.call('slf_init', int(gpu_id))   # raises when there is no device
         self._plan = None
         self._params = None
+        self._bound_map = 0
         self._dim = 3
         self._buffers = {}          # device ptr -> host ndarray (alloc_buf(like=...))
         self._iteration_kernels = []
@@ -336,6 +341,9 @@ class B200Backend(object):
     def to_buf(self, buf, source=None):
         h = np.ascontiguousarray(self._host_of(buf, source))
         self._lib.call('slf_memcpy_h2d', int(buf), h.ctypes.data_as(_vp), int(h.nbytes))
+        if int(buf) == self._bound_map and self._plan is not None:
+            # the node map changed on the host (Subdomain.update_node): re-derive masks/lists
+            self._lib.call('slf_plan_bind_map', self._plan, int(buf))
 
     def from_buf(self, buf, target=None):
         h = self._host_of(buf, target)

@@ -143,17 +143,23 @@ class LBSimulationController(object):
                         dist_b=int(be.ipc_handle_wrap(g['dist_b'])) if g['dist_b'] else 0,
                         lat_n=g['lat_n'], arr_n=g['arr_n'], sems=int(be.ipc_handle_wrap(g['sems'])))
             self._dist = dist
+        by_id = dict((r._spec.id, r) for r in self.runners)
         for r in self.runners:
             for face, other in r._spec._face_conn.items():
                 if face // 2 != axis:
                     continue
-                info = infos.get(other) or remote[other]
                 side = face & 1
-                # the neighbour receives through its opposite side: signal that semaphore
-                peer_ready = info['sems'] + 4 * (1 - side)
-                sp = r.sem_ptrs()
-                r.add_link(HaloLink(face, info['dist_a'], info['dist_b'], info['lat_n'], info['arr_n'],
-                                    peer_ready, sp['ready'][side], sp['consumed'][side]))
+                if other in by_id:
+                    info = infos[other]
+                    r.add_link(HaloLink(face, info['dist_a'], info['dist_b'], info['lat_n'], info['arr_n'],
+                                        peer_runner=by_id[other]))
+                else:
+                    info = remote[other]
+                    # the neighbour receives through its opposite side: signal that semaphore
+                    peer_ready = info['sems'] + 4 * (1 - side)
+                    sp = r.sem_ptrs()
+                    r.add_link(HaloLink(face, info['dist_a'], info['dist_b'], info['lat_n'], info['arr_n'],
+                                        peer_ready, sp['ready'][side], sp['consumed'][side]))
 
     # -- running -------------------------------------------------------------------------------
     def barrier(self):

@@ -9,35 +9,17 @@
 #include <string>
 #include <vector>
 
-#include "slf_kernels.cuh"
+#include "slf_plan.cuh"
 
 static thread_local std::string g_err;
 static std::atomic<uint64_t> g_launches{0};
 static int g_device = -1;
 
-static int fail(int code, const std::string &msg) {
+int slf_fail(int code, const std::string &msg) {
   g_err = msg;
   return code;
 }
-#define CUDA_OK(expr)                                                                         \
-  do {                                                                                        \
-    cudaError_t e_ = (expr);                                                                  \
-    if (e_ != cudaSuccess)                                                                    \
-      return fail((int)e_, std::string(#expr) + ": " + cudaGetErrorString(e_));              \
-  } while (0)
-#define LAUNCH_OK(name)                                                                       \
-  do {                                                                                        \
-    cudaError_t e_ = cudaGetLastError();                                                      \
-    if (e_ != cudaSuccess) return fail((int)e_, std::string(name) + ": " + cudaGetErrorString(e_)); \
-    g_launches.fetch_add(1, std::memory_order_relaxed);                                       \
-  } while (0)
-
-struct SlfPlan {
-  SlfParams hp;
-  DevParams dp;
-  float *d_node_params = nullptr;
-  int Q = 0, D = 0;
-};
+void slf_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 extern "C" {
 
@@ -208,49 +190,64 @@ int slf_plan_create(const SlfParams *p, SlfPlan **out) {
 int slf_plan_destroy(SlfPlan *plan) {
   if (!plan) return 0;
   if (plan->d_node_params) cudaFree(plan->d_node_params);
+  if (plan->d_fluid_mask) cudaFree(plan->d_fluid_mask);
+  if (plan->d_wall_mask) cudaFree(plan->d_wall_mask);
+  if (plan->d_list) cudaFree(plan->d_list);
   delete plan;
   return 0;
 }
 
-}  // extern "C"
 
-// ---- dispatch helpers --------------------------------------------------------------------
-template <class L, int MODEL, int MODE, bool SAVE>
-static int launch_collide(SlfPlan *pl, const uint32_t *map, const float *din, float *dout, float *rho,
-                          float *vx, float *vy, float *vz, long long gi0, long long gi1, cudaStream_t s) {
-  const long long n = gi1 - gi0;
-  if (n <= 0) return 0;
-  {
-    const int bs = 256;
-    const long long nb = (n + bs - 1) / bs;
-    collide_bulk<L, MODEL, MODE, SAVE><<<(unsigned)nb, bs, 0, s>>>(pl->dp, map, din, dout, rho, vx, vy, vz, gi0, gi1);
-    LAUNCH_OK("collide_bulk");
+// Derives the per-map acceleration structures: 1-bit masks of plain fluid nodes and of
+// full-way bounce-back walls (handled by the bulk kernel without touching the uint32 map)
+// and the sorted list of all other active nodes (handled by the boundary kernel).  Call
+// again after the map changes (Subdomain.update_node); unbound maps still work through the
+// generic scanning kernels.
+int slf_plan_bind_map(SlfPlan *pl, uint64_t map) {
+  if (!pl) return fail(SLF_EINVAL, "null plan");
+  const DevParams &d = pl->dp;
+  if (d.DS >= (1ll << 32)) return fail(SLF_EUNSUPPORTED, "node lists use 32-bit indices");
+  pl->bound_map = 0;
+  if (!map) return 0;
+  std::vector<uint32_t> h((size_t)d.DS);
+  CUDA_OK(cudaMemcpy(h.data(), (const void *)map, (size_t)d.DS * 4, cudaMemcpyDeviceToHost));
+  const long long words = (d.DS + 31) / 32;
+  std::vector<uint32_t> fm((size_t)words, 0u), wm((size_t)words, 0u), list;
+  const int outer = pl->D == 3 ? d.nz : d.ny;
+  const long long slab = pl->D == 3 ? d.sz : d.sy;
+  pl->layer_off.assign(outer + 1, 0);
+  const uint32_t t_fluid = d.tid[SLF_NT_FLUID], t_wall = d.tid[SLF_NT_FULLBB_WALL];
+  const uint32_t t_ghost = d.tid[SLF_NT_GHOST], t_unused = d.tid[SLF_NT_UNUSED], t_prop = d.tid[SLF_NT_PROPAGATION_ONLY];
+  for (int o = 0; o < outer; o++) {
+    pl->layer_off[o] = (long long)list.size();
+    for (long long gi = slab * o; gi < slab * (o + 1); gi++) {
+      const uint32_t type = h[gi] & d.tmask;
+      if (type == t_ghost || type == t_unused || type == t_prop) continue;
+      const int x = (int)(gi % d.ax);
+      const long long t = gi / d.ax;
+      const int y = (int)(t % d.ay), z = (int)(t / d.ay);
+      if (x >= d.nx || y >= d.ny || z >= d.nz) continue;
+      const bool interior = x > 0 && x < d.nx - 1 && y > 0 && y < d.ny - 1 && (pl->D == 2 || (z > 0 && z < d.nz - 1));
+      if (type == t_fluid && interior) fm[gi >> 5] |= 1u << (gi & 31);
+      else if (type == t_wall && interior) wm[gi >> 5] |= 1u << (gi & 31);
+      else list.push_back((uint32_t)gi);
+    }
   }
-  {
-    const int bs = 128;
-    const long long nb = (n + bs - 1) / bs;
-    collide_boundary<L, MODEL, MODE, SAVE><<<(unsigned)nb, bs, 0, s>>>(pl->dp, map, din, dout, rho, vx, vy, vz, gi0, gi1);
-    LAUNCH_OK("collide_boundary");
-  }
+  pl->layer_off[outer] = (long long)list.size();
+  if (pl->d_fluid_mask) { cudaFree(pl->d_fluid_mask); pl->d_fluid_mask = nullptr; }
+  if (pl->d_wall_mask) { cudaFree(pl->d_wall_mask); pl->d_wall_mask = nullptr; }
+  if (pl->d_list) { cudaFree(pl->d_list); pl->d_list = nullptr; }
+  CUDA_OK(cudaMalloc((void **)&pl->d_fluid_mask, (size_t)words * 4));
+  CUDA_OK(cudaMalloc((void **)&pl->d_wall_mask, (size_t)words * 4));
+  CUDA_OK(cudaMalloc((void **)&pl->d_list, (list.size() + 1) * 4));
+  CUDA_OK(cudaMemcpy(pl->d_fluid_mask, fm.data(), (size_t)words * 4, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(pl->d_wall_mask, wm.data(), (size_t)words * 4, cudaMemcpyHostToDevice));
+  if (!list.empty()) CUDA_OK(cudaMemcpy(pl->d_list, list.data(), list.size() * 4, cudaMemcpyHostToDevice));
+  pl->bound_map = map;
   return 0;
 }
 
-template <class L, int MODEL>
-static int dispatch_mode(SlfPlan *pl, int mode, bool save, const uint32_t *map, const float *din, float *dout,
-                         float *rho, float *vx, float *vy, float *vz, long long gi0, long long gi1,
-                         cudaStream_t s) {
-#define SLF_CASE(M)                                                                                     \
-  case M:                                                                                               \
-    return save ? launch_collide<L, MODEL, M, true>(pl, map, din, dout, rho, vx, vy, vz, gi0, gi1, s)   \
-                : launch_collide<L, MODEL, M, false>(pl, map, din, dout, rho, vx, vy, vz, gi0, gi1, s);
-  switch (mode) {
-    SLF_CASE(MODE_AB)
-    SLF_CASE(MODE_AA_EVEN)
-    SLF_CASE(MODE_AA_ODD)
-  }
-#undef SLF_CASE
-  return fail(SLF_EINVAL, "bad mode");
-}
+}  // extern "C"
 
 extern "C" {
 
@@ -262,8 +259,7 @@ int slf_collide_and_propagate(SlfPlan *pl, uint64_t map, uint64_t dist_in, uint6
   const int outer = pl->D == 3 ? d.nz : d.ny;
   if (z_end < 0) z_end = outer;
   if (z_begin < 0 || z_end > outer || z_begin > z_end) return fail(SLF_EINVAL, "bad slab range");
-  const long long slab = pl->D == 3 ? d.sz : d.sy;
-  const long long gi0 = slab * z_begin, gi1 = slab * z_end;
+  const int gi0 = z_begin, gi1 = z_end;   // slab range; converted to node / list ranges at launch
   int mode;
   if (pl->hp.access_pattern == SLF_AB) {
     mode = MODE_AB;
@@ -280,14 +276,11 @@ int slf_collide_and_propagate(SlfPlan *pl, uint64_t map, uint64_t dist_in, uint6
   cudaStream_t s = (cudaStream_t)stream;
   const int model = pl->hp.model;
   switch (pl->hp.lattice) {
-    case SLF_D2Q9:
-      return model == SLF_MRT ? dispatch_mode<D2Q9, SLF_MRT>(pl, mode, save, m, din, dout, r, x, y, z, gi0, gi1, s)
-                              : dispatch_mode<D2Q9, SLF_BGK>(pl, mode, save, m, din, dout, r, x, y, z, gi0, gi1, s);
+    case SLF_D2Q9: return slf_collide_d2q9(pl, model, mode, save, m, din, dout, r, x, y, z, gi0, gi1, s);
     case SLF_D3Q19:
-      return model == SLF_MRT ? dispatch_mode<D3Q19, SLF_MRT>(pl, mode, save, m, din, dout, r, x, y, z, gi0, gi1, s)
-                              : dispatch_mode<D3Q19, SLF_BGK>(pl, mode, save, m, din, dout, r, x, y, z, gi0, gi1, s);
-    case SLF_D3Q27:
-      return dispatch_mode<D3Q27, SLF_BGK>(pl, mode, save, m, din, dout, r, x, y, z, gi0, gi1, s);
+      return model == SLF_MRT ? slf_collide_d3q19_mrt(pl, mode, save, m, din, dout, r, x, y, z, gi0, gi1, s)
+                              : slf_collide_d3q19_bgk(pl, mode, save, m, din, dout, r, x, y, z, gi0, gi1, s);
+    case SLF_D3Q27: return slf_collide_d3q27(pl, mode, save, m, din, dout, r, x, y, z, gi0, gi1, s);
   }
   return fail(SLF_EINVAL, "bad lattice");
 }

@@ -1,0 +1,74 @@
+// slf_collide.cuh -- launch + template dispatch of the collide kernels (included by slf_collide_*.cu).
+#pragma once
+#include <cstdlib>
+
+#include "slf_plan.cuh"
+
+#ifndef SLF_HINT
+#define SLF_HINT 1
+#endif
+
+static inline int slf_env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+// ---- dispatch helpers --------------------------------------------------------------------
+template <class L, int MODEL, int MODE, bool SAVE>
+static int launch_collide(SlfPlan *pl, const uint32_t *map, const float *din, float *dout, float *rho,
+                          float *vx, float *vy, float *vz, int z0, int z1, cudaStream_t s) {
+  const long long slab = pl->D == 3 ? pl->dp.sz : pl->dp.sy;
+  const long long gi0 = slab * z0, gi1 = slab * z1;
+  const long long n = gi1 - gi0;
+  if (n <= 0) return 0;
+  const bool bound = pl->bound_map != 0 && pl->bound_map == (uint64_t)map;
+  {
+    // 128-thread blocks and streaming (.cs) loads/stores measured best on B200
+    // (profiles/r01_sweep_blocksize_hint.txt); SLF_BULK_BS overrides the block size.
+    static const int bs = slf_env_int("SLF_BULK_BS", 128);
+    const long long nb = (n + bs - 1) / bs;
+    if (bound)
+      collide_bulk<L, MODEL, MODE, SAVE, true, SLF_HINT><<<(unsigned)nb, bs, 0, s>>>(
+          pl->dp, map, pl->d_fluid_mask, pl->d_wall_mask, din, dout, rho, vx, vy, vz, gi0, gi1);
+    else
+      collide_bulk<L, MODEL, MODE, SAVE, false, SLF_HINT><<<(unsigned)nb, bs, 0, s>>>(
+          pl->dp, map, nullptr, nullptr, din, dout, rho, vx, vy, vz, gi0, gi1);
+    LAUNCH_OK("collide_bulk");
+  }
+  {
+    const int bs = 128;
+    if (bound) {
+      const long long k0 = pl->layer_off[z0], k1 = pl->layer_off[z1];
+      if (k1 > k0) {
+        const long long nb = (k1 - k0 + bs - 1) / bs;
+        collide_boundary<L, MODEL, MODE, SAVE, true><<<(unsigned)nb, bs, 0, s>>>(
+            pl->dp, map, pl->d_list, din, dout, rho, vx, vy, vz, k0, k1);
+        LAUNCH_OK("collide_boundary");
+      }
+    } else {
+      const long long nb = (n + bs - 1) / bs;
+      collide_boundary<L, MODEL, MODE, SAVE, false><<<(unsigned)nb, bs, 0, s>>>(
+          pl->dp, map, nullptr, din, dout, rho, vx, vy, vz, gi0, gi1);
+      LAUNCH_OK("collide_boundary");
+    }
+  }
+  return 0;
+}
+
+template <class L, int MODEL>
+static int dispatch_mode(SlfPlan *pl, int mode, bool save, const uint32_t *map, const float *din, float *dout,
+                         float *rho, float *vx, float *vy, float *vz, int gi0, int gi1,
+                         cudaStream_t s) {
+#define SLF_CASE(M)                                                                                     \
+  case M:                                                                                               \
+    return save ? launch_collide<L, MODEL, M, true>(pl, map, din, dout, rho, vx, vy, vz, gi0, gi1, s)   \
+                : launch_collide<L, MODEL, M, false>(pl, map, din, dout, rho, vx, vy, vz, gi0, gi1, s);
+  switch (mode) {
+    SLF_CASE(MODE_AB)
+    SLF_CASE(MODE_AA_EVEN)
+    SLF_CASE(MODE_AA_ODD)
+  }
+#undef SLF_CASE
+  return fail(SLF_EINVAL, "bad mode");
+}
+

@@ -1,0 +1,5 @@
+#include "slf_collide.cuh"
+int slf_collide_d3q19_mrt(SlfPlan *pl, int mode, bool save, const uint32_t *map, const float *din, float *dout,
+                          float *rho, float *vx, float *vy, float *vz, int z0, int z1, cudaStream_t s) {
+  return dispatch_mode<D3Q19, SLF_MRT>(pl, mode, save, map, din, dout, rho, vx, vy, vz, z0, z1, s);
+}

@@ -122,6 +122,13 @@ __device__ __forceinline__ void collide_bgk(const DevParams &P, float rho, float
   }
 }
 
+// MS_relaxate (relaxation_mrt.mako:31-97): m = M f; non-conserved moments relax towards their
+// equilibria with rate s_k; f = M^-1 m.  The rows of M are mutually orthogonal (Gram-Schmidt,
+// sym.py:918-942, :1044), hence M^-1 = M^T diag(1/|row|^2).  Evaluated here in the
+// algebraically identical "delta" form  f += M^-1 [ -s_k (m_k - m_k^eq) ]  : only the small
+// change of each moment goes through the back-transform, so its round-off scales with the
+// change rather than with the populations (closer to the exact result than transforming the
+// full moment vector; the parity tests measure both against the fp64 oracle).
 template <class L, bool EQ_NODE>
 __device__ __forceinline__ void collide_mrt(const DevParams &P, float (&v)[3], float (&f)[L::Q]) {
   if constexpr (L::HAS_MRT) {
@@ -131,7 +138,6 @@ __device__ __forceinline__ void collide_mrt(const DevParams &P, float (&v)[3], f
       float s = 0.f;
 #pragma unroll
       for (int i = 0; i < L::Q; i++) {
-        constexpr int dummy = 0; (void)dummy;
         const int c = L::m(k, i);
         if (c == 1) s += f[i];
         else if (c == -1) s -= f[i];
@@ -139,13 +145,14 @@ __device__ __forceinline__ void collide_mrt(const DevParams &P, float (&v)[3], f
       }
       m[k] = s;
     }
-    if (P.forced) {
+    constexpr int IZ = L::I_MZ < 0 ? 0 : L::I_MZ;
+    if (P.forced) {                               // fluid_momentum, relaxation_mrt.mako:11-28
       m[L::I_MX] = fmaf(0.5f, P.a[0], m[L::I_MX]);
       m[L::I_MY] = fmaf(0.5f, P.a[1], m[L::I_MY]);
-      if (L::D == 3) m[L::I_MZ < 0 ? 0 : L::I_MZ] = fmaf(0.5f, P.a[2], m[L::I_MZ < 0 ? 0 : L::I_MZ]);
+      if (L::D == 3) m[IZ] = fmaf(0.5f, P.a[2], m[IZ]);
     }
     const float rho = m[0], mx = m[L::I_MX], my = m[L::I_MY];
-    const float mz = L::D == 3 ? m[L::I_MZ < 0 ? 0 : L::I_MZ] : 0.f;
+    const float mz = L::D == 3 ? m[IZ] : 0.f;
     float meq[L::Q];
 #pragma unroll
     for (int k = 0; k < L::Q; k++) meq[k] = 0.f;
@@ -164,34 +171,38 @@ __device__ __forceinline__ void collide_mrt(const DevParams &P, float (&v)[3], f
       meq[11] = ir * (my * my - mz * mz);
       meq[13] = ir * mx * my; meq[14] = ir * my * mz; meq[15] = ir * mx * mz;
     }
+    // change of each moment, pre-divided by |row|^2
+    float dm[L::Q];
 #pragma unroll
     for (int k = 0; k < L::Q; k++) {
       if (L::rate(k) != 0.0f) {
         const float s = L::rate(k) < 0.f ? P.inv_tau_mrt : L::rate(k);
-        float mk = EQ_NODE ? meq[k] : m[k];     // relaxation_mrt.mako:59-77
-        m[k] = mk - s * (mk - meq[k]);
+        // equilibrium nodes first overwrite the moment with its equilibrium (:59-77), i.e. s = 1
+        dm[k] = (EQ_NODE ? 1.0f : s) * (meq[k] - m[k]) * L::mnorm_inv(k);
+      } else {
+        dm[k] = 0.f;
       }
     }
     if (P.forced) {
-      m[L::I_MX] = fmaf(0.5f, P.a[0], m[L::I_MX]);
-      m[L::I_MY] = fmaf(0.5f, P.a[1], m[L::I_MY]);
-      if (L::D == 3) m[L::I_MZ < 0 ? 0 : L::I_MZ] = fmaf(0.5f, P.a[2], m[L::I_MZ < 0 ? 0 : L::I_MZ]);
+      // both half-steps of fluid_momentum add a/2 to the (conserved) momentum moments
+      dm[L::I_MX] = P.a[0] * L::mnorm_inv(L::I_MX);
+      dm[L::I_MY] = P.a[1] * L::mnorm_inv(L::I_MY);
+      if (L::D == 3) dm[IZ] = P.a[2] * L::mnorm_inv(IZ);
 #pragma unroll
-      for (int d = 0; d < L::D; d++) v[d] = fmaf(0.5f, P.a[d], v[d]);
+      for (int d = 0; d < L::D; d++) v[d] = fmaf(0.5f, P.a[d], v[d]);   // fluid_output_velocity
     }
-#pragma unroll
-    for (int k = 0; k < L::Q; k++) m[k] *= L::mnorm_inv(k);
 #pragma unroll
     for (int i = 0; i < L::Q; i++) {
       float s = 0.f;
 #pragma unroll
       for (int k = 0; k < L::Q; k++) {
         const int c = L::m(k, i);
-        if (c == 1) s += m[k];
-        else if (c == -1) s -= m[k];
-        else if (c != 0) s = fmaf((float)c, m[k], s);
+        if (L::rate(k) == 0.0f && !(k == L::I_MX || k == L::I_MY || k == IZ)) continue;
+        if (c == 1) s += dm[k];
+        else if (c == -1) s -= dm[k];
+        else if (c != 0) s = fmaf((float)c, dm[k], s);
       }
-      f[i] = s;
+      f[i] += s;
     }
   }
 }
@@ -202,12 +213,28 @@ __device__ __forceinline__ long long noff(const DevParams &P, int i) {
   return (long long)L::ex(i) + (long long)L::ey(i) * P.sy + (long long)L::ez(i) * P.sz;
 }
 
-template <class L, int MODE>
-__device__ __forceinline__ void load_node(const DevParams &P, const float *__restrict__ din, long long gi,
+// HINT selects the cache operator of the population loads/stores of the bulk kernel:
+// 0 default (ld.global / st.global), 1 streaming (.cs: evict-first in L1/L2 -- every value is
+// used exactly once per step), 2 L2-only loads (.cg) + write-through stores (.wt).
+template <int HINT>
+__device__ __forceinline__ float ldp(const float *p) {
+  if (HINT == 1) return __ldcs(p);
+  if (HINT == 2) return __ldcg(p);
+  return *p;
+}
+template <int HINT>
+__device__ __forceinline__ void stp(float *p, float v) {
+  if (HINT == 1) __stcs(p, v);
+  else if (HINT == 2) __stwt(p, v);
+  else *p = v;
+}
+
+template <class L, int MODE, int HINT = 0>
+__device__ __forceinline__ void load_node(const DevParams &P, const float *din, long long gi,
                                           float (&f)[L::Q]) {
 #pragma unroll
   for (int i = 0; i < L::Q; i++) {
-    if (MODE == MODE_AA_ODD) f[i] = din[gi - noff<L>(P, i) + P.DS * L::opp(i)];
-    else f[i] = din[gi + P.DS * i];
+    if (MODE == MODE_AA_ODD) f[i] = ldp<HINT>(din + (gi - noff<L>(P, i) + P.DS * L::opp(i)));
+    else f[i] = ldp<HINT>(din + (gi + P.DS * i));
   }
 }

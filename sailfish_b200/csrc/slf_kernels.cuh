@@ -23,18 +23,51 @@ __device__ __forceinline__ int node_class(const DevParams &P, uint32_t type) {
 // ----------------------------------------------------------------------------------------
 // Bulk kernel.  gi range [gi0, gi1) is a contiguous run of nodes (whole z-slabs).
 // ----------------------------------------------------------------------------------------
-template <class L, int MODEL, int MODE, bool SAVE>
+// MASKED = true: node classes come from two 1-bit-per-node masks built once per node map
+// (slf_plan_bind_map): bit set in `fluid` -> plain fluid node; bit set in `wall` -> full-way
+// bounce-back wall.  A warp covers 32 consecutive nodes = one mask word, so the 4 B/node
+// map read of the reference layout becomes 2 x 4 B per warp.  Walls are handled here too
+// (bounce-back is a pure slot permutation) so that wall columns on x faces share their
+// sectors with the neighbouring fluid nodes instead of being fetched one sector per value.
+template <class L, int MODEL, int MODE, bool SAVE, bool MASKED, int HINT = 0>
 __global__ void __launch_bounds__(256)
-collide_bulk(const DevParams P, const uint32_t *__restrict__ map, const float *din, float *dout,
+collide_bulk(const DevParams P, const uint32_t *__restrict__ map, const uint32_t *__restrict__ fluid_mask,
+             const uint32_t *__restrict__ wall_mask, const float *din, float *dout,
              float *__restrict__ orho, float *__restrict__ ovx, float *__restrict__ ovy,
              float *__restrict__ ovz, long long gi0, long long gi1) {
   const long long gi = gi0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gi >= gi1) return;
-  const uint32_t code = map[gi];
-  if ((code & P.tmask) != P.tid[SLF_NT_FLUID]) return;
+  bool is_wall = false;
+  if (MASKED) {
+    const uint32_t bit = 1u << (gi & 31);
+    const bool is_fluid = (fluid_mask[gi >> 5] & bit) != 0;
+    is_wall = (wall_mask[gi >> 5] & bit) != 0;
+    if (!is_fluid && !is_wall) return;
+  } else {
+    const uint32_t code = map[gi];
+    if ((code & P.tmask) != P.tid[SLF_NT_FLUID]) return;
+  }
+
+  // NTFullBBWall (boundary.mako:791-795: reflect, no relaxation, no macroscopic output).  In
+  // the AA pattern a node reads and writes the same Q addresses, and reflecting then storing
+  // "opposite slot, same node" (even) or "natural slot, downstream node" (odd) puts every
+  // value back where it was read from: a full-way bounce-back node is a no-op.
+  if (MASKED && is_wall && MODE != MODE_AB && P.prop) return;
 
   float f[L::Q];
-  load_node<L, MODE>(P, din, gi, f);
+  load_node<L, MODE, HINT>(P, din, gi, f);
+
+  if (MASKED && is_wall) {
+    if (!P.prop) {
+#pragma unroll
+      for (int i = 0; i < L::Q; i++) dout[gi + P.DS * i] = f[L::opp(i)];
+    } else {
+      // AB: the mask only admits walls whose every neighbour lies inside the array
+#pragma unroll
+      for (int i = 0; i < L::Q; i++) dout[gi + noff<L>(P, i) + P.DS * i] = f[L::opp(i)];
+    }
+    return;
+  }
 
   float rho, v[3];
   moments<L>(f, rho, v);
@@ -51,16 +84,16 @@ collide_bulk(const DevParams P, const uint32_t *__restrict__ map, const float *d
   }
   if (!P.prop) {
 #pragma unroll
-    for (int i = 0; i < L::Q; i++) dout[gi + P.DS * i] = f[i];
+    for (int i = 0; i < L::Q; i++) stp<HINT>(dout + (gi + P.DS * i), f[i]);
   } else if (MODE == MODE_AA_EVEN) {
 #pragma unroll
-    for (int i = 0; i < L::Q; i++) dout[gi + P.DS * L::opp(i)] = f[i];
+    for (int i = 0; i < L::Q; i++) stp<HINT>(dout + (gi + P.DS * L::opp(i)), f[i]);
   } else {
     // A fluid node is never on the outermost layer (that layer is always ghost,
     // subdomain.py:952-977), so every target is inside the array: the bounds tests of
     // propagation.mako:36-41 are vacuous here and live in the boundary kernel only.
 #pragma unroll
-    for (int i = 0; i < L::Q; i++) dout[gi + noff<L>(P, i) + P.DS * i] = f[i];
+    for (int i = 0; i < L::Q; i++) stp<HINT>(dout + (gi + noff<L>(P, i) + P.DS * i), f[i]);
   }
 }
 
@@ -72,16 +105,21 @@ __device__ __forceinline__ int edotn(int i, int n0, int n1, int n2) {
   return L::ex(i) * n0 + L::ey(i) * n1 + L::ez(i) * n2;
 }
 
-template <class L, int MODEL, int MODE, bool SAVE>
+// LISTED = true: `list[k]`, k in [gi0, gi1) are the indices of the nodes to process (built by
+// slf_plan_bind_map: every active node that the masked bulk kernel does not handle, sorted by
+// gi).  LISTED = false: scan the node range [gi0, gi1) and pick the non-fluid nodes.
+template <class L, int MODEL, int MODE, bool SAVE, bool LISTED>
 __global__ void __launch_bounds__(128)
-collide_boundary(const DevParams P, const uint32_t *__restrict__ map, const float *din, float *dout,
+collide_boundary(const DevParams P, const uint32_t *__restrict__ map, const uint32_t *__restrict__ list,
+                 const float *din, float *dout,
                  float *__restrict__ orho, float *__restrict__ ovx, float *__restrict__ ovy,
                  float *__restrict__ ovz, long long gi0, long long gi1) {
-  const long long gi = gi0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long gi = gi0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gi >= gi1) return;
+  if (LISTED) gi = list[gi];
   const uint32_t code = map[gi];
   const uint32_t type = code & P.tmask;
-  if (type == P.tid[SLF_NT_FLUID]) return;
+  if (!LISTED && type == P.tid[SLF_NT_FLUID]) return;
   const int cls = node_class<L>(P, type);
   if (cls < 0 || cls == SLF_NT_GHOST || cls == SLF_NT_UNUSED || cls == SLF_NT_PROPAGATION_ONLY) return;
   const int x = (int)(gi % P.ax);
@@ -183,7 +221,7 @@ collide_boundary(const DevParams P, const uint32_t *__restrict__ map, const floa
     }
   }
 
-  const bool wet = cls == SLF_NT_HALFBB_WALL || vel_bc || den_bc || cls == SLF_NT_DO_NOTHING;
+  const bool wet = cls == SLF_NT_FLUID || cls == SLF_NT_HALFBB_WALL || vel_bc || den_bc || cls == SLF_NT_DO_NOTHING;
   if (wet && P.relax) {
     if (MODEL == SLF_MRT) {
       if (cls == SLF_NT_EQUILIBRIUM_VELOCITY || cls == SLF_NT_EQUILIBRIUM_DENSITY) collide_mrt<L, true>(P, v, f);

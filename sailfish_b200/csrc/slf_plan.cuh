@@ -1,0 +1,46 @@
+// slf_plan.cuh -- host-side plan object and error plumbing shared by the translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "slf_kernels.cuh"
+
+int slf_fail(int code, const std::string &msg);
+void slf_count_launch();
+#define fail slf_fail
+#define CUDA_OK(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return slf_fail((int)e_, std::string(#expr) + ": " + cudaGetErrorString(e_));          \
+  } while (0)
+#define LAUNCH_OK(name)                                                                       \
+  do {                                                                                        \
+    cudaError_t e_ = cudaGetLastError();                                                      \
+    if (e_ != cudaSuccess) return slf_fail((int)e_, std::string(name) + ": " + cudaGetErrorString(e_)); \
+    slf_count_launch();                                                                       \
+  } while (0)
+
+struct SlfPlan {
+  SlfParams hp;
+  DevParams dp;
+  float *d_node_params = nullptr;
+  int Q = 0, D = 0;
+  // derived from a bound node map (slf_plan_bind_map)
+  uint64_t bound_map = 0;
+  uint32_t *d_fluid_mask = nullptr, *d_wall_mask = nullptr, *d_list = nullptr;
+  std::vector<long long> layer_off;    // list offsets per outermost-axis layer (size n + 1)
+};
+
+// one per lattice, each in its own translation unit (slf_collide_*.cu) so they build in parallel
+int slf_collide_d2q9(SlfPlan *pl, int model, int mode, bool save, const uint32_t *map, const float *din, float *dout,
+                     float *rho, float *vx, float *vy, float *vz, int z0, int z1, cudaStream_t s);
+int slf_collide_d3q19_bgk(SlfPlan *pl, int mode, bool save, const uint32_t *map, const float *din, float *dout,
+                          float *rho, float *vx, float *vy, float *vz, int z0, int z1, cudaStream_t s);
+int slf_collide_d3q19_mrt(SlfPlan *pl, int mode, bool save, const uint32_t *map, const float *din, float *dout,
+                          float *rho, float *vx, float *vy, float *vz, int z0, int z1, cudaStream_t s);
+int slf_collide_d3q27(SlfPlan *pl, int mode, bool save, const uint32_t *map, const float *din, float *dout,
+                      float *rho, float *vx, float *vy, float *vz, int z0, int z1, cudaStream_t s);

@@ -1,0 +1,44 @@
+"""Which planes cross a face, host-side statement (the device statement is
+sailfish_b200/csrc/slf_halo.cuh; tests check they agree).
+
+For subdomains split along the outermost axis a face message is, per population that
+crosses the face (sym.get_interblock_dists, sym.py:829-845), one whole plane of the SoA
+lattice.  Layer and slot selection follow the reference's collect/distribute kernels
+(kernel_utils.mako:526-794, subdomain_runner.py:488-510):
+
+  after an AB or AA-odd step  (with_swap=False): ghost layer, natural slots
+                                                 -> neighbour's first real layer
+  after an AA-even step       (with_swap=True) : first real layer, opposite slots
+                                                 -> neighbour's ghost layer
+"""
+import numpy as np
+
+
+def face_transfer(grid, face, with_swap, lat_n, peer_lat_n):
+    """Returns (slots, src_layer, dst_layer) for the local `face` (2*axis + high)."""
+    axis, hi = face // 2, face & 1
+    sgn = 1 if hi else -1
+    slots = [i for i, e in enumerate(grid.basis) if int(e[axis]) * sgn >= 1]
+    if with_swap:
+        slots = [int(grid.opposite[i]) for i in slots]
+        src = lat_n - 2 if hi else 1
+        dst = 0 if hi else peer_lat_n - 1
+    else:
+        src = lat_n - 1 if hi else 0
+        dst = 1 if hi else peer_lat_n - 2
+    return slots, src, dst
+
+
+def with_swap_for(access_pattern_aa, iteration_before_step):
+    """The AA in-place (even) step is followed by the WithSwap transfer."""
+    return bool(access_pattern_aa and (iteration_before_step & 1) == 0)
+
+
+def extract_planes(dist, slots, layer):
+    """dist: [Q, n_outer, ...] array view.  Returns a [len(slots), ...] copy."""
+    return np.stack([dist[s, layer] for s in slots])
+
+
+def insert_planes(dist, slots, layer, planes):
+    for k, s in enumerate(slots):
+        dist[s, layer] = planes[k]

@@ -50,6 +50,8 @@ class DeviceLattice(object):
         nbytes = self.Q * self.n * 4
         self.d_dist_a = self.be.alloc_buf(size=nbytes)
         self.d_dist_b = None if self.aa else self.be.alloc_buf(size=nbytes)
+        self.lib.call('slf_plan_bind_map', self.plan, int(self.d_map))
+        self.be._bound_map = int(self.d_map)
         self.iteration = 0
         self.stream = self.be.make_stream()
         self.set_initial_conditions()

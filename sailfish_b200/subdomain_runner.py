@@ -26,13 +26,13 @@ _u64 = ctypes.c_uint64
 class HaloLink(object):
     """One directed neighbour relation across the split axis.
 
-    ``peer_dist`` maps (iteration parity) -> neighbour's lattice base pointer as seen from
-    this process; ``peer_ready`` is the neighbour's semaphore this side signals after a push;
-    ``my_ready`` / ``my_consumed`` are the local semaphore the neighbour signals and its
-    consumption counter."""
+    Same process (several subdomains driven by one process, the reference's "several
+    subdomains per GPU" regtest mode): ``peer_runner`` is set and ordering uses CUDA events.
+    Other rank: the neighbour's lattice and semaphore are CUDA-IPC mappings and ordering uses
+    the stream-ordered device semaphores of slf_sem_signal / slf_sem_wait."""
 
-    def __init__(self, face, peer_dist_a, peer_dist_b, peer_lat_n, peer_arr_n, peer_ready,
-                 my_ready, my_consumed):
+    def __init__(self, face, peer_dist_a, peer_dist_b, peer_lat_n, peer_arr_n, peer_ready=0,
+                 my_ready=0, my_consumed=0, peer_runner=None):
         self.face = face
         self.peer_dist_a = int(peer_dist_a)
         self.peer_dist_b = int(peer_dist_b) if peer_dist_b else 0
@@ -41,6 +41,7 @@ class HaloLink(object):
         self.peer_ready = int(peer_ready)
         self.my_ready = int(my_ready)
         self.my_consumed = int(my_consumed)
+        self.peer_runner = peer_runner
 
 
 class LBOutput(object):
@@ -178,6 +179,8 @@ class SubdomainRunner(object):
         self._data_stream = self.backend.make_stream(high_priority=True)
         # semaphores: [ready_low, ready_high, consumed_low, consumed_high]
         self._sems = self.backend.alloc_buf(size=64)
+        self._push_events = [self.backend.make_event(self._data_stream), self.backend.make_event(self._data_stream)]
+        self._slab_event = self.backend.make_event(self._calc_stream)
 
     def initialize(self):
         self._init_fields()
@@ -221,6 +224,8 @@ class SubdomainRunner(object):
 
     # -- stepping ---------------------------------------------------------------------------------
     def step(self, sync_req):
+        """One time step: boundary slabs -> push planes to the neighbours (data stream) while the
+        interior is computed (calc stream) -> local PBC.  Cf. subdomain_runner.py:960-1058."""
         dev = self._dev
         it = dev.iteration
         swap = int(dev.aa and (it & 1) == 0)
@@ -232,48 +237,51 @@ class SubdomainRunner(object):
             dev.apply_pbc()
         else:
             cs, ds = self._calc_stream, self._data_stream
-            sp = self.sem_ptrs()
             if it > 0:
+                # the neighbours' planes of the previous step must have landed (and, symmetrically,
+                # the neighbours are done with the layers this step's push overwrites)
                 for side, link in links.items():
-                    self._lib.call('slf_sem_wait', link.my_ready, link.my_consumed, cs.handle)
+                    if link.peer_runner is not None:
+                        cs.wait_for_event(link.peer_runner._push_events[(it - 1) & 1])
+                    else:
+                        self._lib.call('slf_sem_wait', link.my_ready, link.my_consumed, cs.handle)
             if local_pbc:
-                # periodic x/y inside a z-split: the PBC kernels must see the whole step and
-                # run before the planes leave (they fix up the x/y ghost ring of those planes)
+                # periodic x/y inside a z-split: the PBC kernels need the whole step and must run
+                # before the planes leave (they complete the x/y ghost ring of those planes)
                 dev.collide(save_macro=sync_req, stream=cs)
                 dev.apply_pbc(stream=cs)
-                self._push_all(swap, cs)
+                self._push_all(swap, cs, it)
             else:
                 lo, hi = 1, n - 1
                 if 0 in links:
                     dev.collide(save_macro=sync_req, z_begin=1, z_end=2, stream=cs)
                     lo = 2
-                if 1 in links:
+                if 1 in links and n - 2 >= lo:
                     dev.collide(save_macro=sync_req, z_begin=n - 2, z_end=n - 1, stream=cs)
                     hi = n - 2
-                ev = self.backend.make_event(cs)
-                ds.wait_for_event(ev)
-                self._push_all(swap, ds)
+                self._slab_event.record(cs)
+                ds.wait_for_event(self._slab_event)
+                self._push_all(swap, ds, it)
                 if hi > lo:
                     dev.collide(save_macro=sync_req, z_begin=lo, z_end=hi, stream=cs)
-                ev2 = self.backend.make_event(ds)
-                cs.wait_for_event(ev2)
-            del sp
+                cs.wait_for_event(self._push_events[it & 1])
         dev.iteration += 1
         self._sim.iteration += 1
 
-    def _push_all(self, swap, stream):
+    def _push_all(self, swap, stream, it):
         dev = self._dev
         _, dout = dev.io_dists()
-        src = dout
         for side, link in self._links.items():
             if dev.aa:
                 peer = link.peer_dist_a
             else:
                 # the neighbour's output lattice of this step has the same parity as ours
-                peer = link.peer_dist_b if (dev.iteration & 1) == 0 else link.peer_dist_a
-            self._lib.call('slf_halo_push', dev.plan, int(src), link.face, peer, link.peer_lat_n,
+                peer = link.peer_dist_b if (it & 1) == 0 else link.peer_dist_a
+            self._lib.call('slf_halo_push', dev.plan, int(dout), link.face, peer, link.peer_lat_n,
                            link.peer_arr_n, swap, stream.handle)
-            self._lib.call('slf_sem_signal', link.peer_ready, stream.handle)
+            if link.peer_runner is None:
+                self._lib.call('slf_sem_signal', link.peer_ready, stream.handle)
+        self._push_events[it & 1].record(stream)
 
     def _fields_to_host(self):
         self._dev.fields_to_host()

@@ -1,0 +1,66 @@
+"""Several subdomains on one GPU, driven by one process through the public controller: the
+peer-to-peer plane pushes (slf_halo_push) and the slab scheduling of SubdomainRunner.step must
+reproduce the single-subdomain GPU run (the reference's regtest/subdomains bar: 6 decimals) and
+agree with the oracle."""
+import numpy as np
+import pytest
+
+import multi_util
+from sailfish_b200.geo import EqualSubdomainsGeometry2D, EqualSubdomainsGeometry3D
+from sailfish_b200.examples import ldc_2d, ldc_3d, poiseuille_3d
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    'ldc3d': (ldc_3d.LDCSim, EqualSubdomainsGeometry3D, ['--lat_nx=20', '--lat_ny=18', '--lat_nz=30', '--visc=0.04'], 3),
+    'ldc3d_mrt': (ldc_3d.LDCSim, EqualSubdomainsGeometry3D,
+                  ['--lat_nx=20', '--lat_ny=18', '--lat_nz=24', '--visc=0.04', '--model=mrt'], 2),
+    'ldc2d': (ldc_2d.LDCSim, EqualSubdomainsGeometry2D, ['--lat_nx=24', '--lat_ny=22', '--visc=0.05'], 2),
+    'poi3d_force_z': (poiseuille_3d.PoiseuilleSim, EqualSubdomainsGeometry3D,
+                      ['--lat_nx=14', '--lat_ny=14', '--lat_nz=16', '--flow_direction=z', '--drive=force'], 2),
+    'poi3d_force_x': (poiseuille_3d.PoiseuilleSim, EqualSubdomainsGeometry3D,
+                      ['--lat_nx=16', '--lat_ny=12', '--lat_nz=18', '--flow_direction=x', '--drive=force'], 3),
+    'poi3d_press_z': (poiseuille_3d.PoiseuilleSim, EqualSubdomainsGeometry3D,
+                      ['--lat_nx=12', '--lat_ny=12', '--lat_nz=24', '--flow_direction=z', '--drive=pressure',
+                       '--stationary', '--model=mrt'], 4),
+}
+
+
+def gpu_run(cls, geo, args, steps):
+    from sailfish_b200.controller import LBSimulationController
+    ctrl = LBSimulationController(cls, geo)
+    ctrl.setup(args + ['--quiet'])
+    for k in range(steps):
+        for r in ctrl.runners:
+            r.step(k == steps - 1)
+    ctrl.sync()
+    dim = ctrl.dim
+    pieces = []
+    for r in ctrl.runners:
+        r._fields_to_host()
+        sl = r._spec._nonghost_slice
+        f = [np.array(r.field_base(r._sim.rho))[sl]] + [np.array(r.field_base(c))[sl] for c in r._sim.v]
+        pieces.append((r._spec.location[dim - 1], f))
+    pieces.sort(key=lambda t: t[0])
+    return [np.concatenate([p[1][k] for p in pieces], axis=0) for k in range(1 + dim)]
+
+
+@pytest.mark.parametrize('name', sorted(CASES))
+@pytest.mark.parametrize('ap', ['AB', 'AA'])
+def test_gpu_n_subdomains_equal_one(oracle, name, ap):
+    cls, geo, args, n = CASES[name]
+    steps = 11
+    args = args + ['--access_pattern=' + ap]
+    one = gpu_run(cls, geo, args + ['--subdomains=1'], steps)
+    many = gpu_run(cls, geo, args + ['--subdomains=%d' % n], steps)
+    _, parts = multi_util.build_case(cls, geo, args + ['--subdomains=1'])
+    wet = parts[0]['sd'].fluid_map()
+    ref = multi_util.run_local(oracle, parts, steps, dtype=np.float64)
+    dim = parts[0]['spec'].dim
+    refs = [multi_util.merge_field(parts, ref, lambda s: s.o.rho, dim)] + \
+           [multi_util.merge_field(parts, ref, (lambda d: (lambda s: s.o.v[d]))(d), dim) for d in range(dim)]
+    for a, b, c in zip(one, many, refs):
+        # identical kernels on identical data: the split run must match the single run bit for bit
+        assert np.array_equal(a[wet], b[wet]), np.abs(a[wet] - b[wet]).max()
+        scale = max(1e-30, np.abs(c[wet]).max())
+        assert np.abs(b[wet] - c[wet]).max() / scale < 2e-5

@@ -135,5 +135,44 @@ def main(what):
         np.savez_compressed(os.path.join(GOLD, 'steps_%s.npz' % name), **out)
 
 
+
+
+
+def gen_split_geometry():
+    """Encoded maps of every subdomain of z-split runs (geometry only): pins the mirror's
+    ghost / orientation handling at connected faces (subdomain.py:978-1005)."""
+    from sailfish.geo import EqualSubdomainsGeometry3D, EqualSubdomainsGeometry2D
+    ldc3 = ref_harness.load_example('examples/ldc_3d.py').LDCSim
+    ldc2 = ref_harness.load_example('examples/ldc_2d.py').LDCSim
+    poi3 = ref_harness.load_example('examples/poiseuille_3d.py').PoiseuilleSim
+    cases = [
+        ('split_ldc3d_z3', ldc3, EqualSubdomainsGeometry3D,
+         ['--lat_nx=10', '--lat_ny=9', '--lat_nz=14', '--subdomains=3', '--conn_axis=z', '--access_pattern=AA']),
+        ('split_ldc2d_y2', ldc2, EqualSubdomainsGeometry2D,
+         ['--lat_nx=12', '--lat_ny=11', '--subdomains=2', '--conn_axis=y', '--access_pattern=AA']),
+        ('split_poi3d_z2', poi3, EqualSubdomainsGeometry3D,
+         ['--grid=D3Q19', '--lat_nx=10', '--lat_ny=10', '--lat_nz=12', '--flow_direction=z', '--drive=force',
+          '--subdomains=2', '--conn_axis=z', '--access_pattern=AA']),
+    ]
+    for name, cls, geo, args in cases:
+        cfg, runners = ref_harness.make_runners(cls, geo, args=args)
+        out = {'n': np.int32(len(runners))}
+        for i, r in enumerate(runners):
+            ctx = ref_harness.context_of(r)
+            pk = pack_ctx(ctx)
+            for k, v in pk.items():
+                out['%s_%d' % (k, i)] = v
+            out['map_%d' % i] = r._subdomain.encoded_map().astype(np.uint32)
+            out['location_%d' % i] = np.array(r._spec.location)
+            out['size_%d' % i] = np.array(r._spec.size)
+            out['fluid_map_%d' % i] = r._subdomain.fluid_map()
+        np.savez_compressed(os.path.join(GOLD, 'geometry_%s.npz' % name), **out)
+        print('geometry_%s.npz' % name, [tuple(out['size_%d' % i]) for i in range(len(runners))])
+
+
 if __name__ == '__main__':
-    main(sys.argv[1:] or ['geometry', 'steps'])
+    what = sys.argv[1:] or ['geometry', 'steps', 'split']
+    if 'geometry' in what or 'steps' in what:
+        main(what)
+    if 'split' in what:
+        gen_split_geometry()
