@@ -386,6 +386,10 @@ __device__ __forceinline__ bool pbc_corner(int axis, int i, const int (&per)[3],
   return false;
 }
 
+__device__ __forceinline__ void set3(int a, int v, int &x, int &y, int &z) {
+  if (a == 0) x = v; else if (a == 1) y = v; else z = v;
+}
+
 template <class L, bool SWAP>
 __global__ void __launch_bounds__(128)
 apply_pbc(const DevParams P, float *dist, int axis, int per0, int per1, int per2) {
@@ -394,22 +398,27 @@ apply_pbc(const DevParams P, float *dist, int axis, int per0, int per1, int per2
   int oth[2];
   if (L::D == 2) { oth[0] = 1 - axis; oth[1] = 2; }
   else { oth[0] = axis == 0 ? 1 : 0; oth[1] = axis == 2 ? 1 : 2; }
-  const int n1 = lim[oth[0]], n2 = L::D == 3 ? lim[oth[1]] : 1;
+  const int n1 = oth[0] == 0 ? P.nx : P.ny, n2 = L::D == 3 ? (oth[1] == 1 ? P.ny : P.nz) : 1;
   const int i1 = blockIdx.x * blockDim.x + threadIdx.x, i2 = blockIdx.y;
   if (i1 >= n1 || i2 >= n2) return;
   const int idx[2] = {i1, i2};
-  const int maxd[2] = {lim[oth[0]] - 2, L::D == 3 ? lim[oth[1]] - 2 : 0};
-  if (SWAP && L::D == 3) { if (i1 >= lim[oth[0]] - 1 || i2 >= lim[oth[1]] - 1 || i1 < 1 || i2 < 1) return; }
+  const int maxd[2] = {n1 - 2, L::D == 3 ? n2 - 2 : 0};
+  if (SWAP && L::D == 3) { if (i1 >= n1 - 1 || i2 >= n2 - 1 || i1 < 1 || i2 < 1) return; }
   const long long stride = axis == 0 ? 1 : (axis == 1 ? P.sy : P.sz);
   const long long offset = SWAP ? -stride : stride;
-  int cl[3] = {0, 0, 0}, ch[3] = {0, 0, 0};
-  cl[oth[0]] = ch[oth[0]] = i1;
-  if (L::D == 3) cl[oth[1]] = ch[oth[1]] = i2;
-  cl[axis] = SWAP ? 1 : 0;
-  ch[axis] = SWAP ? lim[axis] - 1 : lim[axis] - 2;
-  const long long gi_low = gidx3<L>(P, cl[0], cl[1], cl[2]), gi_high = gidx3<L>(P, ch[0], ch[1], ch[2]);
+  // (explicit selects instead of run-time indexed local arrays: the latter were miscompiled
+  //  for the 2-D instantiation -- gi_low came out equal to gi_high)
+  int lx = 0, ly = 0, lz = 0, hx = 0, hy = 0, hz = 0;
+  set3(oth[0], i1, lx, ly, lz); set3(oth[0], i1, hx, hy, hz);
+  if (L::D == 3) { set3(oth[1], i2, lx, ly, lz); set3(oth[1], i2, hx, hy, hz); }
+  set3(axis, SWAP ? 1 : 0, lx, ly, lz);
+  set3(axis, SWAP ? lim[axis] - 1 : lim[axis] - 2, hx, hy, hz);
+  const long long gi_low = gidx3<L>(P, lx, ly, lz), gi_high = gidx3<L>(P, hx, hy, hz);
   float val[L::Q];
-  const int ea_tab[3] = {0, 0, 0}; (void)ea_tab;
+#ifdef SLF_DEBUG_PBC
+  if (i1 == 3 && i2 == 0) printf("pbc D=%d swap=%d axis=%d n1=%d n2=%d oth=%d,%d gi_low=%lld gi_high=%lld off=%lld DS=%lld lim=%d,%d,%d\n",
+      L::D, (int)SWAP, axis, n1, n2, oth[0], oth[1], gi_low, gi_high, offset, P.DS, lim[0], lim[1], lim[2]);
+#endif
   // low -> high
 #pragma unroll
   for (int i = 1; i < L::Q; i++) {
@@ -433,6 +442,9 @@ apply_pbc(const DevParams P, float *dist, int axis, int per0, int per1, int per2
           dist[gidx3<L>(P, tgt[0], tgt[1], tgt[2]) + P.DS * j] = fv;
       }
     } else {
+#ifdef SLF_DEBUG_PBC
+      if (i1 == 3 && i2 == 0) printf("  l2h i=%d j=%d fv=%f -> %lld\n", i, j, fv, gi_high + P.DS * j);
+#endif
       dist[gi_high + P.DS * j] = fv;
     }
   }

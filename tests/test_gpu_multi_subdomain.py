@@ -59,8 +59,15 @@ def test_gpu_n_subdomains_equal_one(oracle, name, ap):
     dim = parts[0]['spec'].dim
     refs = [multi_util.merge_field(parts, ref, lambda s: s.o.rho, dim)] + \
            [multi_util.merge_field(parts, ref, (lambda d: (lambda s: s.o.v[d]))(d), dim) for d in range(dim)]
-    for a, b, c in zip(one, many, refs):
+    ref32 = multi_util.run_local(oracle, parts, steps, dtype=np.float32)
+    refs32 = [multi_util.merge_field(parts, ref32, lambda s: s.o.rho, dim)] + \
+             [multi_util.merge_field(parts, ref32, (lambda d: (lambda s: s.o.v[d]))(d), dim) for d in range(dim)]
+    vscale = max(1e-30, max(np.abs(c[wet]).max() for c in refs[1:]))
+    for k, (a, b, c, c32) in enumerate(zip(one, many, refs, refs32)):
         # identical kernels on identical data: the split run must match the single run bit for bit
         assert np.array_equal(a[wet], b[wet]), np.abs(a[wet] - b[wet]).max()
-        scale = max(1e-30, np.abs(c[wet]).max())
-        assert np.abs(b[wet] - c[wet]).max() / scale < 2e-5
+        # and stay inside the fp32 round-off envelope of the reference arithmetic (fp32 oracle vs fp64)
+        scale = np.abs(c[wet]).max() if k == 0 else vscale      # ||.||_inf of rho, resp. of the velocity field
+        err = np.abs(b[wet] - c[wet]).max() / scale
+        env = np.abs(c32[wet] - c[wet]).max() / scale
+        assert err <= 2.0 * env + 1e-6, (k, err, env)

@@ -1,0 +1,104 @@
+"""Bit-exact checks of the data-movement kernels against the oracle on random lattices:
+ApplyPeriodicBoundaryConditions[WithSwap], Collect/DistributeContinuousData[WithSwap] and the
+peer-to-peer plane push (vs sailfish_b200.halo.face_transfer)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import util
+from sailfish_b200 import halo, lattice
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(case):
+    from sailfish_b200.runtime import DeviceLattice
+    c = util.load_case(case)
+    p = util.params_from_case(c)
+    return c, p, DeviceLattice(p, c['map'], c['rho0'], c['v0'])
+
+
+@pytest.mark.parametrize('case', ['box2d_bgk_AA', 'box3d_bgk_AA', 'box3d_q27_AA', 'poi3d_force_bgk_AA'])
+@pytest.mark.parametrize('swap', [0, 1])
+def test_pbc_kernels_bit_exact(oracle, case, swap):
+    c, p, dev = _dev(case)
+    rng = np.random.RandomState(7)
+    shape = (p.Q,) + c['map'].shape
+    d0 = rng.rand(*shape).astype(np.float32)
+    # sprinkle non-finite values: they must never be copied (kernel_utils.mako isfinite tests)
+    d0[rng.rand(*shape) < 0.02] = np.inf
+    for axis in range(p.dim):
+        if not p.periodic[axis]:
+            continue
+        dev.set_dist(d0)
+        dev.lib.call('slf_apply_periodic_boundary_conditions', dev.plan, int(dev.d_dist_a), axis, swap,
+                     dev.stream.handle)
+        g = dev.get_dist()
+        o = d0.copy().reshape(-1)
+        oracle.apply_pbc(p, o, axis, bool(swap))
+        o = o.reshape(shape)
+        same = (g == o) | (np.isnan(g) & np.isnan(o))
+        assert same.all(), (axis, np.argwhere(~same)[:10].tolist())
+
+
+@pytest.mark.parametrize('case', ['ldc2d_bgk_AA', 'ldc3d_bgk_AA', 'ldc3d_q27_AA'])
+@pytest.mark.parametrize('swap', [0, 1])
+def test_collect_distribute_bit_exact(oracle, case, swap):
+    c, p, dev = _dev(case)
+    rng = np.random.RandomState(11)
+    shape = (p.Q,) + c['map'].shape
+    d0 = rng.rand(*shape).astype(np.float32)
+    lat = [int(x) for x in c['lat']]
+    L = lattice.get(str(c['grid']))
+    for face in range(2, 2 * p.dim):
+        ndists = len(L.get_interblock_dists([(1 if face & 1 else -1) if a == face // 2 else 0 for a in range(p.dim)]))
+        max_lx = lat[0] - 2
+        max_other = 1 if p.dim == 2 else (lat[2] - 2 if face // 2 == 1 else lat[1] - 2)
+        nbuf = ndists * max_other * max_lx
+        dev.set_dist(d0)
+        dbuf = dev.be.alloc_buf(size=nbuf * 4)
+        dev.lib.call('slf_collect_continuous_data', dev.plan, int(dev.d_dist_a), face, 1, 1, max_lx, max_other,
+                     int(dbuf), swap, dev.stream.handle)
+        dev.sync()
+        gbuf = np.zeros(nbuf, np.float32)
+        dev.lib.call('slf_memcpy_d2h', gbuf.ctypes.data_as(ctypes.c_void_p), int(dbuf), nbuf * 4)
+        obuf = np.zeros(nbuf, np.float32)
+        oracle.collect(p, d0.reshape(-1), face, 1, 1, max_lx, max_other, obuf, bool(swap))
+        assert np.array_equal(gbuf, obuf), face
+        # distribute a fresh random buffer
+        src = rng.rand(nbuf).astype(np.float32)
+        dev.lib.call('slf_memcpy_h2d', int(dbuf), src.ctypes.data_as(ctypes.c_void_p), nbuf * 4)
+        dev.lib.call('slf_distribute_continuous_data', dev.plan, int(dev.d_dist_a), face, 1, 1, max_lx, max_other,
+                     int(dbuf), swap, dev.stream.handle)
+        g = dev.get_dist()
+        o = d0.copy().reshape(-1)
+        oracle.distribute(p, o, face, 1, 1, max_lx, max_other, src, bool(swap))
+        assert np.array_equal(g, o.reshape(shape)), face
+
+
+@pytest.mark.parametrize('case', ['ldc2d_bgk_AA', 'ldc3d_bgk_AA', 'ldc3d_q27_AA'])
+@pytest.mark.parametrize('swap', [0, 1])
+def test_halo_push_matches_host_statement(case, swap):
+    """slf_halo_push (device statement) == sailfish_b200.halo.face_transfer (host statement)."""
+    c, p, dev = _dev(case)
+    rng = np.random.RandomState(13)
+    shape = (p.Q,) + c['map'].shape
+    src = rng.rand(*shape).astype(np.float32)
+    L = lattice.get(str(c['grid']))
+    outer = shape[1]
+    peer = dev.be.alloc_buf(size=src.nbytes)
+    for side in (0, 1):
+        face = 2 * (p.dim - 1) + side
+        dst0 = rng.rand(*shape).astype(np.float32)
+        dev.set_dist(src)
+        dev.lib.call('slf_memcpy_h2d', int(peer), dst0.ctypes.data_as(ctypes.c_void_p), dst0.nbytes)
+        dev.lib.call('slf_halo_push', dev.plan, int(dev.d_dist_a), face, int(peer), outer, outer, swap,
+                     dev.stream.handle)
+        dev.sync()
+        got = np.zeros_like(dst0)
+        dev.lib.call('slf_memcpy_d2h', got.ctypes.data_as(ctypes.c_void_p), int(peer), got.nbytes)
+        slots, s_layer, d_layer = halo.face_transfer(L, face, bool(swap), outer, outer)
+        want = dst0.copy()
+        halo.insert_planes(want, slots, d_layer, halo.extract_planes(src, slots, s_layer))
+        assert np.array_equal(got, want), (face, swap)
