@@ -23,17 +23,26 @@ static int launch_collide(SlfPlan *pl, const uint32_t *map, const float *din, fl
   if (n <= 0) return 0;
   const bool bound = pl->bound_map != 0 && pl->bound_map == (uint64_t)map;
   {
-    // 128-thread blocks and streaming (.cs) loads/stores measured best on B200
-    // (profiles/r01_sweep_blocksize_hint.txt); SLF_BULK_BS overrides the block size.
-    static const int bs = slf_env_int("SLF_BULK_BS", 128);
+    const int bs = 128;
     const long long nb = (n + bs - 1) / bs;
-    if (bound)
-      collide_bulk<L, MODEL, MODE, SAVE, true, SLF_HINT><<<(unsigned)nb, bs, 0, s>>>(
-          pl->dp, map, pl->d_fluid_mask, pl->d_wall_mask, din, dout, rho, vx, vy, vz, gi0, gi1);
-    else
-      collide_bulk<L, MODEL, MODE, SAVE, false, SLF_HINT><<<(unsigned)nb, bs, 0, s>>>(
-          pl->dp, map, nullptr, nullptr, din, dout, rho, vx, vy, vz, gi0, gi1);
-    LAUNCH_OK("collide_bulk");
+    const bool plain = bound && pl->dp.relax && pl->dp.prop;
+    if constexpr (MODE != MODE_AB) {
+      if (plain) {
+        float *dist = dout;      // AA: dist_in == dist_out (checked by the caller)
+        collide_bulk_aa<L, MODEL, MODE, SAVE><<<(unsigned)nb, bs, 0, s>>>(
+            pl->dp, pl->d_fluid_mask, dist, rho, vx, vy, vz, gi0, gi1);
+        LAUNCH_OK("collide_bulk_aa");
+      }
+    }
+    if (MODE == MODE_AB || !plain) {
+      if (bound)
+        collide_bulk<L, MODEL, MODE, SAVE, true><<<(unsigned)nb, bs, 0, s>>>(
+            pl->dp, map, pl->d_fluid_mask, pl->d_wall_mask, din, dout, rho, vx, vy, vz, gi0, gi1);
+      else
+        collide_bulk<L, MODEL, MODE, SAVE, false><<<(unsigned)nb, bs, 0, s>>>(
+            pl->dp, map, nullptr, nullptr, din, dout, rho, vx, vy, vz, gi0, gi1);
+      LAUNCH_OK("collide_bulk");
+    }
   }
   {
     const int bs = 128;

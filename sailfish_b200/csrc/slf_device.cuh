@@ -88,17 +88,19 @@ __device__ __forceinline__ void equilibrium(float rho, const float (&v)[3], floa
 }
 
 // ---- collision operators ---------------------------------------------------------------
-template <class L>
+// FORCED: 0 / 1 fix the presence of a body force at compile time, -1 reads P.forced.
+template <class L, int FORCED = -1>
 __device__ __forceinline__ void collide_bgk(const DevParams &P, float rho, float (&v)[3], float (&f)[L::Q]) {
+  const bool forced = FORCED < 0 ? (P.forced != 0) : (FORCED != 0);
   float v0[3] = {v[0], v[1], v[2]};
-  if (P.forced) {
+  if (forced) {
 #pragma unroll
     for (int d = 0; d < L::D; d++) v0[d] = fmaf(0.5f, P.a[d], v[d]);
   }
   const float vv = v0[0] * v0[0] + v0[1] * v0[1] + (L::D == 3 ? v0[2] * v0[2] : 0.f);
   const float base = fmaf(-1.5f, vv, 1.0f);
   const float omega = P.omega;
-  if (!P.forced) {
+  if (!forced) {
 #pragma unroll
     for (int i = 0; i < L::Q; i++) {
       const float ev = edotv<L>(i, v0);
@@ -129,9 +131,10 @@ __device__ __forceinline__ void collide_bgk(const DevParams &P, float rho, float
 // change of each moment goes through the back-transform, so its round-off scales with the
 // change rather than with the populations (closer to the exact result than transforming the
 // full moment vector; the parity tests measure both against the fp64 oracle).
-template <class L, bool EQ_NODE>
+template <class L, bool EQ_NODE, int FORCED = -1>
 __device__ __forceinline__ void collide_mrt(const DevParams &P, float (&v)[3], float (&f)[L::Q]) {
   if constexpr (L::HAS_MRT) {
+    const bool forced = FORCED < 0 ? (P.forced != 0) : (FORCED != 0);
     float m[L::Q];
 #pragma unroll
     for (int k = 0; k < L::Q; k++) {
@@ -146,7 +149,7 @@ __device__ __forceinline__ void collide_mrt(const DevParams &P, float (&v)[3], f
       m[k] = s;
     }
     constexpr int IZ = L::I_MZ < 0 ? 0 : L::I_MZ;
-    if (P.forced) {                               // fluid_momentum, relaxation_mrt.mako:11-28
+    if (forced) {                                 // fluid_momentum, relaxation_mrt.mako:11-28
       m[L::I_MX] = fmaf(0.5f, P.a[0], m[L::I_MX]);
       m[L::I_MY] = fmaf(0.5f, P.a[1], m[L::I_MY]);
       if (L::D == 3) m[IZ] = fmaf(0.5f, P.a[2], m[IZ]);
@@ -183,7 +186,7 @@ __device__ __forceinline__ void collide_mrt(const DevParams &P, float (&v)[3], f
         dm[k] = 0.f;
       }
     }
-    if (P.forced) {
+    if (forced) {
       // both half-steps of fluid_momentum add a/2 to the (conserved) momentum moments
       dm[L::I_MX] = P.a[0] * L::mnorm_inv(L::I_MX);
       dm[L::I_MY] = P.a[1] * L::mnorm_inv(L::I_MY);

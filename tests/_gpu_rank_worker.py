@@ -1,0 +1,75 @@
+"""torchrun worker: rank r owns subdomain r on GPU r (the production process model), halo planes
+travel GPU-to-GPU through CUDA-IPC mappings ordered by device semaphores.  Rank 0 then repeats
+the run as a single subdomain and checks bit-identity of the merged fields."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+from sailfish_b200.controller import LBSimulationController  # noqa: E402
+from sailfish_b200.geo import EqualSubdomainsGeometry3D  # noqa: E402
+from sailfish_b200.examples import ldc_3d, poiseuille_3d  # noqa: E402
+
+CASES = {
+    'ldc3d': (ldc_3d.LDCSim, ['--lat_nx=40', '--lat_ny=36', '--lat_nz=64', '--visc=0.04']),
+    'poi3d_force_z': (poiseuille_3d.PoiseuilleSim,
+                      ['--lat_nx=20', '--lat_ny=20', '--lat_nz=32', '--flow_direction=z', '--drive=force']),
+    'poi3d_force_x': (poiseuille_3d.PoiseuilleSim,
+                      ['--lat_nx=24', '--lat_ny=20', '--lat_nz=32', '--flow_direction=x', '--drive=force']),
+}
+
+
+def run(cls, args, steps, single=False):
+    ctrl = LBSimulationController(cls, EqualSubdomainsGeometry3D)
+    if single:
+        saved = {k: os.environ.pop(k) for k in ('WORLD_SIZE', 'RANK') if k in os.environ}
+        os.environ['WORLD_SIZE'] = '1'
+    ctrl.setup(args + ['--quiet'])
+    if single:
+        os.environ.update(saved)
+    for k in range(steps):
+        for r in ctrl.runners:
+            r.step(k == steps - 1)
+    ctrl.sync()
+    out = []
+    for r in ctrl.runners:
+        r._fields_to_host()
+        sl = r._spec._nonghost_slice
+        out.append((r._spec.location[2], np.array([np.array(r.field_base(r._sim.rho))[sl]] +
+                                                   [np.array(r.field_base(c))[sl] for c in r._sim.v])))
+    return out
+
+
+def main():
+    name, ap = sys.argv[1], sys.argv[2]
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group('cpu:gloo,cuda:nccl', device_id=torch.device('cuda', local_rank))
+    rank, ws = dist.get_rank(), dist.get_world_size()
+    cls, args = CASES[name]
+    args = args + ['--access_pattern=' + ap]
+    steps = 21
+    mine = run(cls, args + ['--subdomains=%d' % ws], steps)
+    gathered = [None] * ws
+    dist.all_gather_object(gathered, mine[0])
+    ok = True
+    if rank == 0:
+        gathered.sort(key=lambda t: t[0])
+        merged = np.concatenate([g[1] for g in gathered], axis=1)
+        one = run(cls, args + ['--subdomains=1'], steps, single=True)[0][1]
+        finite = np.isfinite(one)
+        ok = bool(np.array_equal(merged[finite], one[finite])) and bool((np.isfinite(merged) == finite).all())
+        print('RESULT', name, ap, 'ranks', ws, 'bit-identical' if ok else 'MISMATCH max %g' % np.nanmax(np.abs(merged - one)))
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == '__main__':
+    main()

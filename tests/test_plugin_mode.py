@@ -1,0 +1,80 @@
+"""Drop-in check: the UNMODIFIED reference (controller -> master -> SubdomainRunner.run, its own
+examples, its own output writer) runs on ``--backends=b200`` through sailfish_b200.plugin.
+
+The build container has the reference but no GPU (and the GPU box has no reference), so the
+device behind the C ABI is replaced here by tests/fake_device.py (host memory + the CPU oracle).
+What this pins is everything between the reference and the C entry points: backend duck type,
+kernel-name/argument mapping (lb_single.py:72-185), iteration patching (backend_cuda.py:128-130),
+AA/AB lattice selection, PBC kernel variants and the "file N holds step N's pre-collision
+moments" convention.  The .npz files the reference writes must match the golden vectors.
+Skipped where /root/reference does not exist."""
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import util
+
+REF = os.environ.get('SAILFISH_REFERENCE', '/root/reference')
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'sailfish')),
+                                reason='reference tree not available')
+
+CASES = {
+    'ldc3d_bgk': ('examples/ldc_3d.py', 'LDCSim', None,
+                  ['--lat_nx=12', '--lat_ny=10', '--lat_nz=11', '--visc=0.04'], 20),
+    'ldc3d_mrt': ('examples/ldc_3d.py', 'LDCSim', None,
+                  ['--lat_nx=12', '--lat_ny=10', '--lat_nz=11', '--visc=0.04', '--model=mrt'], 20),
+    'ldc2d_bgk': ('examples/ldc_2d.py', 'LDCSim', None, ['--lat_nx=16', '--lat_ny=14', '--visc=0.05'], 20),
+    'poi3d_force_bgk': ('examples/poiseuille_3d.py', 'PoiseuilleSim', 'EqualSubdomainsGeometry3D',
+                        ['--grid=D3Q19', '--lat_nx=14', '--lat_ny=12', '--lat_nz=12', '--flow_direction=x',
+                         '--drive=force', '--visc=0.1'], 20),
+    'poi3d_press_mrt': ('examples/poiseuille_3d.py', 'PoiseuilleSim', 'EqualSubdomainsGeometry3D',
+                        ['--grid=D3Q19', '--lat_nx=12', '--lat_ny=12', '--lat_nz=16', '--flow_direction=z',
+                         '--drive=pressure', '--stationary', '--model=mrt', '--visc=0.1'], 20),
+    'box3d_bgk': None,   # needs a custom class, see below
+}
+
+
+@pytest.fixture(scope='module')
+def reference():
+    from sailfish_b200 import plugin
+    plugin.install(REF)
+    sys.path.insert(0, os.path.join(util.ROOT, 'tools'))
+    import ref_harness
+    return ref_harness
+
+
+@pytest.mark.parametrize('name', [k for k, v in CASES.items() if v is not None])
+@pytest.mark.parametrize('ap', ['AB', 'AA'])
+def test_reference_runs_on_b200_backend(reference, oracle, monkeypatch, tmp_path, name, ap):
+    import fake_device
+    fake = fake_device.install_fake(monkeypatch)
+    script, cls_name, geo_name, args, steps = CASES[name]
+    mod = reference.load_example(script)
+    from sailfish.controller import LBSimulationController
+    from sailfish import geo
+    out = str(tmp_path / 'out')
+    argv = [script] + args + ['--access_pattern=' + ap, '--backends=b200', '--debug_single_process',
+                              '--max_iters=%d' % steps, '--every=%d' % steps, '--output=' + out, '--quiet']
+    monkeypatch.setattr(sys, 'argv', argv)
+    ctrl = LBSimulationController(getattr(mod, cls_name), getattr(geo, geo_name) if geo_name else None)
+    ctrl.run()
+    assert 'slf_collide_and_propagate' in fake.calls and 'slf_set_initial_conditions' in fake.calls
+    files = sorted(glob.glob(out + '.0.*%d.npz' % steps))
+    assert files, glob.glob(out + '*')
+    res = np.load(files[-1])
+    c = util.load_case(name + '_' + ap)
+    m = util.real_mask(c)
+    wet = c['fluid_map']
+    rho = c['rho'][m].reshape(res['rho'].shape)
+    assert np.isnan(res['rho'][~wet]).all()          # io.py:53-59 masks non-fluid nodes
+    err = np.abs(res['rho'][wet] - rho[wet]).max() / np.abs(rho[wet]).max()
+    assert err < 5e-6, err
+    vscale = max(np.abs(c['v'][d][m].reshape(rho.shape)[wet]).max() for d in range(res['v'].shape[0]))
+    for d in range(res['v'].shape[0]):
+        v = c['v'][d][m].reshape(rho.shape)
+        assert np.abs(res['v'][d][wet] - v[wet]).max() / vscale < 5e-5
+    if c['periodic'].any():
+        assert 'slf_apply_periodic_boundary_conditions' in fake.calls
