@@ -319,6 +319,56 @@ static inline int in_bounds_target(const Ctx *C, const int *e, int x, int y, int
   return 1;
 }
 
+/* Plain fluid node, BGK, no body force: the same operations as the generic path below
+ * (getDist -> standard getMacro -> BGK_relaxate0 -> propagate) with the lattice tables as
+ * compile-time constants so that gcc unrolls and vectorises.  Used for the CPU baseline; the
+ * golden tests run through it as well (it is bit-identical to the generic path by construction:
+ * same expressions, same order). */
+static const REAL W_D2Q9[9] = {(REAL)(4.0/9), (REAL)(1.0/9), (REAL)(1.0/9), (REAL)(1.0/9), (REAL)(1.0/9),
+                               (REAL)(1.0/36), (REAL)(1.0/36), (REAL)(1.0/36), (REAL)(1.0/36)};
+static const REAL W_D3Q19[19] = {(REAL)(1.0/3), (REAL)(1.0/18), (REAL)(1.0/18), (REAL)(1.0/18), (REAL)(1.0/18), (REAL)(1.0/18), (REAL)(1.0/18),
+                                 (REAL)(1.0/36), (REAL)(1.0/36), (REAL)(1.0/36), (REAL)(1.0/36), (REAL)(1.0/36), (REAL)(1.0/36),
+                                 (REAL)(1.0/36), (REAL)(1.0/36), (REAL)(1.0/36), (REAL)(1.0/36), (REAL)(1.0/36), (REAL)(1.0/36)};
+static const int OPP_D2Q9[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+static const int OPP_D3Q19[19] = {0, 2, 1, 4, 3, 6, 5, 10, 9, 8, 7, 14, 13, 12, 11, 18, 17, 16, 15};
+
+static inline __attribute__((always_inline)) void fluid_bgk_node(
+    const int Q, const int D, const int (*E)[3], const REAL *W, const int *OPP, const long long *off,
+    const long long DS, const long long gi, const REAL *din, REAL *dout, const int odd, const int aa,
+    const REAL omega, const int save, REAL *orho, REAL **ov) {
+  REAL f[MAXQ];
+#pragma GCC unroll 27
+  for (int i = 0; i < Q; i++) f[i] = odd ? din[gi - off[i] + DS * OPP[i]] : din[gi + DS * i];
+  REAL rho = 0;
+#pragma GCC unroll 27
+  for (int i = 0; i < Q; i++) rho += f[i];
+  REAL v[3] = {0, 0, 0};
+  for (int d = 0; d < D; d++) {
+    REAL s = 0;
+#pragma GCC unroll 27
+    for (int i = 0; i < Q; i++) s += (REAL)E[i][d] * f[i];
+    v[d] = s / rho;
+  }
+  REAL vv = 0;
+  for (int d = 0; d < D; d++) vv += v[d] * v[d];
+#pragma GCC unroll 27
+  for (int i = 0; i < Q; i++) {
+    REAL ev = 0;
+    for (int d = 0; d < D; d++) ev += (REAL)E[i][d] * v[d];
+    REAL h = (REAL)3.0 * ev + (REAL)4.5 * ev * ev - (REAL)1.5 * vv;
+    REAL feq = W[i] * (rho + rho * h);
+    f[i] += omega * (feq - f[i]);
+  }
+  if (save) { orho[gi] = rho; for (int d = 0; d < D; d++) ov[d][gi] = v[d]; }
+  if (aa && !odd) {
+#pragma GCC unroll 27
+    for (int i = 0; i < Q; i++) dout[gi + DS * OPP[i]] = f[i];
+  } else {
+#pragma GCC unroll 27
+    for (int i = 0; i < Q; i++) dout[gi + off[i] + DS * i] = f[i];
+  }
+}
+
 int orc_collide_and_propagate(const SlfParams *P, const uint32_t *map, const REAL *din, REAL *dout,
                               REAL *orho, REAL *ovx, REAL *ovy, REAL *ovz,
                               int options, uint32_t iteration, int z_begin, int z_end) {
@@ -332,11 +382,17 @@ int orc_collide_and_propagate(const SlfParams *P, const uint32_t *map, const REA
   if (z_end < 0) z_end = outer_n;
   long long off[MAXQ];
   for (int i = 0; i < Q; i++) off[i] = L->e[i][0] + C->stride[1] * L->e[i][1] + C->stride[2] * L->e[i][2];
+  const int fast_ok = P->model == SLF_BGK && !C->forced && P->relaxation_enabled && P->propagation_enabled &&
+                      (P->lattice == SLF_D3Q19 || P->lattice == SLF_D2Q9);
 
+  /* rows (z, y) are independent work items: enough of them to balance any core count */
+  const int rows_per_o = D == 3 ? C->ny : 1;
+  const long long row0 = (long long)z_begin * rows_per_o, row1 = (long long)z_end * rows_per_o;
 #pragma omp parallel for schedule(static)
-  for (int o = z_begin; o < z_end; o++) {
-    const int y0 = D == 3 ? 0 : o, y1 = D == 3 ? C->ny : o + 1, z = D == 3 ? o : 0;
-    for (int y = y0; y < y1; y++)
+  for (long long row = row0; row < row1; row++) {
+    const int o = (int)(row / rows_per_o);
+    const int z = D == 3 ? o : 0;
+    const int y = D == 3 ? (int)(row % rows_per_o) : o;
     for (int x = 0; x < C->nx; x++) {
       const long long gi = x + C->stride[1] * y + C->stride[2] * z;
       const uint32_t code = map[gi];
@@ -345,6 +401,15 @@ int orc_collide_and_propagate(const SlfParams *P, const uint32_t *map, const REA
       if (cls == SLF_NT_GHOST || cls == SLF_NT_UNUSED) continue;      /* isExcludedNode */
       if (cls == SLF_NT_PROPAGATION_ONLY) continue;                   /* nothing but barriers */
       if (cls < 0) continue;
+      if (cls == SLF_NT_FLUID && fast_ok && x > 0 && x < C->nx - 1 && y > 0 && y < C->ny - 1 &&
+          (D == 2 || (z > 0 && z < C->nz - 1))) {
+        const int save = (options & SLF_OPTION_SAVE_MACRO_FIELDS) != 0;
+        if (P->lattice == SLF_D3Q19)
+          fluid_bgk_node(19, 3, E_D3Q27, W_D3Q19, OPP_D3Q19, off, DS, gi, din, dout, odd, aa, C->omega, save, orho, ov);
+        else
+          fluid_bgk_node(9, 2, E_D2Q9, W_D2Q9, OPP_D2Q9, off, DS, gi, din, dout, odd, aa, C->omega, save, orho, ov);
+        continue;
+      }
       const int orient = (int)(code >> C->oshift);
       REAL f[MAXQ], rho, v[3] = {0, 0, 0};
       /* getDist */
@@ -674,3 +739,111 @@ int orc_distribute_continuous_data(const SlfParams *P, REAL *dist, int face, int
 }
 
 int orc_sizeof_real(void) { return (int)sizeof(REAL); }
+
+/* ------------------------------------------------------------------------------------
+ * Formula-level hooks for tests/test_oracle_formulas.py (golden: tests/golden/formulas.npz,
+ * produced by lambdifying the reference's SymPy expressions).  n independent samples;
+ * arrays are [component][sample].
+ * ------------------------------------------------------------------------------------ */
+int orc_eval_feq(int lattice, int n, const REAL *rho, const REAL *v, REAL *out) {
+  lat_init();
+  if (lattice < 0 || lattice > 2) return SLF_EINVAL;
+  const Lat *L = &g_lat[lattice];
+  for (int s = 0; s < n; s++) {
+    REAL vv[3] = {0, 0, 0}, f[MAXQ];
+    for (int d = 0; d < L->D; d++) vv[d] = v[d * n + s];
+    feq_all(L, rho[s], vv, f);
+    for (int i = 0; i < L->Q; i++) out[i * n + s] = f[i];
+  }
+  return 0;
+}
+
+/* Guo term added to f_i (sym_force.py:121-160) for velocity v (already shifted by a/2),
+ * acceleration a and relaxation time tau. */
+int orc_eval_guo(int lattice, int n, const REAL *rho, const REAL *v, const REAL *a, REAL tau, REAL *out) {
+  lat_init();
+  if (lattice < 0 || lattice > 2) return SLF_EINVAL;
+  const Lat *L = &g_lat[lattice];
+  for (int s = 0; s < n; s++) {
+    REAL pref = rho[s] * (REAL)3.0 * ((REAL)1.0 - (REAL)1.0 / ((REAL)2.0 * tau));
+    for (int i = 0; i < L->Q; i++) {
+      REAL ev = 0, t = 0;
+      for (int d = 0; d < L->D; d++) ev += (REAL)L->e[i][d] * v[d * n + s];
+      for (int d = 0; d < L->D; d++) t += ((REAL)L->e[i][d] - v[d * n + s] + (REAL)3.0 * ev * (REAL)L->e[i][d]) * a[d * n + s];
+      out[i * n + s] = pref * (REAL)L->w[i] * t;
+    }
+  }
+  return 0;
+}
+
+/* Moments m = M f, their equilibria and the relaxation rates (relaxation_mrt.mako:31-57). */
+int orc_eval_mrt(int lattice, int n, const REAL *f, double visc, REAL *m_out, REAL *meq_out, REAL *rates_out) {
+  lat_init();
+  if (lattice != SLF_D2Q9 && lattice != SLF_D3Q19) return SLF_EUNSUPPORTED;
+  const Lat *L = &g_lat[lattice]; const int Q = L->Q;
+  REAL inv_tau = (REAL)1.0 / ((REAL)0.5 + (REAL)3.0 * (REAL)visc);
+  for (int k = 0; k < Q; k++) rates_out[k] = L->rates[k] < 0 ? inv_tau : (REAL)L->rates[k];
+  for (int s = 0; s < n; s++) {
+    REAL m[MAXQ], meq[MAXQ];
+    for (int k = 0; k < Q; k++) { REAL t = 0; for (int i = 0; i < Q; i++) t += (REAL)L->M[k][i] * f[i * n + s]; m[k] = t; meq[k] = 0; }
+    REAL rho = m[0], mx = m[L->i_mx], my = m[L->i_my], mz = L->D == 3 ? m[L->i_mz] : 0;
+    if (lattice == SLF_D2Q9) {
+      meq[1] = (REAL)-2.0 * rho + (REAL)3.0 * (mx*mx + my*my); meq[2] = rho - (REAL)3.0 * (mx*mx + my*my);
+      meq[4] = -mx; meq[6] = -my; meq[7] = mx*mx - my*my; meq[8] = mx*my;
+    } else {
+      REAL ir = (REAL)1.0 / rho, m2 = mx*mx + my*my + mz*mz;
+      meq[1] = (REAL)-11.0 * rho + (REAL)19.0 * ir * m2; meq[2] = (REAL)(-475.0/63.0) * ir * m2;
+      meq[4] = (REAL)(-2.0/3.0) * mx; meq[6] = (REAL)(-2.0/3.0) * my; meq[8] = (REAL)(-2.0/3.0) * mz;
+      meq[9] = ir * ((REAL)2.0*mx*mx - (my*my + mz*mz)); meq[11] = ir * (my*my - mz*mz);
+      meq[13] = ir * mx*my; meq[14] = ir * my*mz; meq[15] = ir * mx*mz;
+    }
+    for (int k = 0; k < Q; k++) { m_out[k * n + s] = m[k]; meq_out[k * n + s] = meq[k]; }
+  }
+  return 0;
+}
+
+/* Velocity-/density-node closures and the regularised boundary step for one orientation
+ * (boundary.mako:418-459, 817-835; sym.py:573-682, 750-766, 882-891).
+ * mode 0: out_rho = rho/(1 - n.v) for the velocity BC (f already filled)           -> rho_out
+ * mode 1: v = -n (rho - par_rho)/par_rho for the density BC                          -> v_out
+ * mode 2: non-equilibrium bounce-back of f for (rho, v)                              -> f_out
+ * mode 3: regularised populations max(1e-7, feq + w 9/2 Q:Pi_neq) from f, rho, v     -> f_out */
+int orc_eval_bc(int lattice, int mode, int orientation, int n, const REAL *f, const REAL *rho, const REAL *v,
+                REAL par_rho, REAL *rho_out, REAL *v_out, REAL *f_out) {
+  lat_init();
+  if (lattice < 0 || lattice > 2) return SLF_EINVAL;
+  const Lat *L = &g_lat[lattice]; const int Q = L->Q, D = L->D;
+  const int *nn = L->e[L->dir2vec[orientation]];
+  for (int s = 0; s < n; s++) {
+    REAL vv[3] = {0, 0, 0}, ff[MAXQ], feq[MAXQ];
+    for (int d = 0; d < D; d++) vv[d] = v ? v[d * n + s] : 0;
+    if (f) for (int i = 0; i < Q; i++) ff[i] = f[i * n + s];
+    if (mode == 0) {
+      REAL nv = 0; for (int d = 0; d < D; d++) nv += (REAL)nn[d] * vv[d];
+      rho_out[s] = rho[s] / ((REAL)1.0 - nv);
+    } else if (mode == 1) {
+      for (int d = 0; d < D; d++) v_out[d * n + s] = (REAL)(-nn[d]) * (rho[s] - par_rho) / par_rho;
+    } else if (mode == 2) {
+      feq_all(L, rho[s], vv, feq);
+      for (int i = 0; i < Q; i++) {
+        int sp = 0; for (int d = 0; d < D; d++) sp += L->e[i][d] * nn[d];
+        f_out[i * n + s] = sp > 0 ? ff[L->opp[i]] - feq[L->opp[i]] + feq[i] : ff[i];
+      }
+    } else {
+      feq_all(L, rho[s], vv, feq);
+      REAL flux[3][3];
+      for (int a = 0; a < D; a++) for (int b = 0; b < D; b++) {
+        REAL t = 0; for (int i = 0; i < Q; i++) t += (REAL)(L->e[i][a] * L->e[i][b]) * ff[i];
+        flux[a][b] = t - (a == b ? rho[s] * (vv[a]*vv[a] + (REAL)(1.0/3.0)) : rho[s] * vv[a] * vv[b]);
+      }
+      for (int i = 0; i < Q; i++) {
+        REAL t = 0;
+        for (int a = 0; a < D; a++) for (int b = 0; b < D; b++)
+          t += flux[a][b] * ((REAL)(L->e[i][a] * L->e[i][b]) - (a == b ? (REAL)(1.0/3.0) : (REAL)0));
+        REAL r = feq[i] + (REAL)L->w[i] * (REAL)4.5 * t;
+        f_out[i * n + s] = r > (REAL)1e-7 ? r : (REAL)1e-7;
+      }
+    }
+  }
+  return 0;
+}

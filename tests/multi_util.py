@@ -35,7 +35,9 @@ def build_case(cls, geo, args):
         per = list(spec._periodicity) + [False] * (3 - dim)
         p = P.make_params(sim.grid.name, cfg.model, cfg.access_pattern, lat, arr, per, sd.bits,
                           sd.type_ids_by_name(), sd.node_params, cfg.visc, sim.body_acceleration(),
-                          use_link_tags=cfg.use_link_tags)
+                          use_link_tags=cfg.use_link_tags,
+                          relaxation_enabled=getattr(cfg, 'relaxation_enabled', True),
+                          propagation_enabled=getattr(cfg, 'propagation_enabled', True))
         parts.append(dict(spec=spec, sd=sd, sim=sim, params=p, rho=base[0], v=base[1:], grid=sim.grid))
     return cfg, parts
 
