@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SLF_ABI_VERSION 1
+#define SLF_ABI_VERSION 2
 
 /* error codes (negative; positive values are cudaError_t) */
 #define SLF_EINVAL      (-1)   /* bad argument / unsupported configuration          */
@@ -48,6 +48,10 @@ enum { SLF_D2Q9 = 0, SLF_D3Q19 = 1, SLF_D3Q27 = 2 };
 enum { SLF_BGK = 0, SLF_MRT = 1 };
 /* --access_pattern, lb_base.py:61-65 */
 enum { SLF_AB = 0, SLF_AA = 1 };
+/* ctx['simtype']: single fluid (lb_single.py:60) or binary Shan-Chen (lb_binary.py:422-427) */
+enum { SLF_SIM_LBM = 0, SLF_SIM_SHAN_CHEN = 1 };
+/* --sc_potential, sym.py:896-908 */
+enum { SLF_SC_LINEAR = 0, SLF_SC_CLASSIC = 1 };
 
 /* Node classes understood by the kernels (sailfish/node_type.py).  type_id[] in
  * SlfParams holds the per-run remapped id (geo_encoder.py:83-91) of each class,
@@ -100,8 +104,14 @@ typedef struct SlfParams {
   double   visc;                /* --visc; tau = (6 visc + 1) / 2  (sym.py:847)          */
   double   accel[3];            /* body acceleration (sym_force.py:72-119, accel=True)  */
   int32_t  num_node_params;     /* len(ctx['node_params'])                              */
-  int32_t  reserved1;
+  int32_t  simtype;             /* SLF_SIM_LBM | SLF_SIM_SHAN_CHEN   (ctx['simtype'])   */
   const double *node_params;    /* host pointer, copied by slf_plan_create              */
+  /* binary Shan-Chen mixture (lb_binary.py:375-420): second lattice relaxation time,
+   * coupling constants G11, G12, G21 (= G12), G22 and the pseudopotential */
+  double   tau_phi;             /* --tau_phi                                            */
+  double   sc_g[4];             /* G11, G12, G21, G22  (constants(), lb_binary.py:387-393) */
+  int32_t  sc_potential;        /* SLF_SC_LINEAR | SLF_SC_CLASSIC (sym.py:896-908)       */
+  int32_t  reserved1;
 } SlfParams;
 
 typedef struct SlfPlan SlfPlan;
@@ -162,9 +172,43 @@ int  slf_collide_and_propagate(SlfPlan *plan, uint64_t map, uint64_t dist_in, ui
                                int options, uint32_t iteration,
                                int z_begin, int z_end, uint64_t stream);
 
+/* Runs `nsteps` whole time steps from C: CollideAndPropagate over the subdomain followed by the
+ * PBC kernels of the locally periodic axes, with the AA in-place / AB ping-pong lattice selection
+ * of lb_single.py:96-185 -- the body of SubdomainRunner.main()/step() (subdomain_runner.py:960-974,
+ * :1673-1748) for stretches without output or halo exchange.  Pairs of steps are replayed as a CUDA
+ * graph, which removes the per-step host cost that dominates small lattices (ldc_2d 256^2).
+ * `iteration` is the number of the first step; save_last stores rho, v in the last one. */
+int  slf_run_steps(SlfPlan *plan, uint64_t map, uint64_t dist_a, uint64_t dist_b, uint64_t rho,
+                   uint64_t vx, uint64_t vy, uint64_t vz, uint32_t iteration, int nsteps,
+                   int save_last, uint64_t stream);
+
 /* PrepareMacroFields(map, dist, rho, options, iteration)  lb_single_fluid.mako:129-159 */
 int  slf_prepare_macro_fields(SlfPlan *plan, uint64_t map, uint64_t dist, uint64_t rho,
                               int options, uint32_t iteration, uint64_t stream);
+
+/* ---- binary Shan-Chen mixture (BASELINE config 5; lb_binary.py:375-517) ---------------------
+ * SetInitialConditions(map, dist1, dist2, ivx, ivy[, ivz], irho, iphi)  lb_binary_fluid.mako:88-127 */
+int  slf_sc_set_initial_conditions(SlfPlan *plan, uint64_t map, uint64_t dist1, uint64_t dist2,
+                                   uint64_t vx, uint64_t vy, uint64_t vz, uint64_t rho, uint64_t phi,
+                                   uint64_t stream);
+/* ShanChenPrepareMacroFields(map, dist1, dist2, orho0, orho1, ovx, ovy[, ovz], options, iteration)
+ * binary_shan_chen.mako:19-87: both densities and the tau-weighted common velocity. */
+int  slf_sc_prepare_macro_fields(SlfPlan *plan, uint64_t map, uint64_t dist1, uint64_t dist2,
+                                 uint64_t rho, uint64_t phi, uint64_t vx, uint64_t vy, uint64_t vz,
+                                 int options, uint32_t iteration, int z_begin, int z_end, uint64_t stream);
+/* ShanChenCollideAndPropagate{0,1}(map, dist_in, dist_out, gg0m0, gg1m0, ovx, ovy[, ovz], options,
+ * iteration)  binary_shan_chen.mako:89-141 + shan_chen.mako:9-84: grid_idx selects the component. */
+int  slf_sc_collide_and_propagate(SlfPlan *plan, int grid_idx, uint64_t map, uint64_t dist_in,
+                                  uint64_t dist_out, uint64_t rho, uint64_t phi, uint64_t vx, uint64_t vy,
+                                  uint64_t vz, int options, uint32_t iteration, int z_begin, int z_end,
+                                  uint64_t stream);
+/* ApplyMacroPeriodicBoundaryConditions(field, axis)  kernel_utils.mako:410-474 */
+int  slf_apply_macro_periodic_boundary_conditions(SlfPlan *plan, uint64_t field, int axis, uint64_t stream);
+/* Ghost-layer exchange of a scalar field across the split axis (replaces
+ * Collect/DistributeContinuousMacroData + connectors, kernel_utils.mako:839-953,
+ * subdomain_runner.py:1900-2100): first/last real layer -> neighbour's ghost layer. */
+int  slf_halo_push_field(SlfPlan *plan, uint64_t field, int face, uint64_t peer_field, int peer_lat_n,
+                         uint64_t stream);
 
 /* ApplyPeriodicBoundaryConditions[WithSwap](dist, axis)  kernel_utils.mako:295-384 */
 int  slf_apply_periodic_boundary_conditions(SlfPlan *plan, uint64_t dist, int axis,

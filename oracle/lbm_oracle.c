@@ -847,3 +847,173 @@ int orc_eval_bc(int lattice, int mode, int orientation, int n, const REAL *f, co
   }
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------
+ * Binary Shan-Chen mixture (BASELINE config 5).  Reference: lb_binary.py:375-517 (model class,
+ * kernel arguments), templates/models/lb_binary_fluid.mako:88-127 (SetInitialConditions),
+ * templates/models/binary_shan_chen.mako:19-141 (ShanChenPrepareMacroFields,
+ * ShanChenCollideAndPropagate{0,1}), templates/shan_chen.mako:9-84 (force),
+ * relaxation.mako:99-181 with relaxation_common.mako (BGK_relaxate{0,1} + Guo forcing),
+ * kernel_utils.mako:410-474 (ApplyMacroPeriodicBoundaryConditions).
+ * ------------------------------------------------------------------------------------ */
+static inline REAL sc_ppot(int pot, REAL x) {       /* sym.py:896-908 */
+  return pot == SLF_SC_CLASSIC ? (REAL)1.0 * ((REAL)1.0 - (REAL)exp(-(double)x / 1.0)) : x;
+}
+
+static inline int is_wet(int cls) {
+  return cls == SLF_NT_FLUID || cls == SLF_NT_HALFBB_WALL || cls == SLF_NT_EQUILIBRIUM_VELOCITY ||
+         cls == SLF_NT_EQUILIBRIUM_DENSITY || cls == SLF_NT_REGULARIZED_VELOCITY ||
+         cls == SLF_NT_REGULARIZED_DENSITY || cls == SLF_NT_DO_NOTHING;
+}
+
+int orc_sc_set_initial_conditions(const SlfParams *P, const uint32_t *map, REAL *d1, REAL *d2, const REAL *ivx,
+                                  const REAL *ivy, const REAL *ivz, const REAL *irho, const REAL *iphi) {
+  Ctx Cs; int rc = ctx_init(&Cs, P); if (rc) return rc;
+  const Ctx *C = &Cs; const Lat *L = C->L;
+  for (int z = 0; z < C->nz; z++) for (int y = 0; y < C->ny; y++) for (int x = 0; x < C->nx; x++) {
+    long long gi = x + C->stride[1] * y + C->stride[2] * z;
+    int cls = nclass(C, map[gi] & C->tmask);
+    if (!is_wet(cls) && cls != SLF_NT_FULLBB_WALL) {
+      for (int i = 0; i < L->Q; i++) { d1[gi + C->DS * i] = (REAL)INFINITY; d2[gi + C->DS * i] = (REAL)INFINITY; }
+      continue;
+    }
+    REAL v[3], feq[MAXQ]; v[0] = ivx[gi]; v[1] = ivy[gi]; v[2] = L->D == 3 ? ivz[gi] : (REAL)0;
+    feq_all(L, irho[gi], v, feq);
+    for (int i = 0; i < L->Q; i++) d1[gi + C->DS * i] = feq[i];
+    feq_all(L, iphi[gi], v, feq);
+    for (int i = 0; i < L->Q; i++) d2[gi + C->DS * i] = feq[i];
+  }
+  return 0;
+}
+
+int orc_sc_prepare_macro_fields(const SlfParams *P, const uint32_t *map, const REAL *d1, const REAL *d2,
+                                REAL *orho, REAL *ophi, REAL *ovx, REAL *ovy, REAL *ovz, int options,
+                                uint32_t iteration, int z_begin, int z_end) {
+  (void)options;
+  Ctx Cs; int rc = ctx_init(&Cs, P); if (rc) return rc;
+  const Ctx *C = &Cs; const Lat *L = C->L; const int Q = L->Q, D = L->D;
+  REAL *ov[3] = {ovx, ovy, ovz};
+  const int odd = P->access_pattern == SLF_AA && (iteration & 1);
+  const REAL tau0_inv = (REAL)1.0 / C->tau, tau1_inv = (REAL)1.0 / (REAL)P->tau_phi;
+  const int outer_n = D == 3 ? C->nz : C->ny;
+  if (z_end < 0) z_end = outer_n;
+  long long off[MAXQ];
+  for (int i = 0; i < Q; i++) off[i] = L->e[i][0] + C->stride[1] * L->e[i][1] + C->stride[2] * L->e[i][2];
+  const int rows_per_o = D == 3 ? C->ny : 1;
+#pragma omp parallel for schedule(static)
+  for (long long row = (long long)z_begin * rows_per_o; row < (long long)z_end * rows_per_o; row++) {
+    const int o = (int)(row / rows_per_o), z = D == 3 ? o : 0, y = D == 3 ? (int)(row % rows_per_o) : o;
+    for (int x = 0; x < C->nx; x++) {
+      const long long gi = x + C->stride[1] * y + C->stride[2] * z;
+      const int cls = nclass(C, map[gi] & C->tmask);
+      if (!is_wet(cls)) continue;
+      if (cls == SLF_NT_EQUILIBRIUM_DENSITY) continue;   /* pressure nodes keep their density */
+      REAL v[3] = {0, 0, 0}, rho[2];
+      const REAL *dd[2] = {d1, d2}; const REAL ti[2] = {tau0_inv, tau1_inv};
+      for (int g = 0; g < 2; g++) {
+        REAL f[MAXQ], r = 0;
+        for (int i = 0; i < Q; i++) f[i] = odd ? dd[g][gi - off[i] + C->DS * L->opp[i]] : dd[g][gi + C->DS * i];
+        for (int i = 0; i < Q; i++) r += f[i];
+        rho[g] = r;
+        for (int d = 0; d < D; d++) {
+          REAL s = 0; for (int i = 0; i < Q; i++) s += (REAL)L->e[i][d] * f[i];
+          v[d] = g == 0 ? ti[g] * s : v[d] + ti[g] * s;      /* compute_1st_moment(fi, v, add, factor) */
+        }
+      }
+      orho[gi] = rho[0]; ophi[gi] = rho[1];
+      const REAL total = tau0_inv * rho[0] + tau1_inv * rho[1];
+      for (int d = 0; d < D; d++) ov[d][gi] = v[d] / total;
+    }
+  }
+  return 0;
+}
+
+int orc_sc_collide_and_propagate(const SlfParams *P, int grid_idx, const uint32_t *map, const REAL *din, REAL *dout,
+                                 const REAL *rho_f, const REAL *phi_f, const REAL *ovx, const REAL *ovy,
+                                 const REAL *ovz, int options, uint32_t iteration, int z_begin, int z_end) {
+  (void)options;
+  Ctx Cs; int rc = ctx_init(&Cs, P); if (rc) return rc;
+  const Ctx *C = &Cs; const Lat *L = C->L; const int Q = L->Q, D = L->D;
+  const REAL *ov[3] = {ovx, ovy, ovz};
+  const int aa = P->access_pattern == SLF_AA, odd = aa && (iteration & 1);
+  const int outer_n = D == 3 ? C->nz : C->ny;
+  if (z_end < 0) z_end = outer_n;
+  long long off[MAXQ];
+  for (int i = 0; i < Q; i++) off[i] = L->e[i][0] + C->stride[1] * L->e[i][1] + C->stride[2] * L->e[i][2];
+  const REAL *own = grid_idx == 0 ? rho_f : phi_f;
+  const REAL *fields[2] = {rho_f, phi_f};
+  const REAL G[2] = {(REAL)P->sc_g[2 * grid_idx + 0], (REAL)P->sc_g[2 * grid_idx + 1]};
+  const double tau_g = grid_idx == 0 ? (6.0 * P->visc + 1.0) / 2.0 : P->tau_phi;
+  const REAL omega = (REAL)(1.0 / tau_g), tauf = (REAL)tau_g;
+  const int rows_per_o = D == 3 ? C->ny : 1;
+#pragma omp parallel for schedule(static)
+  for (long long row = (long long)z_begin * rows_per_o; row < (long long)z_end * rows_per_o; row++) {
+    const int o = (int)(row / rows_per_o), z = D == 3 ? o : 0, y = D == 3 ? (int)(row % rows_per_o) : o;
+    for (int x = 0; x < C->nx; x++) {
+      const long long gi = x + C->stride[1] * y + C->stride[2] * z;
+      const int cls = nclass(C, map[gi] & C->tmask);
+      if (cls < 0 || cls == SLF_NT_GHOST || cls == SLF_NT_UNUSED || cls == SLF_NT_PROPAGATION_ONLY) continue;
+      const int wet = is_wet(cls);
+      const REAL gm = own[gi];
+      REAL a[3] = {0, 0, 0};
+      if (wet) {                                     /* sc_calculate_force, shan_chen.mako:9-25 */
+        for (int k = 0; k < 2; k++) {
+          if (G[k] == (REAL)0) continue;
+          REAL force[3] = {0, 0, 0};
+          for (int i = 1; i < Q; i++) {               /* shan_chen_force, :45-84 */
+            const REAL psi = sc_ppot(P->sc_potential, fields[k][gi + off[i]]);
+            for (int d = 0; d < D; d++) if (L->e[i][d]) force[d] += psi * (REAL)(L->e[i][d] * L->w[i]);
+          }
+          const REAL psi0 = sc_ppot(P->sc_potential, gm);
+          for (int d = 0; d < D; d++) a[d] += force[d] * (-psi0 * G[k]);
+        }
+        for (int d = 0; d < D; d++) a[d] /= gm;
+      }
+      REAL f[MAXQ], v[3] = {0, 0, 0};
+      for (int i = 0; i < Q; i++) f[i] = odd ? din[gi - off[i] + C->DS * L->opp[i]] : din[gi + C->DS * i];
+      for (int d = 0; d < D; d++) v[d] = ov[d][gi];
+      if (cls == SLF_NT_FULLBB_WALL) bounce_back(L, f);
+      if (wet && P->relaxation_enabled) {             /* BGK_relaxate{grid_idx} with Guo forcing */
+        REAL v0[3] = {0, 0, 0}, feq[MAXQ];
+        for (int d = 0; d < D; d++) v0[d] = v[d] + (REAL)0.5 * a[d];
+        feq_all(L, gm, v0, feq);
+        for (int i = 0; i < Q; i++) f[i] += omega * (feq[i] - f[i]);
+        const REAL pref = gm * (REAL)3.0 * ((REAL)1.0 - (REAL)1.0 / ((REAL)2.0 * tauf));
+        for (int i = 0; i < Q; i++) {
+          REAL ev = 0, s = 0;
+          for (int d = 0; d < D; d++) ev += (REAL)L->e[i][d] * v0[d];
+          for (int d = 0; d < D; d++) s += ((REAL)L->e[i][d] - v0[d] + (REAL)3.0 * ev * (REAL)L->e[i][d]) * a[d];
+          f[i] += pref * (REAL)L->w[i] * s;
+        }
+      }
+      if (!P->propagation_enabled) {
+        for (int i = 0; i < Q; i++) dout[gi + C->DS * i] = f[i];
+      } else if (aa && !odd) {
+        for (int i = 0; i < Q; i++) dout[gi + C->DS * L->opp[i]] = f[i];
+      } else {
+        for (int i = 0; i < Q; i++) if (in_bounds_target(C, L->e[i], x, y, z)) dout[gi + off[i] + C->DS * i] = f[i];
+      }
+    }
+  }
+  return 0;
+}
+
+int orc_apply_macro_periodic_boundary_conditions(const SlfParams *P, REAL *field, int axis) {
+  Ctx Cs; int rc = ctx_init(&Cs, P); if (rc) return rc;
+  const Ctx *C = &Cs; const int D = C->L->D;
+  if (axis < 0 || axis >= D) return D == 2 && axis == 2 ? 0 : SLF_EINVAL;
+  const int lim[3] = {C->nx, C->ny, C->nz};
+  int o1 = axis == 0 ? 1 : 0, o2 = axis == 2 ? 1 : 2;
+  if (D == 2) { o1 = 1 - axis; o2 = 2; }
+  const int n1 = lim[o1], n2 = D == 3 ? lim[o2] : 1;
+  for (int i2 = 0; i2 < n2; i2++) for (int i1 = 0; i1 < n1; i1++) {
+    int c[3] = {0, 0, 0};
+    c[o1] = i1; if (D == 3) c[o2] = i2;
+    long long g0, g1;
+    c[axis] = 0; g0 = gidx(C, c); c[axis] = lim[axis] - 2; g1 = gidx(C, c);
+    if (isfinite(field[g1])) field[g0] = field[g1];
+    c[axis] = 1; g0 = gidx(C, c); c[axis] = lim[axis] - 1; g1 = gidx(C, c);
+    if (isfinite(field[g0])) field[g1] = field[g0];
+  }
+  return 0;
+}

@@ -145,3 +145,92 @@ class Simulation(object):
     def run(self, steps, save_last=True):
         for k in range(steps):
             self.step(save_macro=(save_last and k == steps - 1))
+
+
+# ---- binary Shan-Chen (BASELINE config 5) ------------------------------------------------------
+def sc_set_initial_conditions(params, node_map, d1, d2, v, rho, phi):
+    lib = _lib(d1.dtype)
+    vz = v[2] if len(v) > 2 else None
+    _chk(lib.orc_sc_set_initial_conditions(ctypes.byref(params), _p(node_map), _p(d1), _p(d2), _p(v[0]), _p(v[1]),
+                                           _p(vz), _p(rho), _p(phi)), 'sc_set_initial_conditions')
+
+
+def sc_prepare_macro_fields(params, node_map, d1, d2, rho, phi, v, options, iteration, z_begin=0, z_end=-1):
+    lib = _lib(d1.dtype)
+    vz = v[2] if len(v) > 2 else None
+    _chk(lib.orc_sc_prepare_macro_fields(ctypes.byref(params), _p(node_map), _p(d1), _p(d2), _p(rho), _p(phi),
+                                         _p(v[0]), _p(v[1]), _p(vz), int(options), ctypes.c_uint32(iteration),
+                                         int(z_begin), int(z_end)), 'sc_prepare_macro_fields')
+
+
+def sc_collide_and_propagate(params, grid_idx, node_map, din, dout, rho, phi, v, options, iteration,
+                             z_begin=0, z_end=-1):
+    lib = _lib(din.dtype)
+    vz = v[2] if len(v) > 2 else None
+    _chk(lib.orc_sc_collide_and_propagate(ctypes.byref(params), int(grid_idx), _p(node_map), _p(din), _p(dout),
+                                          _p(rho), _p(phi), _p(v[0]), _p(v[1]), _p(vz), int(options),
+                                          ctypes.c_uint32(iteration), int(z_begin), int(z_end)), 'sc_collide')
+
+
+def apply_macro_pbc(params, field, axis):
+    lib = _lib(field.dtype)
+    _chk(lib.orc_apply_macro_periodic_boundary_conditions(ctypes.byref(params), _p(field), int(axis)), 'macro_pbc')
+
+
+class ShanChenSimulation(object):
+    """Step sequence of NNSubdomainRunner.step (subdomain_runner.py:2102-2197) for one subdomain:
+    macro fields -> macro PBC -> both collide kernels -> distribution PBC."""
+
+    def __init__(self, params, node_map, rho, phi, v, dtype=np.float32):
+        self.p = params
+        self.dtype = np.dtype(dtype)
+        self.map = np.ascontiguousarray(node_map, dtype=np.uint32)
+        n = params.dist_size
+        c = lambda a: np.ascontiguousarray(a, dtype=self.dtype).reshape(-1).copy()
+        self.rho, self.phi = c(rho), c(phi)
+        self.v = [c(x) for x in v]
+        ab = params.access_pattern == 0
+        self.d = [[np.zeros(params.Q * n, self.dtype), np.zeros(params.Q * n, self.dtype) if ab else None]
+                  for _ in range(2)]
+        self.iteration = 0
+        sc_set_initial_conditions(params, self.map, self.d[0][0], self.d[1][0], self.v, self.rho, self.phi)
+        if ab:
+            sc_set_initial_conditions(params, self.map, self.d[0][1], self.d[1][1], self.v, self.rho, self.phi)
+
+    def _io(self, g):
+        a, b = self.d[g]
+        if b is None:
+            return a, a
+        return (a, b) if (self.iteration & 1) == 0 else (b, a)
+
+    def current(self, g):
+        a, b = self.d[g]
+        return a if (b is None or (self.iteration & 1) == 0) else b
+
+    def macro(self):
+        it = self.iteration
+        sc_prepare_macro_fields(self.p, self.map, self._io(0)[0], self._io(1)[0], self.rho, self.phi, self.v, 0, it)
+        for axis in range(self.p.dim):
+            if self.p.periodic[axis]:
+                apply_macro_pbc(self.p, self.rho, axis)
+                apply_macro_pbc(self.p, self.phi, axis)
+
+    def collide(self):
+        it = self.iteration
+        aa = self.d[0][1] is None
+        for g in range(2):
+            din, dout = self._io(g)
+            sc_collide_and_propagate(self.p, g, self.map, din, dout, self.rho, self.phi, self.v, 0, it)
+        for axis in range(self.p.dim):
+            if self.p.periodic[axis]:
+                for g in range(2):
+                    apply_pbc(self.p, self._io(g)[1], axis, with_swap=(aa and (it & 1) == 0))
+
+    def step(self):
+        self.macro()
+        self.collide()
+        self.iteration += 1
+
+    def run(self, steps):
+        for _ in range(steps):
+            self.step()

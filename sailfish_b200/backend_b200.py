@@ -54,7 +54,13 @@ _PROTOTYPES = {
     'slf_plan_bind_map': [_vp, _u64],
     'slf_set_initial_conditions': [_vp, _u64, _u64, _u64, _u64, _u64, _u64, _u64],
     'slf_collide_and_propagate': [_vp, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _i, _u32, _i, _i, _u64],
+    'slf_run_steps': [_vp, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u32, _i, _i, _u64],
     'slf_prepare_macro_fields': [_vp, _u64, _u64, _u64, _i, _u32, _u64],
+    'slf_sc_set_initial_conditions': [_vp, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64],
+    'slf_sc_prepare_macro_fields': [_vp, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _i, _u32, _i, _i, _u64],
+    'slf_sc_collide_and_propagate': [_vp, _i, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _i, _u32, _i, _i, _u64],
+    'slf_apply_macro_periodic_boundary_conditions': [_vp, _u64, _i, _u64],
+    'slf_halo_push_field': [_vp, _u64, _i, _u64, _i, _u64],
     'slf_apply_periodic_boundary_conditions': [_vp, _u64, _i, _i, _u64],
     'slf_collect_continuous_data': [_vp, _u64, _i, _i, _i, _i, _i, _u64, _i, _u64],
     'slf_distribute_continuous_data': [_vp, _u64, _i, _i, _i, _i, _i, _u64, _i, _u64],
@@ -98,7 +104,7 @@ class Lib(object):
             fn = getattr(self.cdll, name)
             fn.argtypes = argtypes
             fn.restype = restype
-        if self.cdll.slf_abi_version() != 1:
+        if self.cdll.slf_abi_version() != 2:
             raise B200Error('ABI version mismatch')
 
     def call(self, name, *args):

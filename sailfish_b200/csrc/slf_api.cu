@@ -21,6 +21,11 @@ int slf_fail(int code, const std::string &msg) {
 }
 void slf_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+struct StepGraphKey { uint64_t map, a, b, rho; int parity; };
+struct StepGraph { StepGraphKey key; cudaGraphExec_t exec; uint64_t kernels; };
+static std::vector<std::pair<SlfPlan *, StepGraph>> g_graphs;
+
+
 extern "C" {
 
 int slf_abi_version(void) { return SLF_ABI_VERSION; }
@@ -189,6 +194,10 @@ int slf_plan_create(const SlfParams *p, SlfPlan **out) {
 
 int slf_plan_destroy(SlfPlan *plan) {
   if (!plan) return 0;
+  for (size_t k = 0; k < g_graphs.size();) {
+    if (g_graphs[k].first == plan) { cudaGraphExecDestroy(g_graphs[k].second.exec); g_graphs.erase(g_graphs.begin() + k); }
+    else k++;
+  }
   if (plan->d_node_params) cudaFree(plan->d_node_params);
   if (plan->d_fluid_mask) cudaFree(plan->d_fluid_mask);
   if (plan->d_wall_mask) cudaFree(plan->d_wall_mask);
@@ -208,6 +217,10 @@ int slf_plan_bind_map(SlfPlan *pl, uint64_t map) {
   const DevParams &d = pl->dp;
   if (d.DS >= (1ll << 32)) return fail(SLF_EUNSUPPORTED, "node lists use 32-bit indices");
   pl->bound_map = 0;
+  for (size_t k = 0; k < g_graphs.size();) {    // captured launches hold the old mask/list pointers
+    if (g_graphs[k].first == pl) { cudaGraphExecDestroy(g_graphs[k].second.exec); g_graphs.erase(g_graphs.begin() + k); }
+    else k++;
+  }
   if (!map) return 0;
   std::vector<uint32_t> h((size_t)d.DS);
   CUDA_OK(cudaMemcpy(h.data(), (const void *)map, (size_t)d.DS * 4, cudaMemcpyDeviceToHost));
@@ -400,6 +413,76 @@ int slf_distribute_sparse_data(SlfPlan *pl, uint64_t idx_array, uint64_t dist, u
       (const uint32_t *)idx_array, (float *)dist, (float *)buffer, max_idx,
       (unsigned long long)pl->dp.DS * pl->Q);
   LAUNCH_OK("distribute_sparse");
+  return 0;
+}
+
+
+// ---- multi-step driver -------------------------------------------------------------------
+// The reference pays ~10 Python calls + 1-2 pycuda launches per time step
+// (subdomain_runner.py:1673-1748); on small lattices (ldc_2d 256^2: ~66 k nodes, a few
+// microseconds of device work) that host overhead is the whole cost.
+// slf_run_steps issues whole steps from C and replays pairs of steps (one even + one odd: all
+// kernel arguments depend on the iteration only through its parity) as a CUDA graph.
+static int one_step(SlfPlan *pl, uint64_t map, uint64_t dist_a, uint64_t dist_b, uint64_t rho, uint64_t vx,
+                    uint64_t vy, uint64_t vz, uint32_t it, int save, uint64_t stream) {
+  const bool aa = pl->hp.access_pattern == SLF_AA;
+  uint64_t din = dist_a, dout = dist_a;
+  if (!aa) { din = (it & 1) ? dist_b : dist_a; dout = (it & 1) ? dist_a : dist_b; }
+  int rc = slf_collide_and_propagate(pl, map, din, dout, rho, vx, vy, vz, save ? SLF_OPTION_SAVE_MACRO_FIELDS : 0,
+                                     it, 0, -1, stream);
+  if (rc) return rc;
+  const int swap = aa && (it & 1) == 0;
+  for (int axis = 0; axis < pl->D; axis++)
+    if (pl->hp.periodic[axis]) {
+      rc = slf_apply_periodic_boundary_conditions(pl, dout, axis, swap, stream);
+      if (rc) return rc;
+    }
+  return 0;
+}
+
+int slf_run_steps(SlfPlan *pl, uint64_t map, uint64_t dist_a, uint64_t dist_b, uint64_t rho, uint64_t vx,
+                  uint64_t vy, uint64_t vz, uint32_t iteration, int nsteps, int save_last, uint64_t stream) {
+  if (!pl) return fail(SLF_EINVAL, "null plan");
+  if (nsteps <= 0) return 0;
+  if (pl->hp.access_pattern == SLF_AB && !dist_b) return fail(SLF_EINVAL, "AB needs two lattices");
+  cudaStream_t s = (cudaStream_t)stream;
+  int done = 0;
+  const int plain = nsteps - (save_last ? 1 : 0);       // steps that may be replayed from a graph
+  if (plain >= 4 && s != 0) {
+    const int parity = iteration & 1;
+    StepGraph *g = nullptr;
+    for (auto &e : g_graphs)
+      if (e.first == pl && e.second.key.map == map && e.second.key.a == dist_a && e.second.key.b == dist_b &&
+          e.second.key.rho == rho && e.second.key.parity == parity) g = &e.second;
+    if (!g) {
+      const uint64_t before = slf_launch_count();
+      cudaGraph_t graph;
+      CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      int rc = one_step(pl, map, dist_a, dist_b, rho, vx, vy, vz, iteration, 0, stream);
+      if (!rc) rc = one_step(pl, map, dist_a, dist_b, rho, vx, vy, vz, iteration + 1, 0, stream);
+      cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      if (rc) { if (ce == cudaSuccess) cudaGraphDestroy(graph); return rc; }
+      CUDA_OK(ce);
+      StepGraph ng;
+      ng.key = {map, dist_a, dist_b, rho, parity};
+      ng.kernels = slf_launch_count() - before;          // kernels captured (counted, not yet run)
+      CUDA_OK(cudaGraphInstantiate(&ng.exec, graph, 0));
+      cudaGraphDestroy(graph);
+      g_graphs.push_back({pl, ng});
+      g = &g_graphs.back().second;
+      for (uint64_t k = 0; k < ng.kernels; k++) g_launches.fetch_sub(1, std::memory_order_relaxed);
+    }
+    const int pairs = plain / 2;
+    for (int k = 0; k < pairs; k++) {
+      CUDA_OK(cudaGraphLaunch(g->exec, s));
+      g_launches.fetch_add(g->kernels, std::memory_order_relaxed);
+    }
+    done = 2 * pairs;
+  }
+  for (int k = done; k < nsteps; k++) {
+    int rc = one_step(pl, map, dist_a, dist_b, rho, vx, vy, vz, iteration + k, save_last && k == nsteps - 1, stream);
+    if (rc) return rc;
+  }
   return 0;
 }
 

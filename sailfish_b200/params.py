@@ -14,6 +14,8 @@ import numpy as np
 LATTICE_IDS = {'D2Q9': 0, 'D3Q19': 1, 'D3Q27': 2}
 MODEL_IDS = {'bgk': 0, 'mrt': 1}
 ACCESS_IDS = {'AB': 0, 'AA': 1}
+SIMTYPE_IDS = {'lbm': 0, 'shan-chen': 1}
+SC_POTENTIAL_IDS = {'linear': 0, 'classic': 1}
 
 # Order must match the SLF_NT_* enum of include/slf_b200.h.
 NODE_CLASS_NAMES = (
@@ -48,8 +50,12 @@ class SlfParams(ctypes.Structure):
         ('visc', ctypes.c_double),
         ('accel', ctypes.c_double * 3),
         ('num_node_params', ctypes.c_int32),
-        ('reserved1', ctypes.c_int32),
+        ('simtype', ctypes.c_int32),
         ('node_params', ctypes.POINTER(ctypes.c_double)),
+        ('tau_phi', ctypes.c_double),
+        ('sc_g', ctypes.c_double * 4),
+        ('sc_potential', ctypes.c_int32),
+        ('reserved1', ctypes.c_int32),
     ]
 
     # keeps the node_params array alive
@@ -74,7 +80,8 @@ class UnsupportedConfiguration(ValueError):
 
 def make_params(lattice, model, access_pattern, lat_size, arr_size, periodic,
                 bits, type_ids, node_params, visc, accel=None, use_link_tags=True,
-                relaxation_enabled=True, propagation_enabled=True):
+                relaxation_enabled=True, propagation_enabled=True, shan_chen=None):
+    """shan_chen: None (single fluid) or dict(tau_phi=, G11=, G12=, G21=, G22=, potential=)."""
     """lat_size/arr_size are (nx, ny, nz) with nz = 1 in 2-D; type_ids maps node
     class name -> remapped id."""
     p = SlfParams()
@@ -105,6 +112,12 @@ def make_params(lattice, model, access_pattern, lat_size, arr_size, periodic,
     p._np_keepalive = arr
     p.num_node_params = int(arr.size)
     p.node_params = arr.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    if shan_chen is not None:
+        p.simtype = SIMTYPE_IDS['shan-chen']
+        p.tau_phi = float(shan_chen.get('tau_phi', 1.0))
+        for i, k in enumerate(('G11', 'G12', 'G21', 'G22')):
+            p.sc_g[i] = float(shan_chen.get(k, 0.0))
+        p.sc_potential = SC_POTENTIAL_IDS[shan_chen.get('potential', 'linear')]
     return p
 
 
@@ -117,8 +130,9 @@ def from_context(ctx):
     cfg = ctx.get('config')
     if ctx.get('node_addressing', 'direct') != 'direct':
         raise UnsupportedConfiguration('--node_addressing=indirect is out of scope')
-    if ctx.get('simtype', 'lbm') != 'lbm':
-        raise UnsupportedConfiguration('simtype %r' % ctx.get('simtype'))
+    simtype = ctx.get('simtype', 'lbm')
+    if simtype not in SIMTYPE_IDS:
+        raise UnsupportedConfiguration('simtype %r' % simtype)
     for flag in ('incompressible', 'regularized'):
         if ctx.get(flag):
             raise UnsupportedConfiguration('--%s is out of scope' % flag)
@@ -149,8 +163,16 @@ def from_context(ctx):
             if ctx.get('force_implementation', 'guo') != 'guo':
                 raise UnsupportedConfiguration('only --force_implementation=guo')
             accel = [float(a) for a in numeric[0][True]] + [0.0] * (3 - len(numeric[0][True]))
-    if ctx.get('force_couplings'):
-        raise UnsupportedConfiguration('Shan-Chen couplings go through the binary-fluid path')
+    shan_chen = None
+    if simtype == 'shan-chen':
+        if len(ctx.get('grids', [])) != 2:
+            raise UnsupportedConfiguration('single-component Shan-Chen is out of scope (binary only)')
+        consts = ctx.get('constants', {})
+        shan_chen = dict(tau_phi=ctx['tau_phi'], potential=ctx.get('sc_potential', 'linear'),
+                         G11=consts.get('G11', 0.0), G12=consts.get('G12', 0.0),
+                         G21=consts.get('G21', 0.0), G22=consts.get('G22', 0.0))
+    elif ctx.get('force_couplings'):
+        raise UnsupportedConfiguration('force couplings without the Shan-Chen model')
     dim = 2 if name == 'D2Q9' else 3
     lat = (ctx['lat_nx'], ctx['lat_ny'], ctx['lat_nz'] if dim == 3 else 1)
     arr = (ctx['arr_nx'], ctx['arr_ny'], ctx['arr_nz'] if dim == 3 else 1)
@@ -160,4 +182,4 @@ def from_context(ctx):
         type_ids, [float(x) for x in ctx['node_params']], ctx['visc'], accel,
         use_link_tags=ctx.get('use_link_tags', True),
         relaxation_enabled=ctx.get('relaxation_enabled', True),
-        propagation_enabled=ctx.get('propagation_enabled', True))
+        propagation_enabled=ctx.get('propagation_enabled', True), shan_chen=shan_chen)

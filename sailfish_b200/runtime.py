@@ -103,6 +103,16 @@ class DeviceLattice(object):
         self.iteration += 1
 
     def run(self, steps, save_last=True):
+        """`steps` time steps issued from C (slf_run_steps: CUDA-graph replay of step pairs)."""
+        if steps <= 0:
+            return
+        self.lib.call('slf_run_steps', self.plan, int(self.d_map), int(self.d_dist_a),
+                      int(self.d_dist_b) if self.d_dist_b else 0, int(self.d_rho), int(self.d_v[0]),
+                      int(self.d_v[1]), self._vz(), self.iteration, int(steps), int(bool(save_last)),
+                      self.stream.handle)
+        self.iteration += steps
+
+    def run_python_loop(self, steps, save_last=True):
         for k in range(steps):
             self.step(save_macro=(save_last and k == steps - 1))
 

@@ -19,11 +19,16 @@ def load_case(name):
 def params_from_case(c, access_pattern=None):
     type_ids = {str(n): int(i) for n, i in zip(c['type_names'], c['type_ids'])}
     accel = [float(a) for a in c['accel']]
+    shan_chen = None
+    if 'simtype' in c.files and str(c['simtype']) == 'shan-chen':
+        g = [float(x) for x in c['sc_g']]
+        shan_chen = dict(tau_phi=float(c['tau_phi']), G11=g[0], G12=g[1], G21=g[2], G22=g[3],
+                         potential=str(c['sc_potential']))
     return P.make_params(
         str(c['grid']), str(c['model']), access_pattern or str(c['access_pattern']),
         [int(x) for x in c['lat']], [int(x) for x in c['arr']], [int(x) for x in c['periodic']],
         [int(x) for x in c['bits']], type_ids, [float(x) for x in c['node_params']],
-        float(c['visc']), accel, use_link_tags=bool(c['use_link_tags']))
+        float(c['visc']), accel, use_link_tags=bool(c['use_link_tags']), shan_chen=shan_chen)
 
 
 def real_mask(c):
@@ -49,5 +54,6 @@ def rel_linf(a, b):
     return float(np.max(d) / scale) if scale > 0 else float(np.max(d))
 
 
+SC_CASES = ['sc3d', 'sc3d_walls', 'sc2d_classic']
 CASES = ['ldc2d_bgk', 'ldc2d_mrt', 'ldc3d_bgk', 'ldc3d_mrt', 'ldc3d_q27', 'poi3d_press_mrt',
          'poi3d_force_bgk', 'poi3d_force_mrt', 'box3d_bgk', 'box3d_q27', 'box2d_bgk']

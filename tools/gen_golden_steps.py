@@ -170,9 +170,91 @@ def gen_split_geometry():
         print('geometry_%s.npz' % name, [tuple(out['size_%d' % i]) for i in range(len(runners))])
 
 
+
+def gen_shan_chen():
+    """Binary Shan-Chen goldens (BASELINE config 5, examples/binary_fluid/sc_separation_3d.py)."""
+    from ref_stepper import RefShanChenStepper
+    ex3 = ref_harness.load_example('examples/binary_fluid/sc_separation_3d.py')
+    from sailfish.subdomain import Subdomain3D, Subdomain2D
+    from sailfish.lb_binary import LBBinaryFluidShanChen
+    from sailfish.node_type import NTFullBBWall
+    from sailfish.geo import LBGeometry3D, LBGeometry2D
+
+    class WalledDomain(Subdomain3D):
+        def initial_conditions(self, sim, hx, hy, hz):
+            sim.rho[:] = 1.0 + 0.01 * np.sin(2 * np.pi * hx / self.gx) * np.cos(2 * np.pi * hy / self.gy)
+            sim.phi[:] = 1.0 - 0.01 * np.sin(2 * np.pi * hx / self.gx) * np.cos(2 * np.pi * hy / self.gy)
+
+        def boundary_conditions(self, hx, hy, hz):
+            self.set_node((hz == 0) | (hz == self.gz - 1), NTFullBBWall)
+
+    class WalledSim(LBBinaryFluidShanChen):
+        subdomain = WalledDomain
+
+        @classmethod
+        def update_defaults(cls, defaults):
+            defaults.update({'lat_nx': 10, 'lat_ny': 9, 'lat_nz': 8, 'grid': 'D3Q19', 'G12': 0.9, 'G11': -0.3,
+                             'visc': 0.12, 'tau_phi': 0.9, 'periodic_x': True, 'periodic_y': True})
+
+    class Sep2D(Subdomain2D):
+        def initial_conditions(self, sim, hx, hy):
+            sim.rho[:] = 1.0 + np.random.rand(*sim.rho.shape) / 1000.0
+            sim.phi[:] = 1.0 + np.random.rand(*sim.phi.shape) / 1000.0
+
+        def boundary_conditions(self, hx, hy):
+            pass
+
+    class Sep2DSim(LBBinaryFluidShanChen):
+        subdomain = Sep2D
+
+        @classmethod
+        def update_defaults(cls, defaults):
+            defaults.update({'lat_nx': 14, 'lat_ny': 12, 'grid': 'D2Q9', 'G12': 1.1, 'visc': 1.0 / 6.0,
+                             'periodic_x': True, 'periodic_y': True, 'sc_potential': 'classic'})
+
+    cases = []
+    for ap in ('AB', 'AA'):
+        cases.append(('sc3d_' + ap, ex3.SeparationSCSim, LBGeometry3D,
+                      ['--lat_nx=12', '--lat_ny=10', '--lat_nz=9', '--seed=1234', '--access_pattern=' + ap], 12))
+        cases.append(('sc3d_walls_' + ap, WalledSim, LBGeometry3D, ['--seed=1234', '--access_pattern=' + ap], 12))
+        cases.append(('sc2d_classic_' + ap, Sep2DSim, LBGeometry2D, ['--seed=1234', '--access_pattern=' + ap], 12))
+    for name, cls, geo, args, steps in cases:
+        cfg, runners = ref_harness.make_runners(cls, geo, args=args)
+        r = runners[0]
+        ctx = ref_harness.context_of(r)
+        out = pack_ctx(ctx)
+        out['simtype'] = 'shan-chen'
+        out['tau_phi'] = np.float64(ctx['tau_phi'])
+        c = ctx['constants']
+        out['sc_g'] = np.array([c['G11'], c['G12'], c['G21'], c['G22']], dtype=np.float64)
+        out['sc_potential'] = ctx['sc_potential']
+        out['map'] = r._subdomain.encoded_map().astype(np.uint32)
+        sim = r._sim
+        rho0 = r.field_base(sim.rho).astype(np.float64)
+        phi0 = r.field_base(sim.phi).astype(np.float64)
+        v0 = [r.field_base(cc).astype(np.float64) for cc in sim.v]
+        out['rho0'], out['phi0'], out['v0'] = rho0, phi0, np.array(v0)
+        out['fluid_map'] = r._subdomain.fluid_map()
+        st = RefShanChenStepper(r, ctx)
+        st.set_initial_conditions(rho0, phi0, v0)
+        for k in range(steps):
+            st.step()
+        out['steps'] = np.int32(steps)
+        out['dist1'], out['dist2'] = st.current(0).copy(), st.current(1).copy()
+        out['rho'], out['phi'], out['v'] = st.rho, st.phi, np.array(st.v)
+        fm = np.zeros(st.rho.shape, bool)
+        fm[r._spec._nonghost_slice] = out['fluid_map']
+        print('%-20s steps=%d rho[%.6f %.6f] phi[%.6f %.6f] max|v|=%.3e mass=%.10f' % (
+            name, steps, st.rho[fm].min(), st.rho[fm].max(), st.phi[fm].min(), st.phi[fm].max(),
+            max(np.abs(cc[fm]).max() for cc in st.v), st.rho[fm].sum() + st.phi[fm].sum()))
+        np.savez_compressed(os.path.join(GOLD, 'steps_%s.npz' % name), **out)
+
+
 if __name__ == '__main__':
-    what = sys.argv[1:] or ['geometry', 'steps', 'split']
+    what = sys.argv[1:] or ['geometry', 'steps', 'split', 'sc']
     if 'geometry' in what or 'steps' in what:
         main(what)
     if 'split' in what:
         gen_split_geometry()
+    if 'sc' in what:
+        gen_shan_chen()

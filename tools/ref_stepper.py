@@ -406,3 +406,157 @@ class RefStepper(object):
                         shp[pos] = good.size
                         ok = ok & good.reshape(shp)
                 b[ok] = a[ok]
+
+
+class RefShanChenStepper(object):
+    """Binary Shan-Chen mixture (lb_binary.py:375-517) with the reference's expressions:
+    equilibria = LBBinaryFluidShanChen.equilibria (bgk_equilibrium for rho and for phi),
+    pseudopotential = sym.SHAN_CHEN_POTENTIALS, forcing = sym_force.guo_external_force{,_pref}
+    for grid 0 and 1.  Control flow: binary_shan_chen.mako:19-141, shan_chen.mako:9-84,
+    NNSubdomainRunner.step (subdomain_runner.py:2102-2197).  fp64, all-wet or FullBB geometries."""
+
+    def __init__(self, runner, ctx):
+        from functools import partial
+        self.base = RefStepper.__new__(RefStepper)
+        b = self.base
+        # reuse geometry decoding of RefStepper
+        RefStepper.__init__(b, runner, dict(ctx, model='bgk', forces=None))
+        g, S, cfg = b.grid, sym.S, b.cfg
+        self.g, self.D, self.Q = g, b.D, b.Q
+        self.aa = b.aa
+        self.ctx = ctx
+        self.tau = [float(ctx['tau']), float(ctx['tau_phi'])]
+        consts = ctx['constants']
+        self.G = [[consts['G11'], consts['G12']], [consts['G21'], consts['G22']]]
+        x = sympy.Symbol('x')
+        self.ppot = _lam([x], sym.SHAN_CHEN_POTENTIALS[ctx['sc_potential']]('x'))
+        vs = b.vs
+        eq0 = sym_equilibrium.bgk_equilibrium(g, cfg).expression
+        eq1 = sym_equilibrium.bgk_equilibrium(g, cfg, rho=S.phi, rho0=S.phi).expression
+        self.feq = [[_lam([S.rho] + vs, e) for e in eq0], [_lam([S.phi] + vs, e) for e in eq1]]
+        pref = sympy.Symbol('pref')
+        self.guo, self.guo_pref = [], []
+        for gn, dens, tsym in ((0, S.rho, S.tau0), (1, S.phi, S.tau1)):
+            ea = [getattr(S, 'g%dea%s' % (gn, c)) for c in 'xyz'][:self.D]
+            self.guo.append([_lam([pref] + vs + ea, e) for e in sym_force.guo_external_force(g, grid_num=gn)])
+            self.guo_pref.append(_lam([dens, tsym], sym_force.guo_external_force_pref(g, cfg, grid_num=gn)))
+        self.rho_std, self.mom = b.rho_std, b.mom
+        shape = b.shape
+        self.d = [[np.zeros((self.Q,) + shape), None if self.aa else np.zeros((self.Q,) + shape)] for _ in range(2)]
+        self.iteration = 0
+
+    def set_initial_conditions(self, rho, phi, v):
+        b = self.base
+        with np.errstate(all='ignore'):
+            okmask = b.wet | b.is_cls(nt.NTFullBBWall) if nt.NTFullBBWall in self.ctx['node_types'] else b.wet
+            for gidx, dens in ((0, rho), (1, phi)):
+                for i in range(self.Q):
+                    val = self.feq[gidx][i](dens, *v) * np.ones(b.shape)
+                    val[~okmask] = np.inf
+                    val[..., b.lat[-1]:] = 0.0
+                    for arr in self.d[gidx]:
+                        if arr is not None:
+                            arr[i] = val
+        self.rho, self.phi = np.array(rho, float).copy(), np.array(phi, float).copy()
+        self.v = [np.array(c, float).copy() for c in v]
+
+    def _io(self, gidx):
+        a, bb = self.d[gidx]
+        if bb is None:
+            return a, a
+        return (a, bb) if (self.iteration & 1) == 0 else (bb, a)
+
+    def current(self, gidx):
+        a, bb = self.d[gidx]
+        return a if (bb is None or (self.iteration & 1) == 0) else bb
+
+    def _load(self, din, idx, odd):
+        g, D, Q = self.g, self.D, self.Q
+        f = np.zeros((Q, idx[0].size))
+        for i in range(Q):
+            if not odd:
+                f[i] = din[i][idx]
+            else:
+                e = [int(c) for c in g.basis[i]]
+                f[i] = din[g.idx_opposite[i]][tuple(idx[k] - e[D - 1 - k] for k in range(D))]
+        return f
+
+    def step(self):
+        b, g, D, Q = self.base, self.g, self.D, self.Q
+        it = self.iteration
+        odd = self.aa and (it & 1)
+        # ShanChenPrepareMacroFields: wet nodes only
+        idx = np.nonzero(b.active & b.wet)
+        ti = [1.0 / t for t in self.tau]
+        f0 = self._load(self._io(0)[0], idx, odd)
+        f1 = self._load(self._io(1)[0], idx, odd)
+        rho0, rho1 = self.rho_std(*f0), self.rho_std(*f1)
+        total = ti[0] * rho0 + ti[1] * rho1
+        self.rho[idx], self.phi[idx] = rho0, rho1
+        for d in range(D):
+            self.v[d][idx] = (ti[0] * self.mom[d](*f0) + ti[1] * self.mom[d](*f1)) / total
+        # ApplyMacroPeriodicBoundaryConditions (kernel_utils.mako:410-474), x, y, z passes
+        for field in (self.rho, self.phi):
+            for axis in range(D):
+                if not b.periodic[axis]:
+                    continue
+                ax = D - 1 - axis
+                n = b.lat[ax]
+                sl = lambda c: tuple(c if k == ax else (slice(0, b.lat[-1]) if k == D - 1 else slice(None)) for k in range(D))
+                src = field[sl(n - 2)]; dst = field[sl(0)]; ok = np.isfinite(src); dst[ok] = src[ok]
+                src = field[sl(1)]; dst = field[sl(n - 1)]; ok = np.isfinite(src); dst[ok] = src[ok]
+        # ShanChenCollideAndPropagate{0,1}
+        idx = np.nonzero(b.active)
+        N = idx[0].size
+        wet = b.wet[idx]
+        fields = [self.rho, self.phi]
+        wall = b.is_cls(nt.NTFullBBWall)[idx] if nt.NTFullBBWall in self.ctx['node_types'] else np.zeros(N, bool)
+        for gidx in range(2):
+            din, dout = self._io(gidx)
+            gm = fields[gidx][idx]
+            acc = np.zeros((D, N))
+            for k in range(2):
+                Gc = self.G[gidx][k]
+                if Gc == 0.0:
+                    continue
+                force = np.zeros((D, N))
+                for i in range(1, Q):
+                    e = [int(c) for c in g.basis[i]]
+                    nb = tuple(idx[kk] + e[D - 1 - kk] for kk in range(D))
+                    psi = self.ppot(fields[k][nb])
+                    for d in range(D):
+                        if e[d]:
+                            force[d] += psi * (e[d] * float(g.weights[i]))
+                acc += force * (-self.ppot(gm) * Gc)
+            with np.errstate(all='ignore'):
+                acc = np.where(wet, acc / gm, 0.0)
+            f = self._load(din, idx, odd)
+            v = np.array([self.v[d][idx] for d in range(D)])
+            if wall.any():
+                for i in sym.bb_swap_pairs(g):
+                    j = g.idx_opposite[i]
+                    t = f[i, wall].copy(); f[i, wall] = f[j, wall]; f[j, wall] = t
+            s = wet
+            v0 = v[:, s] + 0.5 * acc[:, s]
+            omega = 1.0 / self.tau[gidx]
+            for i in range(Q):
+                f[i, s] += omega * (self.feq[gidx][i](gm[s], *v0) - f[i, s])
+            pref = self.guo_pref[gidx](gm[s], self.tau[gidx])
+            for i in range(Q):
+                f[i, s] += self.guo[gidx][i](pref, *v0, *acc[:, s])
+            if self.aa and not odd:
+                for i in range(Q):
+                    dout[g.idx_opposite[i]][idx] = f[i]
+            else:
+                for i in range(Q):
+                    e = [int(c) for c in g.basis[i]]
+                    ok = np.ones(N, bool)
+                    for k in range(D):
+                        c = e[D - 1 - k]
+                        if c > 0:
+                            ok &= idx[k] < b.lat[k] - 1
+                        elif c < 0:
+                            ok &= idx[k] > 0
+                    dout[i][tuple(idx[k][ok] + e[D - 1 - k] for k in range(D))] = f[i, ok]
+            b._pbc(dout, swap=(self.aa and not odd))
+        self.iteration += 1
