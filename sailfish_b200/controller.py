@@ -106,22 +106,18 @@ class LBSimulationController(object):
         self.runners = []
         for s in mine:
             sim = self._lb_class(self.config)
-            r = SubdomainRunner(sim, s, output=LBOutput(self.config, s.id), device=devices[s.id])
+            runner_cls = self._lb_class.subdomain_runner or SubdomainRunner
+            r = runner_cls(sim, s, output=LBOutput(self.config, s.id), device=devices[s.id])
             r.initialize()
             self.runners.append(r)
         self._link(dist_mode, rank, ws)
         return self
 
     def _link(self, dist_mode, rank, ws):
-        """Exchanges lattice/semaphore addresses between neighbours: plain pointers inside one
-        process, CUDA IPC handles (backend_cuda.py:122-126 wraps them, never uses them) across
-        ranks."""
+        """Exchanges buffer addresses between neighbours: plain pointers inside one process, CUDA
+        IPC handles (backend_cuda.py:122-126 wraps them, never uses them) across ranks."""
         axis = self.dim - 1
-        infos = {}
-        for r in self.runners:
-            d = r._dev
-            infos[r._spec.id] = dict(dist_a=int(d.d_dist_a), dist_b=int(d.d_dist_b) if d.d_dist_b else 0,
-                                     lat_n=r._lat_size[0], arr_n=r._physical_size[0], sems=int(r._sems))
+        by_id = dict((r._spec.id, r) for r in self.runners)
         remote = {}
         if dist_mode:
             import torch.distributed as dist
@@ -130,36 +126,28 @@ class LBSimulationController(object):
             mine = self.runners[0]
             be = mine.backend
             payload = dict(id=mine._spec.id, lat_n=mine._lat_size[0], arr_n=mine._physical_size[0],
-                           dist_a=be.ipc_handle(mine._dev.d_dist_a),
-                           dist_b=be.ipc_handle(mine._dev.d_dist_b) if mine._dev.d_dist_b else None,
-                           sems=be.ipc_handle(mine._sems))
+                           bufs=dict((k, be.ipc_handle(v) if v else None) for k, v in mine.export_buffers().items()))
             gathered = [None] * ws
             dist.all_gather_object(gathered, payload)
             needed = set(mine._spec._face_conn.values())
             for g in gathered:
                 if g['id'] in needed and g['id'] != mine._spec.id:
-                    remote[g['id']] = dict(
-                        dist_a=int(be.ipc_handle_wrap(g['dist_a'])),
-                        dist_b=int(be.ipc_handle_wrap(g['dist_b'])) if g['dist_b'] else 0,
-                        lat_n=g['lat_n'], arr_n=g['arr_n'], sems=int(be.ipc_handle_wrap(g['sems'])))
+                    remote[g['id']] = dict(lat_n=g['lat_n'], arr_n=g['arr_n'],
+                                           bufs=dict((k, int(be.ipc_handle_wrap(h)) if h else 0)
+                                                     for k, h in g['bufs'].items()))
             self._dist = dist
-        by_id = dict((r._spec.id, r) for r in self.runners)
         for r in self.runners:
             for face, other in r._spec._face_conn.items():
                 if face // 2 != axis:
                     continue
-                side = face & 1
                 if other in by_id:
-                    info = infos[other]
-                    r.add_link(HaloLink(face, info['dist_a'], info['dist_b'], info['lat_n'], info['arr_n'],
-                                        peer_runner=by_id[other]))
+                    o = by_id[other]
+                    r.add_link(HaloLink(face, o.export_buffers(), o._lat_size[0], o._physical_size[0],
+                                        peer_runner=o))
                 else:
                     info = remote[other]
-                    # the neighbour receives through its opposite side: signal that semaphore
-                    peer_ready = info['sems'] + 4 * (1 - side)
-                    sp = r.sem_ptrs()
-                    r.add_link(HaloLink(face, info['dist_a'], info['dist_b'], info['lat_n'], info['arr_n'],
-                                        peer_ready, sp['ready'][side], sp['consumed'][side]))
+                    r.add_link(HaloLink(face, info['bufs'], info['lat_n'], info['arr_n'],
+                                        peer_sems=info['bufs']['sems'], my_sems=int(r._sems)))
 
     # -- running -------------------------------------------------------------------------------
     def barrier(self):

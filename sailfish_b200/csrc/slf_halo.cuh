@@ -83,6 +83,27 @@ int slf_halo_push(SlfPlan *pl, uint64_t dist, int face, uint64_t peer_dist, int 
   return 0;
 }
 
+int slf_halo_push_field(SlfPlan *pl, uint64_t field, int face, uint64_t peer_field, int peer_lat_n, uint64_t stream) {
+  if (!pl) return fail(SLF_EINVAL, "null plan");
+  const DevParams &d = pl->dp;
+  const int axis = pl->D - 1;
+  if ((face >> 1) != axis) return fail(SLF_EUNSUPPORTED, "halo push is implemented for the outermost axis only");
+  const int hi = face & 1;
+  const int n = axis == 2 ? d.nz : d.ny;
+  const long long plane = axis == 2 ? d.sz : d.sy;
+  if (plane % 4) return fail(SLF_EINVAL, "plane size must be a multiple of 4 floats");
+  HaloArgs a;
+  a.n = 1; a.plane = plane;
+  a.src[0] = (const float *)field + plane * (hi ? n - 2 : 1);             // first / last real layer
+  a.dst[0] = (float *)peer_field + plane * (hi ? 0 : peer_lat_n - 1);     // neighbour's ghost layer
+  const long long n4 = plane / 4;
+  int bx = (int)((n4 + 255) / 256);
+  if (bx > 592) bx = 592;
+  halo_push_kernel<<<dim3(bx, 1), 256, 0, (cudaStream_t)stream>>>(a);
+  LAUNCH_OK("halo_push_field");
+  return 0;
+}
+
 int slf_sem_signal(uint64_t sem, uint64_t stream) {
   sem_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned int *)sem);
   LAUNCH_OK("sem_signal");

@@ -1,0 +1,180 @@
+// slf_shan_chen.cuh -- binary Shan-Chen mixture (BASELINE config 5).
+//
+// Reference: templates/models/binary_shan_chen.mako:19-141 (ShanChenPrepareMacroFields,
+// ShanChenCollideAndPropagate{0,1}), templates/shan_chen.mako:9-84 (force stencil),
+// templates/models/lb_binary_fluid.mako:88-127 (SetInitialConditions),
+// relaxation.mako:99-181 + relaxation_common.mako:56-149 (BGK_relaxate{0,1} with Guo forcing),
+// kernel_utils.mako:410-474 (ApplyMacroPeriodicBoundaryConditions).
+//
+// Same three-pass structure as the reference (the density of the next step depends on the
+// neighbours' post-collision populations, so the macro pass cannot be folded into the collide
+// pass): per lattice update 2 x Q x 4 B are read by the macro pass and 2 x (2 Q x 4 B) moved by
+// the two collide passes, plus the 4 + 4 + 4 D bytes of rho, phi, v written once and read twice
+// (the 18-point psi stencil hits L1/L2): 516 B/LUP for D3Q19.
+#pragma once
+#include "slf_kernels.cuh"
+
+struct ScParams {
+  float tau0_inv, tau1_inv;   // 1.0f / tau, 1.0f / tau_phi   (lb_binary_fluid.mako:36-45)
+  float omega[2];             // (float)(1 / tau_g)
+  float tau[2];
+  float g[4];                 // G11, G12, G21, G22
+  int potential;
+};
+
+__device__ __forceinline__ float sc_ppot(int pot, float x) {
+  return pot == SLF_SC_CLASSIC ? 1.0f - expf(-x) : x;       // sym.py:896-908
+}
+
+template <class L>
+__device__ __forceinline__ bool sc_is_wet(const DevParams &P, uint32_t type) {
+  return type == P.tid[SLF_NT_FLUID];
+}
+
+// ShanChenPrepareMacroFields
+template <class L, int MODE>
+__global__ void __launch_bounds__(128)
+sc_prepare_macro(const DevParams P, const ScParams S, const uint32_t *__restrict__ map, const float *d1,
+                 const float *d2, float *__restrict__ orho, float *__restrict__ ophi,
+                 float *__restrict__ ovx, float *__restrict__ ovy, float *__restrict__ ovz, long long gi0,
+                 long long gi1) {
+  const long long gi = gi0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= gi1) return;
+  if ((map[gi] & P.tmask) != P.tid[SLF_NT_FLUID]) return;      // wet nodes only
+  float f[L::Q], rho0, rho1, j0[3], j1[3];
+  load_node<L, MODE>(P, d1, gi, f);
+  moments<L>(f, rho0, j0);
+  load_node<L, MODE>(P, d2, gi, f);
+  moments<L>(f, rho1, j1);
+  const float total = S.tau0_inv * rho0 + S.tau1_inv * rho1;
+  orho[gi] = rho0; ophi[gi] = rho1;
+  ovx[gi] = (S.tau0_inv * j0[0] + S.tau1_inv * j1[0]) / total;
+  ovy[gi] = (S.tau0_inv * j0[1] + S.tau1_inv * j1[1]) / total;
+  if (L::D == 3) ovz[gi] = (S.tau0_inv * j0[2] + S.tau1_inv * j1[2]) / total;
+}
+
+// ShanChenCollideAndPropagate<GRID>
+template <class L, int MODE, int GRID>
+__global__ void __launch_bounds__(128)
+sc_collide(const DevParams P, const ScParams S, const uint32_t *__restrict__ map, const float *din, float *dout,
+           const float *__restrict__ rho_f, const float *__restrict__ phi_f, const float *__restrict__ ovx,
+           const float *__restrict__ ovy, const float *__restrict__ ovz, long long gi0, long long gi1) {
+  const long long gi = gi0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= gi1) return;
+  const uint32_t type = map[gi] & P.tmask;
+  const bool fluid = type == P.tid[SLF_NT_FLUID];
+  const bool wall = type == P.tid[SLF_NT_FULLBB_WALL];
+  if (!fluid && !wall) return;
+  // full-way bounce-back is a no-op in the AA pattern (see collide_bulk_aa)
+  if (wall && MODE != MODE_AB && P.prop) return;
+
+  float f[L::Q];
+  load_node<L, MODE>(P, din, gi, f);
+  if (wall) {
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) {
+      if (!P.prop) dout[gi + P.DS * i] = f[L::opp(i)];
+      else dout[gi + noff<L>(P, i) + P.DS * i] = f[L::opp(i)];   // AB; walls next to the array edge are rejected at bind time
+    }
+    return;
+  }
+  const float *own = GRID == 0 ? rho_f : phi_f;
+  const float gm = own[gi];
+  // Shan-Chen force: F = -G psi(x) sum_i w_i e_i psi'(x + e_i), then acceleration a = F / density
+  float a[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const float G = S.g[2 * GRID + k];
+    if (G == 0.0f) continue;
+    const float *field = k == 0 ? rho_f : phi_f;
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+#pragma unroll
+    for (int i = 1; i < L::Q; i++) {
+      const float psi = sc_ppot(S.potential, field[gi + noff<L>(P, i)]);
+      if (L::ex(i)) fx = fmaf(psi, (float)L::ex(i) * L::w(i), fx);
+      if (L::ey(i)) fy = fmaf(psi, (float)L::ey(i) * L::w(i), fy);
+      if (L::D == 3 && L::ez(i)) fz = fmaf(psi, (float)L::ez(i) * L::w(i), fz);
+    }
+    const float c = -sc_ppot(S.potential, gm) * G;
+    a[0] = fmaf(fx, c, a[0]); a[1] = fmaf(fy, c, a[1]); a[2] = fmaf(fz, c, a[2]);
+  }
+  const float ig = 1.0f / gm;
+  a[0] *= ig; a[1] *= ig; a[2] *= ig;
+
+  float v0[3] = {fmaf(0.5f, a[0], ovx[gi]), fmaf(0.5f, a[1], ovy[gi]), L::D == 3 ? fmaf(0.5f, a[2], ovz[gi]) : 0.f};
+  if (P.relax) {
+    const float vv = v0[0] * v0[0] + v0[1] * v0[1] + (L::D == 3 ? v0[2] * v0[2] : 0.f);
+    const float base = fmaf(-1.5f, vv, 1.0f);
+    const float omega = S.omega[GRID];
+    const float pref = gm * 3.0f * (1.0f - 1.0f / (2.0f * S.tau[GRID]));
+    const float av = a[0] * v0[0] + a[1] * v0[1] + (L::D == 3 ? a[2] * v0[2] : 0.f);
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) {
+      const float ev = edotv<L>(i, v0);
+      const float feq = L::w(i) * gm * fmaf(ev, fmaf(4.5f, ev, 3.0f), base);
+      const float ea = edotv<L>(i, a);
+      f[i] = fmaf(omega, feq - f[i], f[i]) + pref * L::w(i) * (ea - av + 3.0f * ev * ea);
+    }
+  }
+  if (!P.prop) {
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) dout[gi + P.DS * i] = f[i];
+  } else if (MODE == MODE_AA_EVEN) {
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) dout[gi + P.DS * L::opp(i)] = f[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) dout[gi + noff<L>(P, i) + P.DS * i] = f[i];
+  }
+}
+
+// SetInitialConditions of the binary model
+template <class L>
+__global__ void __launch_bounds__(256)
+sc_set_initial_conditions(const DevParams P, const uint32_t *__restrict__ map, float *__restrict__ d1,
+                          float *__restrict__ d2, const float *__restrict__ ivx, const float *__restrict__ ivy,
+                          const float *__restrict__ ivz, const float *__restrict__ irho,
+                          const float *__restrict__ iphi) {
+  const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= P.DS) return;
+  const int x = (int)(gi % P.ax);
+  const long long t = gi / P.ax;
+  const int y = (int)(t % P.ay), z = (int)(t / P.ay);
+  if (x >= P.nx || y >= P.ny || z >= P.nz) return;
+  const uint32_t type = map[gi] & P.tmask;
+  const int cls = node_class<L>(P, type);
+  const bool wet = cls == SLF_NT_FLUID || cls == SLF_NT_HALFBB_WALL || cls == SLF_NT_EQUILIBRIUM_VELOCITY ||
+                   cls == SLF_NT_EQUILIBRIUM_DENSITY || cls == SLF_NT_REGULARIZED_VELOCITY ||
+                   cls == SLF_NT_REGULARIZED_DENSITY || cls == SLF_NT_DO_NOTHING;
+  if (!wet && cls != SLF_NT_FULLBB_WALL) {
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) { d1[gi + P.DS * i] = INFINITY; d2[gi + P.DS * i] = INFINITY; }
+    return;
+  }
+  float v[3] = {ivx[gi], ivy[gi], L::D == 3 ? ivz[gi] : 0.f};
+  float feq[L::Q];
+  equilibrium<L>(irho[gi], v, feq);
+#pragma unroll
+  for (int i = 0; i < L::Q; i++) d1[gi + P.DS * i] = feq[i];
+  equilibrium<L>(iphi[gi], v, feq);
+#pragma unroll
+  for (int i = 0; i < L::Q; i++) d2[gi + P.DS * i] = feq[i];
+}
+
+// ApplyMacroPeriodicBoundaryConditions: ghost <- opposite real layer, both sides, if finite
+__global__ void __launch_bounds__(128)
+macro_pbc(const DevParams P, float *field, int axis, int dim) {
+  const int n1 = axis == 0 ? P.ny : P.nx;
+  const int n2 = dim == 3 ? (axis == 2 ? P.ny : P.nz) : 1;
+  const int i1 = blockIdx.x * blockDim.x + threadIdx.x, i2 = blockIdx.y;
+  if (i1 >= n1 || i2 >= n2) return;
+  int x = 0, y = 0, z = 0;
+  if (axis == 0) { y = i1; z = i2; } else if (axis == 1) { x = i1; z = i2; } else { x = i1; y = i2; }
+  const long long stride = axis == 0 ? 1 : (axis == 1 ? P.sy : P.sz);
+  const int n = axis == 0 ? P.nx : (axis == 1 ? P.ny : P.nz);
+  const long long base = (long long)x + P.sy * y + P.sz * z;   // coordinate along `axis` is 0 here
+  const float hi = field[base + stride * (n - 2)];
+  if (isfinite(hi)) field[base] = hi;
+  const float lo = field[base + stride];
+  if (isfinite(lo)) field[base + stride * (n - 1)] = lo;
+}

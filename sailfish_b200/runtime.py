@@ -140,3 +140,117 @@ class DeviceLattice(object):
         assert dist.shape == (self.Q,) + self.shape
         self.sync()
         self.lib.call('slf_memcpy_h2d', int(self.current_dist_buf()), dist.ctypes.data_as(_vp), int(dist.nbytes))
+
+
+class DeviceShanChenLattice(object):
+    """Binary Shan-Chen mixture on the device: two lattices, rho / phi / v fields and the
+    three-pass step of NNSubdomainRunner.step (sailfish/subdomain_runner.py:2102-2197):
+    ShanChenPrepareMacroFields -> macro PBC (+ field halo) -> ShanChenCollideAndPropagate0/1 ->
+    distribution PBC (+ plane halo)."""
+
+    def __init__(self, params, node_map, rho, phi, v, device=0, backend=None, host_fields=None):
+        self.be = backend or bk.B200Backend(None, device)
+        self.lib = bk.lib()
+        self.p = params
+        self.plan = self.be.build(params)
+        self.n = params.dist_size
+        self.dim = params.dim
+        self.Q = params.Q
+        self.aa = params.access_pattern == P.ACCESS_IDS['AA']
+        self.shape = ((params.arr_nz,) if self.dim == 3 else ()) + (params.arr_ny, params.arr_nx)
+        f32 = np.float32
+        self.h_map = np.ascontiguousarray(node_map, dtype=np.uint32).reshape(self.shape)
+        if host_fields is not None:
+            self.h_rho, self.h_phi, self.h_v = host_fields[0], host_fields[1], list(host_fields[2])
+        else:
+            def pin(a):
+                b = self.be.alloc_async_host_buf(self.shape, f32)
+                b[:] = np.asarray(a, dtype=f32).reshape(self.shape)
+                return b
+            self.h_rho, self.h_phi, self.h_v = pin(rho), pin(phi), [pin(c) for c in v]
+        self.d_map = self.be.alloc_buf(like=self.h_map)
+        self.d_rho = self.be.alloc_buf(like=self.h_rho)
+        self.d_phi = self.be.alloc_buf(like=self.h_phi)
+        self.d_v = [self.be.alloc_buf(like=a) for a in self.h_v]
+        nbytes = self.Q * self.n * 4
+        self.d_dist = [[self.be.alloc_buf(size=nbytes), None if self.aa else self.be.alloc_buf(size=nbytes)]
+                       for _ in range(2)]
+        self.iteration = 0
+        self.stream = self.be.make_stream()
+        self.set_initial_conditions()
+
+    def _vz(self):
+        return int(self.d_v[2]) if self.dim == 3 else 0
+
+    def set_initial_conditions(self):
+        for k in (0, 1):
+            if self.d_dist[0][k] is None:
+                continue
+            self.lib.call('slf_sc_set_initial_conditions', self.plan, int(self.d_map), int(self.d_dist[0][k]),
+                          int(self.d_dist[1][k]), int(self.d_v[0]), int(self.d_v[1]), self._vz(),
+                          int(self.d_rho), int(self.d_phi), self.stream.handle)
+        self.iteration = 0
+
+    def io_dists(self, g):
+        a, b = self.d_dist[g]
+        if b is None:
+            return a, a
+        return (a, b) if (self.iteration & 1) == 0 else (b, a)
+
+    def current_dist_buf(self, g):
+        a, b = self.d_dist[g]
+        return a if (b is None or (self.iteration & 1) == 0) else b
+
+    def macro(self, z_begin=0, z_end=-1, stream=None):
+        self.lib.call('slf_sc_prepare_macro_fields', self.plan, int(self.d_map), int(self.io_dists(0)[0]),
+                      int(self.io_dists(1)[0]), int(self.d_rho), int(self.d_phi), int(self.d_v[0]),
+                      int(self.d_v[1]), self._vz(), 0, self.iteration, z_begin, z_end,
+                      (stream or self.stream).handle)
+
+    def macro_pbc(self, stream=None):
+        for axis in range(self.dim):
+            if self.p.periodic[axis]:
+                for f in (self.d_rho, self.d_phi):
+                    self.lib.call('slf_apply_macro_periodic_boundary_conditions', self.plan, int(f), axis,
+                                  (stream or self.stream).handle)
+
+    def collide(self, z_begin=0, z_end=-1, stream=None):
+        for g in (0, 1):
+            din, dout = self.io_dists(g)
+            self.lib.call('slf_sc_collide_and_propagate', self.plan, g, int(self.d_map), int(din), int(dout),
+                          int(self.d_rho), int(self.d_phi), int(self.d_v[0]), int(self.d_v[1]), self._vz(), 0,
+                          self.iteration, z_begin, z_end, (stream or self.stream).handle)
+
+    def dist_pbc(self, stream=None):
+        swap = int(self.aa and (self.iteration & 1) == 0)
+        for axis in range(self.dim):
+            if self.p.periodic[axis]:
+                for g in (0, 1):
+                    self.lib.call('slf_apply_periodic_boundary_conditions', self.plan, int(self.io_dists(g)[1]),
+                                  axis, swap, (stream or self.stream).handle)
+
+    def step(self):
+        self.macro()
+        self.macro_pbc()
+        self.collide()
+        self.dist_pbc()
+        self.iteration += 1
+
+    def run(self, steps):
+        for _ in range(steps):
+            self.step()
+
+    def sync(self):
+        self.stream.synchronize()
+
+    def fields_to_host(self):
+        self.sync()
+        for b in [self.d_rho, self.d_phi] + self.d_v:
+            self.be.from_buf(b)
+        return self.h_rho, self.h_phi, self.h_v
+
+    def get_dist(self, g):
+        self.sync()
+        out = np.zeros((self.Q,) + self.shape, dtype=np.float32)
+        self.lib.call('slf_memcpy_d2h', out.ctypes.data_as(_vp), int(self.current_dist_buf(g)), int(out.nbytes))
+        return out

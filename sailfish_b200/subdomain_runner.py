@@ -26,22 +26,34 @@ _u64 = ctypes.c_uint64
 class HaloLink(object):
     """One directed neighbour relation across the split axis.
 
-    Same process (several subdomains driven by one process, the reference's "several
-    subdomains per GPU" regtest mode): ``peer_runner`` is set and ordering uses CUDA events.
-    Other rank: the neighbour's lattice and semaphore are CUDA-IPC mappings and ordering uses
-    the stream-ordered device semaphores of slf_sem_signal / slf_sem_wait."""
+    ``peer_bufs`` maps buffer names ('dist0a', 'dist0b', [dist1a, dist1b, rho, phi]) to the
+    neighbour's device pointers as seen from this process.  Same process (several subdomains
+    driven by one process, the reference's "several subdomains per GPU" regtest mode):
+    ``peer_runner`` is set and ordering uses CUDA events.  Other rank: the pointers are CUDA-IPC
+    mappings and ordering uses the stream-ordered device semaphores slf_sem_signal/slf_sem_wait:
+    ``peer_sems`` is the neighbour's semaphore block, ``my_sems`` this runner's."""
 
-    def __init__(self, face, peer_dist_a, peer_dist_b, peer_lat_n, peer_arr_n, peer_ready=0,
-                 my_ready=0, my_consumed=0, peer_runner=None):
+    def __init__(self, face, peer_bufs, peer_lat_n, peer_arr_n, peer_sems=0, my_sems=0, peer_runner=None):
         self.face = face
-        self.peer_dist_a = int(peer_dist_a)
-        self.peer_dist_b = int(peer_dist_b) if peer_dist_b else 0
+        self.side = face & 1
+        self.peer_bufs = dict((k, int(v) if v else 0) for k, v in peer_bufs.items())
         self.peer_lat_n = int(peer_lat_n)
         self.peer_arr_n = int(peer_arr_n)
-        self.peer_ready = int(peer_ready)
-        self.my_ready = int(my_ready)
-        self.my_consumed = int(my_consumed)
+        self.peer_sems = int(peer_sems)
+        self.my_sems = int(my_sems)
         self.peer_runner = peer_runner
+
+    # semaphore block layout (uint32 words): channel c in {0: populations, 1: macro fields}
+    #   ready[c][side] at 8*c + side, consumed[c][side] at 8*c + 2 + side
+    def my_ready(self, channel):
+        return self.my_sems + 4 * (8 * channel + self.side)
+
+    def my_consumed(self, channel):
+        return self.my_sems + 4 * (8 * channel + 2 + self.side)
+
+    def peer_ready(self, channel):
+        # the neighbour receives through its opposite side
+        return self.peer_sems + 4 * (8 * channel + (1 - self.side))
 
 
 class LBOutput(object):
@@ -177,9 +189,8 @@ class SubdomainRunner(object):
                                   host_fields=(self.field_base(sim.rho), [self.field_base(c) for c in sim.v]))
         self._calc_stream = self._dev.stream
         self._data_stream = self.backend.make_stream(high_priority=True)
-        # semaphores: [ready_low, ready_high, consumed_low, consumed_high]
-        self._sems = self.backend.alloc_buf(size=64)
-        self._push_events = [self.backend.make_event(self._data_stream), self.backend.make_event(self._data_stream)]
+        self._sems = self.backend.alloc_buf(size=128)     # see HaloLink for the layout
+        self._push_events = [[self.backend.make_event(self._data_stream) for _ in range(2)] for _ in range(2)]
         self._slab_event = self.backend.make_event(self._calc_stream)
 
     def initialize(self):
@@ -212,15 +223,23 @@ class SubdomainRunner(object):
         return self._subdomain.num_fluid_nodes
 
     # -- halo ------------------------------------------------------------------------------------
-    def sem_ptrs(self):
-        base = int(self._sems)
-        return {'ready': {0: base, 1: base + 4}, 'consumed': {0: base + 8, 1: base + 12}}
+    def export_buffers(self):
+        """Device buffers neighbours write into (name -> pointer)."""
+        d = self._dev
+        return {'dist0a': int(d.d_dist_a), 'dist0b': int(d.d_dist_b) if d.d_dist_b else 0, 'sems': int(self._sems)}
 
     def add_link(self, link):
         self._links[link.face & 1] = link
 
     def _outer_n(self):
         return self._lat_size[0]
+
+    def _wait_incoming(self, channel, it_prev, stream):
+        for side, link in self._links.items():
+            if link.peer_runner is not None:
+                stream.wait_for_event(link.peer_runner._push_events[channel][it_prev & 1])
+            else:
+                self._lib.call('slf_sem_wait', link.my_ready(channel), link.my_consumed(channel), stream.handle)
 
     # -- stepping ---------------------------------------------------------------------------------
     def step(self, sync_req):
@@ -240,11 +259,7 @@ class SubdomainRunner(object):
             if it > 0:
                 # the neighbours' planes of the previous step must have landed (and, symmetrically,
                 # the neighbours are done with the layers this step's push overwrites)
-                for side, link in links.items():
-                    if link.peer_runner is not None:
-                        cs.wait_for_event(link.peer_runner._push_events[(it - 1) & 1])
-                    else:
-                        self._lib.call('slf_sem_wait', link.my_ready, link.my_consumed, cs.handle)
+                self._wait_incoming(0, it - 1, cs)
             if local_pbc:
                 # periodic x/y inside a z-split: the PBC kernels need the whole step and must run
                 # before the planes leave (they complete the x/y ghost ring of those planes)
@@ -264,7 +279,7 @@ class SubdomainRunner(object):
                 self._push_all(swap, ds, it)
                 if hi > lo:
                     dev.collide(save_macro=sync_req, z_begin=lo, z_end=hi, stream=cs)
-                cs.wait_for_event(self._push_events[it & 1])
+                cs.wait_for_event(self._push_events[0][it & 1])
         dev.iteration += 1
         self._sim.iteration += 1
 
@@ -273,15 +288,15 @@ class SubdomainRunner(object):
         _, dout = dev.io_dists()
         for side, link in self._links.items():
             if dev.aa:
-                peer = link.peer_dist_a
+                peer = link.peer_bufs['dist0a']
             else:
                 # the neighbour's output lattice of this step has the same parity as ours
-                peer = link.peer_dist_b if (it & 1) == 0 else link.peer_dist_a
+                peer = link.peer_bufs['dist0b'] if (it & 1) == 0 else link.peer_bufs['dist0a']
             self._lib.call('slf_halo_push', dev.plan, int(dout), link.face, peer, link.peer_lat_n,
                            link.peer_arr_n, swap, stream.handle)
             if link.peer_runner is None:
-                self._lib.call('slf_sem_signal', link.peer_ready, stream.handle)
-        self._push_events[it & 1].record(stream)
+                self._lib.call('slf_sem_signal', link.peer_ready(0), stream.handle)
+        self._push_events[0][it & 1].record(stream)
 
     def run_steps(self, n, save_last=False):
         """n steps without output; issued from C when the subdomain has no neighbours."""
@@ -333,3 +348,110 @@ class SubdomainRunner(object):
     def sync(self):
         self._calc_stream.synchronize()
         self._data_stream.synchronize()
+
+
+class NNSubdomainRunner(SubdomainRunner):
+    """Runner for models whose collision needs neighbour values of macroscopic fields (binary
+    Shan-Chen, BASELINE config 5): mirror of sailfish/subdomain_runner.py:1840-2197.  Per step:
+    ShanChenPrepareMacroFields -> macro PBC -> field ghost layers to the neighbours ->
+    ShanChenCollideAndPropagate0/1 -> distribution PBC -> population planes to the neighbours."""
+
+    def _init_fields(self):
+        sim = self._sim
+        sim.rho, _ = self.make_scalar_field(name='rho')
+        sim.phi, _ = self.make_scalar_field(name='phi')
+        sim.v = self.make_vector_field(name='v')
+        for i, c in enumerate('xyz'[:self.dim]):
+            setattr(sim, 'v' + c, sim.v[i])
+        self._subdomain.init_fields(sim)
+
+    def make_params(self):
+        sd, cfg, g = self._subdomain, self.config, self._sim.grid
+        lat = list(reversed(sd.lat_shape)) + ([1] if self.dim == 2 else [])
+        arr = list(reversed(sd.arr_shape)) + ([1] if self.dim == 2 else [])
+        per = list(self._spec._periodicity) + [False] * (3 - self.dim)
+        unsupported = set(sd.type_ids_by_name()) - {'_NTFluid', '_NTGhost', '_NTUnused', '_NTPropagationOnly',
+                                                    'NTFullBBWall'}
+        if unsupported:
+            raise P.UnsupportedConfiguration('Shan-Chen path supports fluid and full-way bounce-back nodes; got %s'
+                                             % sorted(unsupported))
+        return P.make_params(
+            g.name, 'bgk', cfg.access_pattern, lat, arr, per, sd.bits, sd.type_ids_by_name(),
+            sd.node_params, cfg.visc, None, use_link_tags=getattr(cfg, 'use_link_tags', True),
+            shan_chen=dict(tau_phi=cfg.tau_phi, G11=cfg.G11, G12=cfg.G12, G21=cfg.G12, G22=cfg.G22,
+                           potential=cfg.sc_potential))
+
+    def _init_compute(self):
+        from sailfish_b200.runtime import DeviceShanChenLattice
+        self._params = self.make_params()
+        sim = self._sim
+        fb = self.field_base
+        self._dev = DeviceShanChenLattice(self._params, self._subdomain.encoded_map(), fb(sim.rho), fb(sim.phi),
+                                          [fb(c) for c in sim.v], backend=self.backend,
+                                          host_fields=(fb(sim.rho), fb(sim.phi), [fb(c) for c in sim.v]))
+        self._calc_stream = self._dev.stream
+        self._data_stream = self.backend.make_stream(high_priority=True)
+        self._sems = self.backend.alloc_buf(size=128)
+        self._push_events = [[self.backend.make_event(self._data_stream) for _ in range(2)] for _ in range(2)]
+        self._slab_event = self.backend.make_event(self._calc_stream)
+
+    def gpu_field(self, field):
+        if isinstance(field, list):
+            return list(self._dev.d_v)
+        return self._dev.d_phi if field is self._sim.phi else self._dev.d_rho
+
+    def gpu_dist(self, num, copy):
+        a, b = self._dev.d_dist[num]
+        return a if (copy == 0 or b is None) else b
+
+    def _debug_get_dist(self, output=True, grid_num=0):
+        return self._dev.get_dist(grid_num)
+
+    def export_buffers(self):
+        d = self._dev
+        out = {'rho': int(d.d_rho), 'phi': int(d.d_phi), 'sems': int(self._sems)}
+        for g in (0, 1):
+            out['dist%da' % g] = int(d.d_dist[g][0])
+            out['dist%db' % g] = int(d.d_dist[g][1]) if d.d_dist[g][1] else 0
+        return out
+
+    def step(self, sync_req):
+        dev = self._dev
+        it = dev.iteration
+        cs = self._calc_stream
+        links = self._links
+        if links and it > 0:
+            self._wait_incoming(0, it - 1, cs)
+        dev.macro(stream=cs)
+        dev.macro_pbc(stream=cs)
+        if links:
+            for side, link in links.items():
+                for name, buf in (('rho', dev.d_rho), ('phi', dev.d_phi)):
+                    self._lib.call('slf_halo_push_field', dev.plan, int(buf), link.face, link.peer_bufs[name],
+                                   link.peer_lat_n, cs.handle)
+                if link.peer_runner is None:
+                    self._lib.call('slf_sem_signal', link.peer_ready(1), cs.handle)
+            self._push_events[1][it & 1].record(cs)
+            self._wait_incoming(1, it, cs)
+        dev.collide(stream=cs)
+        dev.dist_pbc(stream=cs)
+        if links:
+            swap = int(dev.aa and (it & 1) == 0)
+            for side, link in links.items():
+                for g in (0, 1):
+                    _, dout = dev.io_dists(g)
+                    if dev.aa:
+                        peer = link.peer_bufs['dist%da' % g]
+                    else:
+                        peer = link.peer_bufs['dist%db' % g] if (it & 1) == 0 else link.peer_bufs['dist%da' % g]
+                    self._lib.call('slf_halo_push', dev.plan, int(dout), link.face, peer, link.peer_lat_n,
+                                   link.peer_arr_n, swap, cs.handle)
+                if link.peer_runner is None:
+                    self._lib.call('slf_sem_signal', link.peer_ready(0), cs.handle)
+            self._push_events[0][it & 1].record(cs)
+        dev.iteration += 1
+        self._sim.iteration += 1
+
+    def run_steps(self, n, save_last=False):
+        for k in range(n):
+            self.step(False)

@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 
 from sailfish_b200.controller import LBSimulationController  # noqa: E402
 from sailfish_b200.geo import EqualSubdomainsGeometry3D  # noqa: E402
-from sailfish_b200.examples import ldc_3d, poiseuille_3d  # noqa: E402
+from sailfish_b200.examples import ldc_3d, poiseuille_3d, sc_separation_3d  # noqa: E402
 
 CASES = {
     'ldc3d': (ldc_3d.LDCSim, ['--lat_nx=40', '--lat_ny=36', '--lat_nz=64', '--visc=0.04']),
@@ -22,6 +22,7 @@ CASES = {
                       ['--lat_nx=20', '--lat_ny=20', '--lat_nz=32', '--flow_direction=z', '--drive=force']),
     'poi3d_force_x': (poiseuille_3d.PoiseuilleSim,
                       ['--lat_nx=24', '--lat_ny=20', '--lat_nz=32', '--flow_direction=x', '--drive=force']),
+    'sc3d': (sc_separation_3d.SeparationSCSim, ['--lat_nx=20', '--lat_ny=18', '--lat_nz=32', '--seed=5']),
 }
 
 
@@ -33,6 +34,16 @@ def run(cls, args, steps, single=False):
     ctrl.setup(args + ['--quiet'])
     if single:
         os.environ.update(saved)
+    for r in ctrl.runners:
+        if hasattr(r._sim, 'phi'):       # decomposition-independent initial state for the mixture
+            sim, spec = r._sim, r._spec
+            hz, hy, hx = np.meshgrid(np.arange(spec.oz, spec.oz + spec.nz), np.arange(spec.ny), np.arange(spec.nx),
+                                     indexing='ij')
+            sim.rho[:] = 1.0 + 1e-3 * np.sin(0.7 * hx + 1.3 * hy + 0.4 * hz)
+            sim.phi[:] = 1.0 + 1e-3 * np.cos(0.5 * hx - 0.9 * hy + 1.1 * hz)
+            for b in (r._dev.d_rho, r._dev.d_phi):
+                r._dev.be.to_buf(b)
+            r._dev.set_initial_conditions()
     for k in range(steps):
         for r in ctrl.runners:
             r.step(k == steps - 1)
@@ -41,7 +52,8 @@ def run(cls, args, steps, single=False):
     for r in ctrl.runners:
         r._fields_to_host()
         sl = r._spec._nonghost_slice
-        out.append((r._spec.location[2], np.array([np.array(r.field_base(r._sim.rho))[sl]] +
+        extra = [np.array(r.field_base(r._sim.phi))[sl]] if hasattr(r._sim, 'phi') else []
+        out.append((r._spec.location[2], np.array([np.array(r.field_base(r._sim.rho))[sl]] + extra +
                                                    [np.array(r.field_base(c))[sl] for c in r._sim.v])))
     return out
 

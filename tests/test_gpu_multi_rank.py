@@ -16,7 +16,7 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize('name,ap', [('ldc3d', 'AA'), ('ldc3d', 'AB'), ('poi3d_force_z', 'AA'), ('poi3d_force_x', 'AA')])
+@pytest.mark.parametrize('name,ap', [('ldc3d', 'AA'), ('ldc3d', 'AB'), ('poi3d_force_z', 'AA'), ('poi3d_force_x', 'AA'), ('sc3d', 'AA'), ('sc3d', 'AB')])
 def test_ranks_equal_single_subdomain(name, ap):
     n = _ngpu()
     if n < 2:

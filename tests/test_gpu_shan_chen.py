@@ -1,0 +1,67 @@
+"""Binary Shan-Chen (BASELINE config 5) on the device vs the oracle / the reference-derived goldens."""
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+ALL = [n + '_' + ap for n in util.SC_CASES for ap in ('AB', 'AA')]
+
+
+def gpu_run(c, steps):
+    from sailfish_b200.runtime import DeviceShanChenLattice
+    p = util.params_from_case(c)
+    dev = DeviceShanChenLattice(p, c['map'], c['rho0'], c['phi0'], c['v0'])
+    dev.run(steps)
+    rho, phi, v = dev.fields_to_host()
+    return dev.get_dist(0), dev.get_dist(1), np.array(rho), np.array(phi), [np.array(x) for x in v]
+
+
+def errs(g, ref, c):
+    m = util.real_mask(c)
+    wet = np.zeros(m.shape, bool)
+    wet[m] = c['fluid_map'].reshape(-1)
+    out = [util.rel_linf(g[0][:, wet], ref[0][:, wet]), util.rel_linf(g[1][:, wet], ref[1][:, wet]),
+           util.rel_linf(g[2][wet], ref[2][wet]), util.rel_linf(g[3][wet], ref[3][wet])]
+    vs = max(1e-30, np.abs(np.array([x[wet] for x in ref[4]])).max())
+    out.append(float(np.abs(np.array([a[wet] - b[wet] for a, b in zip(g[4], ref[4])])).max() / vs))
+    return out
+
+
+def oracle_run(oracle, c, dtype, steps):
+    p = util.params_from_case(c)
+    sim = oracle.ShanChenSimulation(p, c['map'], c['rho0'], c['phi0'], c['v0'], dtype=dtype)
+    sim.run(steps)
+    shp = c['dist1'].shape
+    s = c['map'].shape
+    return (sim.current(0).reshape(shp), sim.current(1).reshape(shp), sim.rho.reshape(s), sim.phi.reshape(s),
+            [x.reshape(s) for x in sim.v])
+
+
+@pytest.mark.parametrize('case', ALL)
+def test_shan_chen_parity(oracle, case):
+    c = util.load_case(case)
+    steps = int(c['steps'])
+    g = gpu_run(c, steps)
+    r64 = oracle_run(oracle, c, np.float64, steps)
+    r32 = oracle_run(oracle, c, np.float32, steps)
+    eg, eo = errs(g, r64, c), errs(r32, r64, c)
+    # populations and densities: within the fp32 round-off envelope of the reference arithmetic
+    for a, b in zip(eg[:4], eo[:4]):
+        assert a <= 2.0 * b + 1e-6, (eg, eo)
+    # the common velocity is O(1e-5) here (a difference of O(1) populations): compare its
+    # absolute error with the fp32 oracle's
+    assert eg[4] <= 2.0 * eo[4] + 1e-3, (eg, eo)
+    gold = (c['dist1'], c['dist2'], c['rho'], c['phi'], list(c['v']))
+    egold = errs(g, gold, c)
+    for a, b in zip(egold[:4], eo[:4]):
+        assert a <= 2.0 * b + 1e-6, (egold, eo)
+
+
+@pytest.mark.parametrize('name', util.SC_CASES)
+def test_shan_chen_aa_equals_ab(name):
+    ca, cb = util.load_case(name + '_AB'), util.load_case(name + '_AA')
+    a, b = gpu_run(ca, int(ca['steps'])), gpu_run(cb, int(cb['steps']))
+    e = errs(a, b, ca)
+    assert e[2] <= 2e-6 and e[3] <= 2e-6, e

@@ -8,7 +8,7 @@ import os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sailfish_b200.controller import LBSimulationController
 from sailfish_b200.geo import EqualSubdomainsGeometry3D
-from sailfish_b200.examples import ldc_2d, ldc_3d, poiseuille_3d
+from sailfish_b200.examples import ldc_2d, ldc_3d, poiseuille_3d, sc_separation_3d
 
 CONFIGS = [
     ('C1 ldc_2d D2Q9 BGK 256^2', ldc_2d.LDCSim, None,
@@ -29,6 +29,8 @@ CONFIGS = [
     ('C3f poiseuille_3d D3Q19 BGK 128x128x512 force+PBC', poiseuille_3d.PoiseuilleSim, EqualSubdomainsGeometry3D,
      ['--lat_nx=128', '--lat_ny=128', '--lat_nz=512', '--flow_direction=z', '--drive=force',
       '--visc=0.1', '--access_pattern=AA'], 1000, 152),
+    ('C5 sc_separation_3d binary Shan-Chen D3Q19 256^3 (1 GPU)', sc_separation_3d.SeparationSCSim, EqualSubdomainsGeometry3D,
+     ['--lat_nx=256', '--lat_ny=256', '--lat_nz=256', '--access_pattern=AA', '--seed=1234'], 100, 516),
 ]
 
 
@@ -46,7 +48,12 @@ def main():
         nodes = r.num_fluid_nodes
         out = {'config': name, 'fluid_nodes': nodes, 'steps': steps}
         for mode in ('c_graph', 'python'):
-            fn = dev.run if mode == 'c_graph' else dev.run_python_loop
+            if not hasattr(dev, 'run_python_loop'):
+                if mode == 'c_graph':
+                    continue
+                fn = lambda n, save_last=False: dev.run(n)
+            else:
+                fn = dev.run if mode == 'c_graph' else dev.run_python_loop
             fn(20, save_last=False)
             ctrl.sync()
             e0 = r.backend.make_event(dev.stream, timing=True)
