@@ -154,10 +154,19 @@ class LBSimulationController(object):
         if getattr(self, '_dist', None) is not None:
             self._dist.barrier()
 
-    def run_steps(self, n):
-        for _ in range(n):
+    def step_all(self, sync_req=False):
+        """One time step on every local subdomain, phase by phase (a phase may end with an exchange
+        the next phase of the *neighbours* depends on)."""
+        for ph in self.runners[0].phases():
             for r in self.runners:
-                r.step(False)
+                getattr(r, ph)(sync_req)
+
+    def run_steps(self, n):
+        if len(self.runners) == 1:
+            self.runners[0].run_steps(n)
+        else:
+            for _ in range(n):
+                self.step_all(False)
 
     def sync(self):
         for r in self.runners:
@@ -171,7 +180,12 @@ class LBSimulationController(object):
         t0 = time.time()
         done = False
         while not done:
-            flags = [r.main_step() for r in self.runners]
+            for r in self.runners:
+                r.begin_main_step()
+            for ph in self.runners[0].phases():
+                for r in self.runners:
+                    getattr(r, ph)(r._fields_req)
+            flags = [r.end_main_step() for r in self.runners]
             done = all(flags)
         self.sync()
         self.barrier()

@@ -242,6 +242,9 @@ class SubdomainRunner(object):
                 self._lib.call('slf_sem_wait', link.my_ready(channel), link.my_consumed(channel), stream.handle)
 
     # -- stepping ---------------------------------------------------------------------------------
+    def phases(self):
+        return ['step']
+
     def step(self, sync_req):
         """One time step: boundary slabs -> push planes to the neighbours (data stream) while the
         interior is computed (calc stream) -> local PBC.  Cf. subdomain_runner.py:960-1058."""
@@ -326,9 +329,16 @@ class SubdomainRunner(object):
         """One pass of the main loop body (subdomain_runner.py:1673-1748); returns True to quit.
         As in the reference, output written at iteration N holds the macroscopic fields the
         N-th step computed from its pre-collision populations."""
-        output_req = self._sim.need_output()
-        sync_req, fields_req = self._sim.need_sync_fields()
-        self.step(fields_req)
+        self.begin_main_step()
+        self.step(self._fields_req)
+        return self.end_main_step()
+
+    def begin_main_step(self):
+        self._output_req = self._sim.need_output()
+        self._sync_req, self._fields_req = self._sim.need_sync_fields()
+
+    def end_main_step(self):
+        output_req, sync_req = self._output_req, self._sync_req
         if sync_req:
             self._fields_to_host()
         quit_ = self.need_quit()
@@ -415,7 +425,16 @@ class NNSubdomainRunner(SubdomainRunner):
             out['dist%db' % g] = int(d.d_dist[g][1]) if d.d_dist[g][1] else 0
         return out
 
+    def phases(self):
+        """A step has a mid-step exchange (macro fields), so a process that drives several
+        subdomains must finish phase 1 on all of them before phase 2 (controller.step_all)."""
+        return ['step_macro', 'step_collide']
+
     def step(self, sync_req):
+        self.step_macro(sync_req)
+        self.step_collide(sync_req)
+
+    def step_macro(self, sync_req):
         dev = self._dev
         it = dev.iteration
         cs = self._calc_stream
@@ -432,6 +451,13 @@ class NNSubdomainRunner(SubdomainRunner):
                 if link.peer_runner is None:
                     self._lib.call('slf_sem_signal', link.peer_ready(1), cs.handle)
             self._push_events[1][it & 1].record(cs)
+
+    def step_collide(self, sync_req):
+        dev = self._dev
+        it = dev.iteration
+        cs = self._calc_stream
+        links = self._links
+        if links:
             self._wait_incoming(1, it, cs)
         dev.collide(stream=cs)
         dev.dist_pbc(stream=cs)

@@ -45,8 +45,7 @@ def run(cls, args, steps, single=False):
                 r._dev.be.to_buf(b)
             r._dev.set_initial_conditions()
     for k in range(steps):
-        for r in ctrl.runners:
-            r.step(k == steps - 1)
+        ctrl.step_all(k == steps - 1)
     ctrl.sync()
     out = []
     for r in ctrl.runners:

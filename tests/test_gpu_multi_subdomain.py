@@ -31,8 +31,7 @@ def gpu_run(cls, geo, args, steps):
     ctrl = LBSimulationController(cls, geo)
     ctrl.setup(args + ['--quiet'])
     for k in range(steps):
-        for r in ctrl.runners:
-            r.step(k == steps - 1)
+        ctrl.step_all(k == steps - 1)
     ctrl.sync()
     dim = ctrl.dim
     pieces = []

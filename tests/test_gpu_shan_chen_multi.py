@@ -26,8 +26,7 @@ def run(args, steps):
             dev.be.to_buf(b)
         dev.set_initial_conditions()
     for k in range(steps):
-        for r in ctrl.runners:
-            r.step(False)
+        ctrl.step_all(False)
     ctrl.sync()
     pieces = []
     for r in ctrl.runners:
