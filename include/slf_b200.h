@@ -147,6 +147,11 @@ int  slf_event_elapsed_ms(uint64_t start, uint64_t end, float *ms);
  *      backend_cuda.py:193-218): no source is generated, the context becomes data ---- */
 int  slf_plan_create(const SlfParams *params, SlfPlan **plan);
 int  slf_plan_destroy(SlfPlan *plan);
+/* Declares which faces of the split (outermost) axis have a neighbouring subdomain
+ * (SubdomainSpec.has_face_conn, subdomain.py:242-304).  The PBC kernels of the other axes then leave
+ * alone what the neighbour delivers through slf_halo_push*: the ghost layer of that face and the
+ * crossing populations of the adjacent real layer. */
+int  slf_plan_set_links(SlfPlan *plan, int link_low, int link_high);
 /* Binds a node map (device pointer to the uint32 array the kernels receive as `map`) to the
  * plan and derives, once, what the reference re-reads every step: 1-bit masks of the plain
  * fluid and full-bounce-back nodes for the bulk kernel and the sorted list of the remaining

@@ -51,6 +51,7 @@ _PROTOTYPES = {
     'slf_event_elapsed_ms': [_u64, _u64, ctypes.POINTER(ctypes.c_float)],
     'slf_plan_create': [ctypes.POINTER(P.SlfParams), ctypes.POINTER(_vp)],
     'slf_plan_destroy': [_vp],
+    'slf_plan_set_links': [_vp, _i, _i],
     'slf_plan_bind_map': [_vp, _u64],
     'slf_set_initial_conditions': [_vp, _u64, _u64, _u64, _u64, _u64, _u64, _u64],
     'slf_collide_and_propagate': [_vp, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _i, _u32, _i, _i, _u64],

@@ -111,6 +111,10 @@ class LBSimulationController(object):
             r.initialize()
             self.runners.append(r)
         self._link(dist_mode, rank, ws)
+        # nobody may push into a neighbour's buffers before that neighbour has finished uploading and
+        # initialising them
+        self.sync()
+        self.barrier()
         return self
 
     def _link(self, dist_mode, rank, ws):
@@ -151,7 +155,9 @@ class LBSimulationController(object):
 
     # -- running -------------------------------------------------------------------------------
     def barrier(self):
+        """Host-side rendezvous of all ranks (local streams drained first)."""
         if getattr(self, '_dist', None) is not None:
+            self.sync()
             self._dist.barrier()
 
     def step_all(self, sync_req=False):

@@ -193,6 +193,12 @@ int slf_plan_create(const SlfParams *p, SlfPlan **out) {
   return 0;
 }
 
+int slf_plan_set_links(SlfPlan *plan, int link_low, int link_high) {
+  if (!plan) return fail(SLF_EINVAL, "null plan");
+  plan->link_lo = link_low != 0; plan->link_hi = link_high != 0;
+  return 0;
+}
+
 int slf_plan_destroy(SlfPlan *plan) {
   if (!plan) return 0;
   for (size_t k = 0; k < g_graphs.size();) {
@@ -352,9 +358,9 @@ int slf_apply_periodic_boundary_conditions(SlfPlan *pl, uint64_t dist, int axis,
   cudaStream_t s = (cudaStream_t)stream;
   const int *per = pl->hp.periodic;
   if (with_swap) {
-    SLF_LATTICE_SWITCH(pl, (apply_pbc<L, true><<<grid, 128, 0, s>>>(d, (float *)dist, axis, per[0], per[1], per[2])));
+    SLF_LATTICE_SWITCH(pl, (apply_pbc<L, true><<<grid, 128, 0, s>>>(d, (float *)dist, axis, per[0], per[1], per[2], pl->link_lo, pl->link_hi)));
   } else {
-    SLF_LATTICE_SWITCH(pl, (apply_pbc<L, false><<<grid, 128, 0, s>>>(d, (float *)dist, axis, per[0], per[1], per[2])));
+    SLF_LATTICE_SWITCH(pl, (apply_pbc<L, false><<<grid, 128, 0, s>>>(d, (float *)dist, axis, per[0], per[1], per[2], pl->link_lo, pl->link_hi)));
   }
   LAUNCH_OK("apply_pbc");
   return 0;
@@ -528,7 +534,7 @@ int slf_apply_macro_periodic_boundary_conditions(SlfPlan *pl, uint64_t field, in
   const int n1 = axis == 0 ? d.ny : d.nx;
   const int n2 = pl->D == 3 ? (axis == 2 ? d.ny : d.nz) : 1;
   dim3 grid((n1 + 127) / 128, n2);
-  macro_pbc<<<grid, 128, 0, (cudaStream_t)stream>>>(d, (float *)field, axis, pl->D);
+  macro_pbc<<<grid, 128, 0, (cudaStream_t)stream>>>(d, (float *)field, axis, pl->D, pl->link_lo, pl->link_hi);
   LAUNCH_OK("macro_pbc");
   return 0;
 }

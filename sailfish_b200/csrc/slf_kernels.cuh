@@ -444,7 +444,7 @@ __device__ __forceinline__ void set3(int a, int v, int &x, int &y, int &z) {
 
 template <class L, bool SWAP>
 __global__ void __launch_bounds__(128)
-apply_pbc(const DevParams P, float *dist, int axis, int per0, int per1, int per2) {
+apply_pbc(const DevParams P, float *dist, int axis, int per0, int per1, int per2, int link_lo, int link_hi) {
   const int lim[3] = {P.nx, P.ny, P.nz};
   const int per[3] = {per0, per1, per2};
   int oth[2];
@@ -466,6 +466,16 @@ apply_pbc(const DevParams P, float *dist, int axis, int per0, int per1, int per2
   set3(axis, SWAP ? 1 : 0, lx, ly, lz);
   set3(axis, SWAP ? lim[axis] - 1 : lim[axis] - 2, hx, hy, hz);
   const long long gi_low = gidx3<L>(P, lx, ly, lz), gi_high = gidx3<L>(P, hx, hy, hz);
+  // Subdomain split along the outermost axis: the neighbours deliver whole, PBC-completed planes
+  // into the ghost layer (after in-place steps) or into the crossing slots of the first/last real
+  // layer (after streaming steps), possibly while this kernel runs -- leave exactly those alone.
+  const int so = L::D - 1;                       // split axis
+  const int io = (oth[0] == so) ? i1 : ((L::D == 3 && oth[1] == so) ? i2 : -1);
+  const int no = so == 2 ? P.nz : P.ny;
+  // (after streaming steps the ghost layer holds this subdomain's own outgoing populations and must be
+  //  completed here before it is pushed; after in-place steps it is the neighbour's landing zone)
+  if (SWAP && io >= 0 && ((link_lo && io == 0) || (link_hi && io == no - 1))) return;
+  const int skip_e = (SWAP || io < 0) ? 0 : ((link_lo && io == 1) ? 1 : ((link_hi && io == no - 2) ? -1 : 0));
   float val[L::Q];
 #ifdef SLF_DEBUG_PBC
   if (i1 == 3 && i2 == 0) printf("pbc D=%d swap=%d axis=%d n1=%d n2=%d oth=%d,%d gi_low=%lld gi_high=%lld off=%lld DS=%lld lim=%d,%d,%d\n",
@@ -481,6 +491,7 @@ apply_pbc(const DevParams P, float *dist, int axis, int per0, int per1, int per2
   for (int i = 1; i < L::Q; i++) {
     const int ea = axis == 0 ? L::ex(i) : (axis == 1 ? L::ey(i) : L::ez(i));
     if (ea != -1) continue;
+    if (skip_e != 0 && (so == 2 ? L::ez(i) : L::ey(i)) == skip_e) continue;
     const int j = SWAP ? L::opp(i) : i;
     const float fv = val[i];
     if (!isfinite(fv)) continue;
@@ -510,6 +521,7 @@ apply_pbc(const DevParams P, float *dist, int axis, int per0, int per1, int per2
   for (int i = 1; i < L::Q; i++) {
     const int ea = axis == 0 ? L::ex(i) : (axis == 1 ? L::ey(i) : L::ez(i));
     if (ea != 1) continue;
+    if (skip_e != 0 && (so == 2 ? L::ez(i) : L::ey(i)) == skip_e) continue;
     const int j = SWAP ? L::opp(i) : i;
     const float fv = val[i];
     if (!isfinite(fv)) continue;

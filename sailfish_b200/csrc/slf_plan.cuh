@@ -33,6 +33,7 @@ struct SlfPlan {
   uint64_t bound_map = 0;
   uint32_t *d_fluid_mask = nullptr, *d_wall_mask = nullptr, *d_list = nullptr;
   std::vector<long long> layer_off;    // list offsets per outermost-axis layer (size n + 1)
+  int link_lo = 0, link_hi = 0;        // neighbours across the low / high face of the split axis
 };
 
 // one per lattice, each in its own translation unit (slf_collide_*.cu) so they build in parallel

@@ -163,13 +163,16 @@ sc_set_initial_conditions(const DevParams P, const uint32_t *__restrict__ map, f
 
 // ApplyMacroPeriodicBoundaryConditions: ghost <- opposite real layer, both sides, if finite
 __global__ void __launch_bounds__(128)
-macro_pbc(const DevParams P, float *field, int axis, int dim) {
+macro_pbc(const DevParams P, float *field, int axis, int dim, int link_lo, int link_hi) {
   const int n1 = axis == 0 ? P.ny : P.nx;
   const int n2 = dim == 3 ? (axis == 2 ? P.ny : P.nz) : 1;
   const int i1 = blockIdx.x * blockDim.x + threadIdx.x, i2 = blockIdx.y;
   if (i1 >= n1 || i2 >= n2) return;
   int x = 0, y = 0, z = 0;
   if (axis == 0) { y = i1; z = i2; } else if (axis == 1) { x = i1; z = i2; } else { x = i1; y = i2; }
+  // ghost layers across a split face are delivered by the neighbour (slf_halo_push_field)
+  const int io = dim == 3 ? z : y, no = dim == 3 ? P.nz : P.ny;
+  if (axis != dim - 1 && ((link_lo && io == 0) || (link_hi && io == no - 1))) return;
   const long long stride = axis == 0 ? 1 : (axis == 1 ? P.sy : P.sz);
   const int n = axis == 0 ? P.nx : (axis == 1 ? P.ny : P.nz);
   const long long base = (long long)x + P.sy * y + P.sz * z;   // coordinate along `axis` is 0 here

@@ -230,6 +230,7 @@ class SubdomainRunner(object):
 
     def add_link(self, link):
         self._links[link.face & 1] = link
+        self._lib.call('slf_plan_set_links', self._dev.plan, int(0 in self._links), int(1 in self._links))
 
     def _outer_n(self):
         return self._lat_size[0]

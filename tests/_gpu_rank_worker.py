@@ -44,6 +44,8 @@ def run(cls, args, steps, single=False):
             for b in (r._dev.d_rho, r._dev.d_phi):
                 r._dev.be.to_buf(b)
             r._dev.set_initial_conditions()
+    ctrl.sync()
+    ctrl.barrier()
     for k in range(steps):
         ctrl.step_all(k == steps - 1)
     ctrl.sync()
@@ -60,8 +62,12 @@ def run(cls, args, steps, single=False):
 def main():
     name, ap = sys.argv[1], sys.argv[2]
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local_rank)
-    dist.init_process_group('cpu:gloo,cuda:nccl', device_id=torch.device('cuda', local_rank))
+    # gloo only: the ranks exchange IPC handles and results, never tensors; this also lets several
+    # ranks share one GPU (cudaIpc works between processes on the same device)
+    ndev = torch.cuda.device_count()
+    os.environ['LOCAL_RANK'] = str(local_rank % ndev)
+    torch.cuda.set_device(local_rank % ndev)
+    dist.init_process_group('gloo')
     rank, ws = dist.get_rank(), dist.get_world_size()
     cls, args = CASES[name]
     args = args + ['--access_pattern=' + ap]

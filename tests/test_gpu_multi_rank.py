@@ -1,5 +1,5 @@
 """One rank per GPU (torchrun), CUDA-IPC peer pushes + device semaphores: the merged result must
-be bit-identical to the single-subdomain run.  Needs >= 2 GPUs; skipped otherwise."""
+be bit-identical to the single-subdomain run.  With a single GPU two ranks share it."""
 import os
 import subprocess
 import sys
@@ -19,9 +19,11 @@ def _ngpu():
 @pytest.mark.parametrize('name,ap', [('ldc3d', 'AA'), ('ldc3d', 'AB'), ('poi3d_force_z', 'AA'), ('poi3d_force_x', 'AA'), ('sc3d', 'AA'), ('sc3d', 'AB')])
 def test_ranks_equal_single_subdomain(name, ap):
     n = _ngpu()
-    if n < 2:
-        pytest.skip('needs at least 2 GPUs')
-    n = min(n, 4)
+    if n < 1:
+        pytest.skip('needs a GPU')
+    # one rank per GPU; on a single-GPU box the ranks share the device (CUDA IPC between processes
+    # works on one device too), which still exercises the cross-process path
+    n = min(n, 4) if n >= 2 else 2
     port = 29600 + (os.getpid() % 300)
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=%d' % n,
            '--master-addr', '127.0.0.1', '--master-port', str(port),
