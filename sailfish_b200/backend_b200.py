@@ -17,7 +17,8 @@ import numpy as np
 from sailfish_b200 import params as P
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libslf_b200.so')
+# SLF_B200_LIB selects another build of the same library (kernel-tuning experiments)
+LIB_PATH = os.environ.get('SLF_B200_LIB') or os.path.join(_HERE, 'libslf_b200.so')
 
 _u64 = ctypes.c_uint64
 _i = ctypes.c_int
@@ -214,6 +215,30 @@ class Kernel(object):
                 return
             l.call('slf_collide_and_propagate', plan, int(m), int(din), int(dout), int(rho), int(vx),
                    int(vy), int(vz), options, self.iteration, z0, z1, s)
+        elif n == 'SetInitialConditions' and b._params.simtype == P.SIMTYPE_IDS['shan-chen']:
+            # map, dist1, dist2, ivx, ivy[, ivz], irho, iphi  (lb_binary.py:107-128)
+            m, d1, d2 = a[:3]
+            vx, vy = a[3:5]
+            vz, rho, phi = (a[5], a[6], a[7]) if dim == 3 else (0, a[5], a[6])
+            l.call('slf_sc_set_initial_conditions', plan, int(m), int(d1), int(d2), int(vx), int(vy), int(vz),
+                   int(rho), int(phi), s)
+        elif n in ('ShanChenPrepareMacroFields', 'ShanChenCollideAndPropagate0', 'ShanChenCollideAndPropagate1'):
+            # map, dist1|dist_in, dist2|dist_out, rho, phi, vx, vy[, vz], options  (lb_binary.py:423-517)
+            m, da, db, rho, phi, vx, vy = a[:7]
+            vz, options = (a[7], a[8]) if dim == 3 else (0, a[7])
+            options = int(options)
+            z0, z1 = b._region_for(options)
+            if z0 == z1:
+                return
+            if n == 'ShanChenPrepareMacroFields':
+                l.call('slf_sc_prepare_macro_fields', plan, int(m), int(da), int(db), int(rho), int(phi),
+                       int(vx), int(vy), int(vz), options, self.iteration, z0, z1, s)
+            else:
+                l.call('slf_sc_collide_and_propagate', plan, int(n[-1]), int(m), int(da), int(db), int(rho),
+                       int(phi), int(vx), int(vy), int(vz), options, self.iteration, z0, z1, s)
+        elif n == 'ApplyMacroPeriodicBoundaryConditions':
+            field, axis = a[:2]
+            l.call('slf_apply_macro_periodic_boundary_conditions', plan, int(field), int(axis), s)
         elif n == 'SetInitialConditions':
             # dist, ivx, ivy[, ivz], irho, map  (lb_single.py:72-94)
             if dim == 3:

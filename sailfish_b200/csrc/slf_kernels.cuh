@@ -109,8 +109,19 @@ collide_bulk(const DevParams P, const uint32_t *__restrict__ map, const uint32_t
 // Launch shape (measured on B200, profiles/r01_exp_bulk_variants.txt): 128-thread blocks,
 // register budget for 10 resident blocks per SM (48 registers), default cache policy:
 // 6.0 TB/s of algorithmic traffic on D3Q19 BGK 512^3 = 91 % of the measured copy bandwidth.
+#ifndef SLF_MINB_D3Q19_MRT
+#define SLF_MINB_D3Q19_MRT 10
+#endif
+#ifndef SLF_MINB_D3Q27
+#define SLF_MINB_D3Q27 8
+#endif
 template <class L, int MODEL> struct BulkTuning { static constexpr int MINB = 1; };
-template <> struct BulkTuning<D3Q19, SLF_BGK> { static constexpr int MINB = 10; };
+#ifndef SLF_MINB_D3Q19_BGK
+#define SLF_MINB_D3Q19_BGK 10
+#endif
+template <> struct BulkTuning<D3Q19, SLF_BGK> { static constexpr int MINB = SLF_MINB_D3Q19_BGK; };
+template <> struct BulkTuning<D3Q19, SLF_MRT> { static constexpr int MINB = SLF_MINB_D3Q19_MRT; };
+template <> struct BulkTuning<D3Q27, SLF_BGK> { static constexpr int MINB = SLF_MINB_D3Q27; };
 template <> struct BulkTuning<D2Q9, SLF_BGK> { static constexpr int MINB = 10; };
 template <> struct BulkTuning<D2Q9, SLF_MRT> { static constexpr int MINB = 10; };
 

@@ -136,6 +136,43 @@ class FakeLib(object):
         orc.apply_pbc(p, self._arr(dist, np.float32, p.dist_size * p.Q), int(axis), bool(swap))
         self.launches += 1
 
+    # -- binary Shan-Chen ------------------------------------------------------------------------
+    def _v(self, p, vx, vy, vz):
+        f, n = np.float32, p.dist_size
+        return [self._arr(vx, f, n), self._arr(vy, f, n)] + ([self._arr(vz, f, n)] if p.dim == 3 else [])
+
+    def _slf_sc_set_initial_conditions(self, plan, m, d1, d2, vx, vy, vz, rho, phi, stream):
+        p = self._p(plan)
+        f, n = np.float32, p.dist_size
+        orc.sc_set_initial_conditions(p, self._arr(m, np.uint32, n), self._arr(d1, f, n * p.Q),
+                                      self._arr(d2, f, n * p.Q), self._v(p, vx, vy, vz),
+                                      self._arr(rho, f, n), self._arr(phi, f, n))
+        self.launches += 1
+
+    def _slf_sc_prepare_macro_fields(self, plan, m, d1, d2, rho, phi, vx, vy, vz, options, iteration, z0, z1, stream):
+        p = self._p(plan)
+        f, n = np.float32, p.dist_size
+        orc.sc_prepare_macro_fields(p, self._arr(m, np.uint32, n), self._arr(d1, f, n * p.Q),
+                                    self._arr(d2, f, n * p.Q), self._arr(rho, f, n), self._arr(phi, f, n),
+                                    self._v(p, vx, vy, vz), int(options), int(iteration), int(z0), int(z1))
+        self.launches += 1
+
+    def _slf_sc_collide_and_propagate(self, plan, grid_idx, m, din, dout, rho, phi, vx, vy, vz, options,
+                                      iteration, z0, z1, stream):
+        p = self._p(plan)
+        f, n = np.float32, p.dist_size
+        orc.sc_collide_and_propagate(p, int(grid_idx), self._arr(m, np.uint32, n), self._arr(din, f, n * p.Q),
+                                     self._arr(dout, f, n * p.Q), self._arr(rho, f, n), self._arr(phi, f, n),
+                                     self._v(p, vx, vy, vz), int(options), int(iteration), int(z0), int(z1))
+        self.launches += 1
+
+    def _slf_apply_macro_periodic_boundary_conditions(self, plan, field, axis, stream):
+        p = self._p(plan)
+        if axis >= p.dim:
+            return
+        orc.apply_macro_pbc(p, self._arr(field, np.float32, p.dist_size), int(axis))
+        self.launches += 1
+
 
 def install_fake(monkeypatch=None):
     from sailfish_b200 import backend_b200 as bk

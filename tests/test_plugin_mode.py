@@ -78,3 +78,35 @@ def test_reference_runs_on_b200_backend(reference, oracle, monkeypatch, tmp_path
         assert np.abs(res['v'][d][wet] - v[wet]).max() / vscale < 5e-5
     if c['periodic'].any():
         assert 'slf_apply_periodic_boundary_conditions' in fake.calls
+
+
+@pytest.mark.parametrize('ap', ['AB', 'AA'])
+def test_reference_shan_chen_runs_on_b200_backend(reference, oracle, monkeypatch, tmp_path, ap):
+    """BASELINE config 5: the reference's examples/binary_fluid/sc_separation_3d.py, unmodified, through
+    ShanChenPrepareMacroFields / ShanChenCollideAndPropagate{0,1} / ApplyMacroPeriodicBoundaryConditions
+    (lb_binary.py:41-128,423-517) on the b200 backend; output vs the golden vector of the same run."""
+    import fake_device
+    fake = fake_device.install_fake(monkeypatch)
+    script = 'examples/binary_fluid/sc_separation_3d.py'
+    mod = reference.load_example(script)
+    from sailfish.controller import LBSimulationController
+    from sailfish.geo import LBGeometry3D
+    steps = 12
+    out = str(tmp_path / 'out')
+    argv = [script, '--lat_nx=12', '--lat_ny=10', '--lat_nz=9', '--seed=1234', '--access_pattern=' + ap,
+            '--backends=b200', '--debug_single_process', '--max_iters=%d' % steps, '--every=%d' % steps,
+            '--output=' + out, '--quiet']
+    monkeypatch.setattr(sys, 'argv', argv)
+    LBSimulationController(mod.SeparationSCSim, LBGeometry3D).run()
+    for name in ('slf_sc_set_initial_conditions', 'slf_sc_prepare_macro_fields', 'slf_sc_collide_and_propagate',
+                 'slf_apply_macro_periodic_boundary_conditions', 'slf_apply_periodic_boundary_conditions'):
+        assert name in fake.calls, name
+    files = sorted(glob.glob(out + '.0.*%d.npz' % steps))
+    assert files, glob.glob(out + '*')
+    res = np.load(files[-1])
+    c = np.load(os.path.join(util.ROOT, 'tests', 'golden', 'steps_sc3d_%s.npz' % ap))
+    inner = (slice(1, -1),) * 3
+    for k in ('rho', 'phi'):
+        want = c[k][inner][..., :12]
+        assert res[k].shape == want.shape
+        assert np.abs(res[k] - want).max() / np.abs(want).max() < 5e-6, k

@@ -40,7 +40,10 @@ def main():
         peak = json.load(open('MEASURED_PEAKS.json'))['hbm_gbs']
     except Exception:
         pass
+    only = [a for a in sys.argv[1:] if not a.startswith('-')]
     for name, cls, geo, args, steps, bpl in CONFIGS:
+        if only and name.split()[0] not in only:
+            continue
         ctrl = LBSimulationController(cls, geo)
         ctrl.setup(args + ['--quiet'])
         r = ctrl.runners[0]
