@@ -75,6 +75,7 @@ enum {
 /* CollideAndPropagate `options` bits, templates/kernel_common.mako:507-508 */
 #define SLF_OPTION_SAVE_MACRO_FIELDS 1
 #define SLF_OPTION_BULK              2
+#define SLF_OPTION_DENSITIES_ONLY    4   /* library extension: slf_sc_prepare_macro_fields skips the velocity */
 
 /* Faces, sailfish/subdomain.py SubdomainSpec.{X_LOW..Z_HIGH} */
 enum { SLF_X_LOW = 0, SLF_X_HIGH = 1, SLF_Y_LOW = 2, SLF_Y_HIGH = 3, SLF_Z_LOW = 4, SLF_Z_HIGH = 5 };
@@ -207,6 +208,15 @@ int  slf_sc_collide_and_propagate(SlfPlan *plan, int grid_idx, uint64_t map, uin
                                   uint64_t dist_out, uint64_t rho, uint64_t phi, uint64_t vx, uint64_t vy,
                                   uint64_t vz, int options, uint32_t iteration, int z_begin, int z_end,
                                   uint64_t stream);
+/* Both components in one launch (native runner; the reference issues ShanChenCollideAndPropagate0 and 1
+ * back to back, lb_binary.py:494-515, "These kernels can actually run in parallel").  The common
+ * velocity is recomputed from the populations, so the preceding slf_sc_prepare_macro_fields may run
+ * with SLF_OPTION_DENSITIES_ONLY; with SLF_OPTION_SAVE_MACRO_FIELDS the velocity the macro pass
+ * would have stored is written to vx, vy, vz. */
+int  slf_sc_collide_and_propagate_fused(SlfPlan *plan, uint64_t map, uint64_t dist1_in, uint64_t dist1_out,
+                                        uint64_t dist2_in, uint64_t dist2_out, uint64_t rho, uint64_t phi,
+                                        uint64_t vx, uint64_t vy, uint64_t vz, int options, uint32_t iteration,
+                                        int z_begin, int z_end, uint64_t stream);
 /* ApplyMacroPeriodicBoundaryConditions(field, axis)  kernel_utils.mako:410-474 */
 int  slf_apply_macro_periodic_boundary_conditions(SlfPlan *plan, uint64_t field, int axis, uint64_t stream);
 /* Ghost-layer exchange of a scalar field across the split axis (replaces

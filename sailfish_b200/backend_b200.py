@@ -61,6 +61,7 @@ _PROTOTYPES = {
     'slf_sc_set_initial_conditions': [_vp, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64],
     'slf_sc_prepare_macro_fields': [_vp, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _i, _u32, _i, _i, _u64],
     'slf_sc_collide_and_propagate': [_vp, _i, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _i, _u32, _i, _i, _u64],
+    'slf_sc_collide_and_propagate_fused': [_vp, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _i, _u32, _i, _i, _u64],
     'slf_apply_macro_periodic_boundary_conditions': [_vp, _u64, _i, _u64],
     'slf_halo_push_field': [_vp, _u64, _i, _u64, _i, _u64],
     'slf_apply_periodic_boundary_conditions': [_vp, _u64, _i, _i, _u64],

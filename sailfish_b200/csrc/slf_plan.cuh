@@ -45,3 +45,11 @@ int slf_collide_d3q19_mrt(SlfPlan *pl, int mode, bool save, const uint32_t *map,
                           float *rho, float *vx, float *vy, float *vz, int z0, int z1, cudaStream_t s);
 int slf_collide_d3q27(SlfPlan *pl, int mode, bool save, const uint32_t *map, const float *din, float *dout,
                       float *rho, float *vx, float *vy, float *vz, int z0, int z1, cudaStream_t s);
+
+#define SLF_LATTICE_SWITCH(pl, CALL)            \
+  switch ((pl)->hp.lattice) {                    \
+    case SLF_D2Q9: { using L = D2Q9; CALL; } break;   \
+    case SLF_D3Q19: { using L = D3Q19; CALL; } break; \
+    case SLF_D3Q27: { using L = D3Q27; CALL; } break; \
+  }
+

@@ -31,8 +31,71 @@ __device__ __forceinline__ bool sc_is_wet(const DevParams &P, uint32_t type) {
   return type == P.tid[SLF_NT_FLUID];
 }
 
-// ShanChenPrepareMacroFields
+// sum_i w_i e_i psi(field(x + e_i))   (shan_chen.mako:45-84)
+template <class L>
+__device__ __forceinline__ void sc_psi_gradient(const DevParams &P, int pot, const float *__restrict__ field,
+                                                long long gi, float (&grad)[3]) {
+  float fx = 0.f, fy = 0.f, fz = 0.f;
+#pragma unroll
+  for (int i = 1; i < L::Q; i++) {
+    const float psi = sc_ppot(pot, field[gi + noff<L>(P, i)]);
+    if (L::ex(i)) fx = fmaf(psi, (float)L::ex(i) * L::w(i), fx);
+    if (L::ey(i)) fy = fmaf(psi, (float)L::ey(i) * L::w(i), fy);
+    if (L::D == 3 && L::ez(i)) fz = fmaf(psi, (float)L::ez(i) * L::w(i), fz);
+  }
+  grad[0] = fx; grad[1] = fy; grad[2] = fz;
+}
+
+// F += -G psi(own density) grad
+__device__ __forceinline__ void sc_add_force(int pot, float gm, float G, const float (&grad)[3], float (&a)[3]) {
+  const float c = -sc_ppot(pot, gm) * G;
+  a[0] = fmaf(grad[0], c, a[0]); a[1] = fmaf(grad[1], c, a[1]); a[2] = fmaf(grad[2], c, a[2]);
+}
+
+// BGK relaxation of one component towards the equilibrium at the force-shifted common velocity,
+// with the Guo source term (relaxation.mako:99-181, relaxation_common.mako:56-149)
+template <class L>
+__device__ __forceinline__ void sc_relax(float (&f)[L::Q], float gm, const float (&a)[3], const float (&v)[3], float omega,
+                                         float tau) {
+  const float v0[3] = {fmaf(0.5f, a[0], v[0]), fmaf(0.5f, a[1], v[1]), L::D == 3 ? fmaf(0.5f, a[2], v[2]) : 0.f};
+  const float vv = v0[0] * v0[0] + v0[1] * v0[1] + (L::D == 3 ? v0[2] * v0[2] : 0.f);
+  const float base = fmaf(-1.5f, vv, 1.0f);
+  const float pref = gm * 3.0f * (1.0f - 1.0f / (2.0f * tau));
+  const float av = a[0] * v0[0] + a[1] * v0[1] + (L::D == 3 ? a[2] * v0[2] : 0.f);
+#pragma unroll
+  for (int i = 0; i < L::Q; i++) {
+    const float ev = edotv<L>(i, v0);
+    const float feq = L::w(i) * gm * fmaf(ev, fmaf(4.5f, ev, 3.0f), base);
+    const float ea = edotv<L>(i, a);
+    f[i] = fmaf(omega, feq - f[i], f[i]) + pref * L::w(i) * (ea - av + 3.0f * ev * ea);
+  }
+}
+
 template <class L, int MODE>
+__device__ __forceinline__ void sc_store(const DevParams &P, float *dout, long long gi, const float (&f)[L::Q]) {
+  if (!P.prop) {
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) dout[gi + P.DS * i] = f[i];
+  } else if (MODE == MODE_AA_EVEN) {
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) dout[gi + P.DS * L::opp(i)] = f[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) dout[gi + noff<L>(P, i) + P.DS * i] = f[i];
+  }
+}
+
+template <class L>
+__device__ __forceinline__ void sc_wall(const DevParams &P, float *dout, long long gi, const float (&f)[L::Q]) {
+#pragma unroll
+  for (int i = 0; i < L::Q; i++) {
+    if (!P.prop) dout[gi + P.DS * i] = f[L::opp(i)];
+    else dout[gi + noff<L>(P, i) + P.DS * i] = f[L::opp(i)];   // AB; walls next to the array edge are rejected at bind time
+  }
+}
+
+// ShanChenPrepareMacroFields
+template <class L, int MODE, bool WITH_V>
 __global__ void __launch_bounds__(128)
 sc_prepare_macro(const DevParams P, const ScParams S, const uint32_t *__restrict__ map, const float *d1,
                  const float *d2, float *__restrict__ orho, float *__restrict__ ophi,
@@ -46,8 +109,9 @@ sc_prepare_macro(const DevParams P, const ScParams S, const uint32_t *__restrict
   moments<L>(f, rho0, j0);
   load_node<L, MODE>(P, d2, gi, f);
   moments<L>(f, rho1, j1);
-  const float total = S.tau0_inv * rho0 + S.tau1_inv * rho1;
   orho[gi] = rho0; ophi[gi] = rho1;
+  if (!WITH_V) return;     // the fused collide kernel recomputes the common velocity from the populations
+  const float total = S.tau0_inv * rho0 + S.tau1_inv * rho1;
   ovx[gi] = (S.tau0_inv * j0[0] + S.tau1_inv * j1[0]) / total;
   ovy[gi] = (S.tau0_inv * j0[1] + S.tau1_inv * j1[1]) / total;
   if (L::D == 3) ovz[gi] = (S.tau0_inv * j0[2] + S.tau1_inv * j1[2]) / total;
@@ -70,61 +134,82 @@ sc_collide(const DevParams P, const ScParams S, const uint32_t *__restrict__ map
 
   float f[L::Q];
   load_node<L, MODE>(P, din, gi, f);
-  if (wall) {
-#pragma unroll
-    for (int i = 0; i < L::Q; i++) {
-      if (!P.prop) dout[gi + P.DS * i] = f[L::opp(i)];
-      else dout[gi + noff<L>(P, i) + P.DS * i] = f[L::opp(i)];   // AB; walls next to the array edge are rejected at bind time
-    }
-    return;
-  }
+  if (wall) { sc_wall<L>(P, dout, gi, f); return; }
   const float *own = GRID == 0 ? rho_f : phi_f;
   const float gm = own[gi];
-  // Shan-Chen force: F = -G psi(x) sum_i w_i e_i psi'(x + e_i), then acceleration a = F / density
   float a[3] = {0.f, 0.f, 0.f};
 #pragma unroll
   for (int k = 0; k < 2; k++) {
     const float G = S.g[2 * GRID + k];
     if (G == 0.0f) continue;
-    const float *field = k == 0 ? rho_f : phi_f;
-    float fx = 0.f, fy = 0.f, fz = 0.f;
-#pragma unroll
-    for (int i = 1; i < L::Q; i++) {
-      const float psi = sc_ppot(S.potential, field[gi + noff<L>(P, i)]);
-      if (L::ex(i)) fx = fmaf(psi, (float)L::ex(i) * L::w(i), fx);
-      if (L::ey(i)) fy = fmaf(psi, (float)L::ey(i) * L::w(i), fy);
-      if (L::D == 3 && L::ez(i)) fz = fmaf(psi, (float)L::ez(i) * L::w(i), fz);
-    }
-    const float c = -sc_ppot(S.potential, gm) * G;
-    a[0] = fmaf(fx, c, a[0]); a[1] = fmaf(fy, c, a[1]); a[2] = fmaf(fz, c, a[2]);
+    float grad[3];
+    sc_psi_gradient<L>(P, S.potential, k == 0 ? rho_f : phi_f, gi, grad);
+    sc_add_force(S.potential, gm, G, grad, a);
   }
   const float ig = 1.0f / gm;
   a[0] *= ig; a[1] *= ig; a[2] *= ig;
+  const float v[3] = {ovx[gi], ovy[gi], L::D == 3 ? ovz[gi] : 0.f};
+  if (P.relax) sc_relax<L>(f, gm, a, v, S.omega[GRID], S.tau[GRID]);
+  sc_store<L, MODE>(P, dout, gi, f);
+}
 
-  float v0[3] = {fmaf(0.5f, a[0], ovx[gi]), fmaf(0.5f, a[1], ovy[gi]), L::D == 3 ? fmaf(0.5f, a[2], ovz[gi]) : 0.f};
-  if (P.relax) {
-    const float vv = v0[0] * v0[0] + v0[1] * v0[1] + (L::D == 3 ? v0[2] * v0[2] : 0.f);
-    const float base = fmaf(-1.5f, vv, 1.0f);
-    const float omega = S.omega[GRID];
-    const float pref = gm * 3.0f * (1.0f - 1.0f / (2.0f * S.tau[GRID]));
-    const float av = a[0] * v0[0] + a[1] * v0[1] + (L::D == 3 ? a[2] * v0[2] : 0.f);
-#pragma unroll
-    for (int i = 0; i < L::Q; i++) {
-      const float ev = edotv<L>(i, v0);
-      const float feq = L::w(i) * gm * fmaf(ev, fmaf(4.5f, ev, 3.0f), base);
-      const float ea = edotv<L>(i, a);
-      f[i] = fmaf(omega, feq - f[i], f[i]) + pref * L::w(i) * (ea - av + 3.0f * ev * ea);
-    }
+// Both components in one pass (native runner): the common velocity is recomputed from the two sets of
+// populations the thread holds anyway, each psi-gradient is evaluated once instead of twice, and the
+// v fields are neither written by the macro pass nor read here: 2 Q x 4 B in, 2 Q x 4 B out, + rho, phi
+// = 312 B/LUP (D3Q19) against 2 x 172 for the two separate launches.  Same arithmetic, same order.
+#ifndef SLF_MINB_SC_FUSED
+#define SLF_MINB_SC_FUSED 6
+#endif
+template <class L, int MODE, bool SAVE>
+__global__ void __launch_bounds__(128, SLF_MINB_SC_FUSED)
+sc_collide_fused(const DevParams P, const ScParams S, const uint32_t *__restrict__ map, const float *d1in,
+                 float *d1out, const float *d2in, float *d2out, const float *__restrict__ rho_f,
+                 const float *__restrict__ phi_f, float *__restrict__ ovx, float *__restrict__ ovy,
+                 float *__restrict__ ovz, long long gi0, long long gi1) {
+  const long long gi = gi0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= gi1) return;
+  const uint32_t type = map[gi] & P.tmask;
+  const bool fluid = type == P.tid[SLF_NT_FLUID];
+  const bool wall = type == P.tid[SLF_NT_FULLBB_WALL];
+  if (!fluid && !wall) return;
+  if (wall && MODE != MODE_AB && P.prop) return;
+
+  float f0[L::Q], f1[L::Q];
+  load_node<L, MODE>(P, d1in, gi, f0);
+  load_node<L, MODE>(P, d2in, gi, f1);
+  if (wall) { sc_wall<L>(P, d1out, gi, f0); sc_wall<L>(P, d2out, gi, f1); return; }
+  const float g0 = rho_f[gi], g1 = phi_f[gi];
+  float grad0[3] = {0.f, 0.f, 0.f}, grad1[3] = {0.f, 0.f, 0.f};
+  if (S.g[0] != 0.0f || S.g[2] != 0.0f) sc_psi_gradient<L>(P, S.potential, rho_f, gi, grad0);
+  if (S.g[1] != 0.0f || S.g[3] != 0.0f) sc_psi_gradient<L>(P, S.potential, phi_f, gi, grad1);
+
+  float r0, r1, j0[3], j1[3];
+  moments<L>(f0, r0, j0);
+  moments<L>(f1, r1, j1);
+  const float total = S.tau0_inv * r0 + S.tau1_inv * r1;
+  const float v[3] = {(S.tau0_inv * j0[0] + S.tau1_inv * j1[0]) / total, (S.tau0_inv * j0[1] + S.tau1_inv * j1[1]) / total,
+                      L::D == 3 ? (S.tau0_inv * j0[2] + S.tau1_inv * j1[2]) / total : 0.f};
+  if (SAVE) {
+    ovx[gi] = v[0]; ovy[gi] = v[1];
+    if (L::D == 3) ovz[gi] = v[2];
   }
-  if (!P.prop) {
-#pragma unroll
-    for (int i = 0; i < L::Q; i++) dout[gi + P.DS * i] = f[i];
-  } else if (MODE == MODE_AA_EVEN) {
-#pragma unroll
-    for (int i = 0; i < L::Q; i++) dout[gi + P.DS * L::opp(i)] = f[i];
-  } else {
-#pragma unroll
-    for (int i = 0; i < L::Q; i++) dout[gi + noff<L>(P, i) + P.DS * i] = f[i];
+  {
+    float a[3] = {0.f, 0.f, 0.f};
+    if (S.g[0] != 0.0f) sc_add_force(S.potential, g0, S.g[0], grad0, a);
+    if (S.g[1] != 0.0f) sc_add_force(S.potential, g0, S.g[1], grad1, a);
+    const float ig = 1.0f / g0;
+    a[0] *= ig; a[1] *= ig; a[2] *= ig;
+    if (P.relax) sc_relax<L>(f0, g0, a, v, S.omega[0], S.tau[0]);
+    sc_store<L, MODE>(P, d1out, gi, f0);
+  }
+  {
+    float a[3] = {0.f, 0.f, 0.f};
+    if (S.g[2] != 0.0f) sc_add_force(S.potential, g1, S.g[2], grad0, a);
+    if (S.g[3] != 0.0f) sc_add_force(S.potential, g1, S.g[3], grad1, a);
+    const float ig = 1.0f / g1;
+    a[0] *= ig; a[1] *= ig; a[2] *= ig;
+    if (P.relax) sc_relax<L>(f1, g1, a, v, S.omega[1], S.tau[1]);
+    sc_store<L, MODE>(P, d2out, gi, f1);
   }
 }
 

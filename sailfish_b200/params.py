@@ -27,6 +27,7 @@ NT_ABSENT = 0xfffffffe
 
 OPTION_SAVE_MACRO_FIELDS = 1
 OPTION_BULK = 2
+OPTION_DENSITIES_ONLY = 4
 
 
 class SlfParams(ctypes.Structure):

@@ -144,9 +144,12 @@ class DeviceLattice(object):
 
 class DeviceShanChenLattice(object):
     """Binary Shan-Chen mixture on the device: two lattices, rho / phi / v fields and the
-    three-pass step of NNSubdomainRunner.step (sailfish/subdomain_runner.py:2102-2197):
+    step of NNSubdomainRunner.step (sailfish/subdomain_runner.py:2102-2197):
     ShanChenPrepareMacroFields -> macro PBC (+ field halo) -> ShanChenCollideAndPropagate0/1 ->
-    distribution PBC (+ plane halo)."""
+    distribution PBC (+ plane halo).  With ``fused`` (default) the two collide launches are one
+    kernel and the macro pass stores only the densities except on steps whose velocity is wanted."""
+
+    fused = True
 
     def __init__(self, params, node_map, rho, phi, v, device=0, backend=None, host_fields=None):
         self.be = backend or bk.B200Backend(None, device)
@@ -201,10 +204,11 @@ class DeviceShanChenLattice(object):
         a, b = self.d_dist[g]
         return a if (b is None or (self.iteration & 1) == 0) else b
 
-    def macro(self, z_begin=0, z_end=-1, stream=None):
+    def macro(self, z_begin=0, z_end=-1, stream=None, with_v=True):
+        options = 0 if (with_v or not self.fused) else P.OPTION_DENSITIES_ONLY
         self.lib.call('slf_sc_prepare_macro_fields', self.plan, int(self.d_map), int(self.io_dists(0)[0]),
                       int(self.io_dists(1)[0]), int(self.d_rho), int(self.d_phi), int(self.d_v[0]),
-                      int(self.d_v[1]), self._vz(), 0, self.iteration, z_begin, z_end,
+                      int(self.d_v[1]), self._vz(), options, self.iteration, z_begin, z_end,
                       (stream or self.stream).handle)
 
     def macro_pbc(self, stream=None):
@@ -215,6 +219,12 @@ class DeviceShanChenLattice(object):
                                   (stream or self.stream).handle)
 
     def collide(self, z_begin=0, z_end=-1, stream=None):
+        if self.fused:
+            (i0, o0), (i1, o1) = self.io_dists(0), self.io_dists(1)
+            self.lib.call('slf_sc_collide_and_propagate_fused', self.plan, int(self.d_map), int(i0), int(o0),
+                          int(i1), int(o1), int(self.d_rho), int(self.d_phi), int(self.d_v[0]), int(self.d_v[1]),
+                          self._vz(), 0, self.iteration, z_begin, z_end, (stream or self.stream).handle)
+            return
         for g in (0, 1):
             din, dout = self.io_dists(g)
             self.lib.call('slf_sc_collide_and_propagate', self.plan, g, int(self.d_map), int(din), int(dout),
@@ -229,16 +239,17 @@ class DeviceShanChenLattice(object):
                     self.lib.call('slf_apply_periodic_boundary_conditions', self.plan, int(self.io_dists(g)[1]),
                                   axis, swap, (stream or self.stream).handle)
 
-    def step(self):
-        self.macro()
+    def step(self, save=True):
+        """``save``: store the velocity of this step (rho and phi always are)."""
+        self.macro(with_v=save)
         self.macro_pbc()
         self.collide()
         self.dist_pbc()
         self.iteration += 1
 
-    def run(self, steps):
-        for _ in range(steps):
-            self.step()
+    def run(self, steps, save_last=True):
+        for k in range(steps):
+            self.step(save_last and k == steps - 1)
 
     def sync(self):
         self.stream.synchronize()

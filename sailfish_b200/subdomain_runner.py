@@ -442,7 +442,7 @@ class NNSubdomainRunner(SubdomainRunner):
         links = self._links
         if links and it > 0:
             self._wait_incoming(0, it - 1, cs)
-        dev.macro(stream=cs)
+        dev.macro(stream=cs, with_v=bool(sync_req))
         dev.macro_pbc(stream=cs)
         if links:
             for side, link in links.items():
@@ -481,4 +481,4 @@ class NNSubdomainRunner(SubdomainRunner):
 
     def run_steps(self, n, save_last=False):
         for k in range(n):
-            self.step(False)
+            self.step(save_last and k == n - 1)

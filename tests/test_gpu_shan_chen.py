@@ -9,10 +9,11 @@ pytestmark = pytest.mark.gpu
 ALL = [n + '_' + ap for n in util.SC_CASES for ap in ('AB', 'AA')]
 
 
-def gpu_run(c, steps):
+def gpu_run(c, steps, fused=True):
     from sailfish_b200.runtime import DeviceShanChenLattice
     p = util.params_from_case(c)
     dev = DeviceShanChenLattice(p, c['map'], c['rho0'], c['phi0'], c['v0'])
+    dev.fused = fused     # False: one launch per component, the kernel-name contract of the reference
     dev.run(steps)
     rho, phi, v = dev.fields_to_host()
     return dev.get_dist(0), dev.get_dist(1), np.array(rho), np.array(phi), [np.array(x) for x in v]
@@ -39,11 +40,12 @@ def oracle_run(oracle, c, dtype, steps):
             [x.reshape(s) for x in sim.v])
 
 
+@pytest.mark.parametrize('fused', [True, False], ids=['fused', 'per_component'])
 @pytest.mark.parametrize('case', ALL)
-def test_shan_chen_parity(oracle, case):
+def test_shan_chen_parity(oracle, case, fused):
     c = util.load_case(case)
     steps = int(c['steps'])
-    g = gpu_run(c, steps)
+    g = gpu_run(c, steps, fused)
     r64 = oracle_run(oracle, c, np.float64, steps)
     r32 = oracle_run(oracle, c, np.float32, steps)
     eg, eo = errs(g, r64, c), errs(r32, r64, c)
@@ -65,3 +67,12 @@ def test_shan_chen_aa_equals_ab(name):
     a, b = gpu_run(ca, int(ca['steps'])), gpu_run(cb, int(cb['steps']))
     e = errs(a, b, ca)
     assert e[2] <= 2e-6 and e[3] <= 2e-6, e
+
+
+@pytest.mark.parametrize('case', ALL)
+def test_fused_equals_per_component_launches(case):
+    """Same arithmetic in the same order: the fused kernel must reproduce the two separate launches."""
+    c = util.load_case(case)
+    a, b = gpu_run(c, int(c['steps']), True), gpu_run(c, int(c['steps']), False)
+    e = errs(a, b, c)
+    assert max(e[:4]) <= 2e-7, e

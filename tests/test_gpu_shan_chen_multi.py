@@ -26,7 +26,7 @@ def run(args, steps):
             dev.be.to_buf(b)
         dev.set_initial_conditions()
     for k in range(steps):
-        ctrl.step_all(False)
+        ctrl.step_all(k == steps - 1)
     ctrl.sync()
     pieces = []
     for r in ctrl.runners:
