@@ -160,6 +160,52 @@ collide_bulk_aa(const DevParams P, const uint32_t *__restrict__ fluid_mask, floa
   }
 }
 
+// Same kernel with its Q addresses taken from a table of per-slot base pointers (kernel
+// parameters, i.e. the constant bank): address = table[i] + 4 * t with t the 32-bit offset of
+// the thread in the launch.  That is one LDC.64 + one IMAD.WIDE.U32 per access instead of the
+// 64-bit index arithmetic of `dist[gi +- noff(i) + DS * slot]` (about 60 % of the dynamic
+// instructions of the BGK kernel), and it folds the even/odd difference into the table:
+//   even: table[i] = dist + DS * i + gi0;   odd: table[i] = dist + DS * opp(i) + gi0 - noff(i);
+// f_i is loaded from table[i] and stored to table[opp(i)] in both cases.
+template <class L> struct SlotTable { float *p[L::Q]; };
+
+template <class L, int MODEL, bool SAVE>
+__global__ void __launch_bounds__(128, BulkTuning<L, MODEL>::MINB)
+collide_bulk_aa_tab(const DevParams P, const SlotTable<L> T, const uint32_t *__restrict__ fluid_mask,
+                    float *__restrict__ orho, float *__restrict__ ovx, float *__restrict__ ovy,
+                    float *__restrict__ ovz, long long gi0, unsigned n) {
+  const unsigned t = blockIdx.x * 128u + threadIdx.x;
+  if (t >= n) return;
+  const long long gi = gi0 + t;
+  if (!((fluid_mask[gi >> 5] >> (gi & 31)) & 1u)) return;
+
+  float f[L::Q];
+#pragma unroll
+  for (int i = 0; i < L::Q; i++) f[i] = T.p[i][t];
+  float rho, v[3];
+  moments<L>(f, rho, v);
+  const float inv = 1.0f / rho;
+  v[0] *= inv; v[1] *= inv; v[2] *= inv;
+  if (MODEL == SLF_MRT) collide_mrt<L, false>(P, v, f);
+  else collide_bgk<L>(P, rho, v, f);
+  if (SAVE) {
+    orho[gi] = rho; ovx[gi] = v[0]; ovy[gi] = v[1];
+    if (L::D == 3) ovz[gi] = v[2];
+  }
+#pragma unroll
+  for (int i = 0; i < L::Q; i++) T.p[L::opp(i)][t] = f[i];
+}
+
+template <class L>
+static inline SlotTable<L> make_aa_table(const DevParams &P, float *dist, long long gi0, bool odd) {
+  SlotTable<L> T;
+  for (int i = 0; i < L::Q; i++) {
+    const long long off = (long long)L::ex(i) + P.sy * L::ey(i) + P.sz * L::ez(i);
+    T.p[i] = odd ? dist + P.DS * L::opp(i) + gi0 - off : dist + P.DS * i + gi0;
+  }
+  return T;
+}
+
 // ----------------------------------------------------------------------------------------
 // Boundary kernel: all active non-fluid nodes.
 // ----------------------------------------------------------------------------------------

@@ -135,16 +135,17 @@ int slf_sc_collide_and_propagate_fused(SlfPlan *pl, uint64_t map, uint64_t dist1
   const int bs = 128;
   const unsigned nb = (unsigned)((gi1 - gi0 + bs - 1) / bs);
   cudaStream_t s = (cudaStream_t)stream;
-#define SC_FUSED(MODE, SAVE)                                                                                      \
-  SLF_LATTICE_SWITCH(pl, (sc_collide_fused<L, MODE, SAVE><<<nb, bs, 0, s>>>(                                       \
-                             pl->dp, S, (const uint32_t *)map, (const float *)dist1_in, (float *)dist1_out,        \
-                             (const float *)dist2_in, (float *)dist2_out, (const float *)rho, (const float *)phi,  \
-                             (float *)vx, (float *)vy, (float *)vz, gi0, gi1)))
-  if (save) {
-    if (mode == MODE_AB) { SC_FUSED(MODE_AB, true); } else if (mode == MODE_AA_EVEN) { SC_FUSED(MODE_AA_EVEN, true); } else { SC_FUSED(MODE_AA_ODD, true); }
-  } else {
-    if (mode == MODE_AB) { SC_FUSED(MODE_AB, false); } else if (mode == MODE_AA_EVEN) { SC_FUSED(MODE_AA_EVEN, false); } else { SC_FUSED(MODE_AA_ODD, false); }
-  }
+  // walls: bounce-back copies in AB / with propagation off, nothing to do in the AA pattern
+  const int bounce_walls = (mode == MODE_AB || !pl->dp.prop) ? 1 : 0;
+#define SC_FUSED(SAVE)                                                                                            \
+  SLF_LATTICE_SWITCH(pl, (sc_collide_fused<L, SAVE><<<nb, bs, 0, s>>>(                                             \
+                             pl->dp, S,                                                                            \
+                             make_sc_tables<L>(pl->dp, mode, (const float *)dist1_in, (float *)dist1_out,          \
+                                               (const float *)dist2_in, (float *)dist2_out, (const float *)rho,    \
+                                               (const float *)phi, gi0),                                           \
+                             (const uint32_t *)map, (float *)vx, (float *)vy, (float *)vz, gi0,                    \
+                             (unsigned)(gi1 - gi0), bounce_walls)))
+  if (save) { SC_FUSED(true); } else { SC_FUSED(false); }
 #undef SC_FUSED
   LAUNCH_OK("sc_collide_fused");
   return 0;

@@ -57,6 +57,8 @@ __device__ __forceinline__ void sc_add_force(int pot, float gm, float G, const f
 template <class L>
 __device__ __forceinline__ void sc_relax(float (&f)[L::Q], float gm, const float (&a)[3], const float (&v)[3], float omega,
                                          float tau) {
+  // Opposite directions share everything that is even in e_i: the pair (i, opp(i)) is relaxed together.
+  //   f_i^eq = w gm (base + 4.5 ev^2 +- 3 ev),   Guo term = pref w (3 ev ea - av +- ea)
   const float v0[3] = {fmaf(0.5f, a[0], v[0]), fmaf(0.5f, a[1], v[1]), L::D == 3 ? fmaf(0.5f, a[2], v[2]) : 0.f};
   const float vv = v0[0] * v0[0] + v0[1] * v0[1] + (L::D == 3 ? v0[2] * v0[2] : 0.f);
   const float base = fmaf(-1.5f, vv, 1.0f);
@@ -64,10 +66,19 @@ __device__ __forceinline__ void sc_relax(float (&f)[L::Q], float gm, const float
   const float av = a[0] * v0[0] + a[1] * v0[1] + (L::D == 3 ? a[2] * v0[2] : 0.f);
 #pragma unroll
   for (int i = 0; i < L::Q; i++) {
-    const float ev = edotv<L>(i, v0);
-    const float feq = L::w(i) * gm * fmaf(ev, fmaf(4.5f, ev, 3.0f), base);
-    const float ea = edotv<L>(i, a);
-    f[i] = fmaf(omega, feq - f[i], f[i]) + pref * L::w(i) * (ea - av + 3.0f * ev * ea);
+    const int o = L::opp(i);
+    if (o < i) continue;
+    const float wg = L::w(i) * gm, pw = pref * L::w(i);
+    if (o == i) {                                   // rest population
+      f[i] = fmaf(omega, wg * base - f[i], f[i]) - pw * av;
+      continue;
+    }
+    const float ev = edotv<L>(i, v0), ea = edotv<L>(i, a);
+    const float ev3 = 3.0f * ev;
+    const float sym = wg * fmaf(1.5f * ev3, ev, base), asym = wg * ev3;
+    const float fs = pw * fmaf(ev3, ea, -av), fa = pw * ea;
+    f[i] = fmaf(omega, (sym + asym) - f[i], f[i]) + (fs + fa);
+    f[o] = fmaf(omega, (sym - asym) - f[o], f[o]) + (fs - fa);
   }
 }
 
@@ -157,31 +168,63 @@ sc_collide(const DevParams P, const ScParams S, const uint32_t *__restrict__ map
 // populations the thread holds anyway, each psi-gradient is evaluated once instead of twice, and the
 // v fields are neither written by the macro pass nor read here: 2 Q x 4 B in, 2 Q x 4 B out, + rho, phi
 // = 312 B/LUP (D3Q19) against 2 x 172 for the two separate launches.  Same arithmetic, same order.
+// All addresses come from per-slot base pointers in the kernel parameters (see collide_bulk_aa_tab):
+// the access pattern (AB / AA even / AA odd / propagation off) lives in the tables, not in the code.
 #ifndef SLF_MINB_SC_FUSED
-#define SLF_MINB_SC_FUSED 6
+#define SLF_MINB_SC_FUSED 5
 #endif
-template <class L, int MODE, bool SAVE>
+template <class L> struct ScTables {
+  const float *ld1[L::Q], *ld2[L::Q];   // f_i of component 1 / 2 is read from ld[i][t]
+  float *st1[L::Q], *st2[L::Q];         // ... and written to st[i][t]
+  const float *g0[L::Q], *g1[L::Q];     // rho / phi at x + e_i
+};
+
+template <class L, bool CLASSIC>
+__device__ __forceinline__ void sc_psi_gradient_tab(const float *const (&g)[L::Q], unsigned t, float (&grad)[3]) {
+  float fx = 0.f, fy = 0.f, fz = 0.f;
+#pragma unroll
+  for (int i = 1; i < L::Q; i++) {
+    const float x = g[i][t];
+    const float psi = CLASSIC ? 1.0f - expf(-x) : x;
+    if (L::ex(i)) fx = fmaf(psi, (float)L::ex(i) * L::w(i), fx);
+    if (L::ey(i)) fy = fmaf(psi, (float)L::ey(i) * L::w(i), fy);
+    if (L::D == 3 && L::ez(i)) fz = fmaf(psi, (float)L::ez(i) * L::w(i), fz);
+  }
+  grad[0] = fx; grad[1] = fy; grad[2] = fz;
+}
+
+template <class L, bool SAVE>
 __global__ void __launch_bounds__(128, SLF_MINB_SC_FUSED)
-sc_collide_fused(const DevParams P, const ScParams S, const uint32_t *__restrict__ map, const float *d1in,
-                 float *d1out, const float *d2in, float *d2out, const float *__restrict__ rho_f,
-                 const float *__restrict__ phi_f, float *__restrict__ ovx, float *__restrict__ ovy,
-                 float *__restrict__ ovz, long long gi0, long long gi1) {
-  const long long gi = gi0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gi >= gi1) return;
+sc_collide_fused(const DevParams P, const ScParams S, const ScTables<L> T, const uint32_t *__restrict__ map,
+                 float *__restrict__ ovx, float *__restrict__ ovy, float *__restrict__ ovz, long long gi0,
+                 unsigned n, int bounce_walls) {
+  const unsigned t = blockIdx.x * 128u + threadIdx.x;
+  if (t >= n) return;
+  const long long gi = gi0 + t;
   const uint32_t type = map[gi] & P.tmask;
   const bool fluid = type == P.tid[SLF_NT_FLUID];
   const bool wall = type == P.tid[SLF_NT_FULLBB_WALL];
-  if (!fluid && !wall) return;
-  if (wall && MODE != MODE_AB && P.prop) return;
+  if (!fluid && !(wall && bounce_walls)) return;    // full-way bounce-back is a no-op in the AA pattern
 
   float f0[L::Q], f1[L::Q];
-  load_node<L, MODE>(P, d1in, gi, f0);
-  load_node<L, MODE>(P, d2in, gi, f1);
-  if (wall) { sc_wall<L>(P, d1out, gi, f0); sc_wall<L>(P, d2out, gi, f1); return; }
-  const float g0 = rho_f[gi], g1 = phi_f[gi];
+#pragma unroll
+  for (int i = 0; i < L::Q; i++) f0[i] = T.ld1[i][t];
+#pragma unroll
+  for (int i = 0; i < L::Q; i++) f1[i] = T.ld2[i][t];
+  if (wall) {
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) { T.st1[i][t] = f0[L::opp(i)]; T.st2[i][t] = f1[L::opp(i)]; }
+    return;
+  }
+  const float g0 = T.g0[0][t], g1 = T.g1[0][t];
   float grad0[3] = {0.f, 0.f, 0.f}, grad1[3] = {0.f, 0.f, 0.f};
-  if (S.g[0] != 0.0f || S.g[2] != 0.0f) sc_psi_gradient<L>(P, S.potential, rho_f, gi, grad0);
-  if (S.g[1] != 0.0f || S.g[3] != 0.0f) sc_psi_gradient<L>(P, S.potential, phi_f, gi, grad1);
+  if (S.potential == SLF_SC_CLASSIC) {
+    if (S.g[0] != 0.0f || S.g[2] != 0.0f) sc_psi_gradient_tab<L, true>(T.g0, t, grad0);
+    if (S.g[1] != 0.0f || S.g[3] != 0.0f) sc_psi_gradient_tab<L, true>(T.g1, t, grad1);
+  } else {
+    if (S.g[0] != 0.0f || S.g[2] != 0.0f) sc_psi_gradient_tab<L, false>(T.g0, t, grad0);
+    if (S.g[1] != 0.0f || S.g[3] != 0.0f) sc_psi_gradient_tab<L, false>(T.g1, t, grad1);
+  }
 
   float r0, r1, j0[3], j1[3];
   moments<L>(f0, r0, j0);
@@ -200,7 +243,8 @@ sc_collide_fused(const DevParams P, const ScParams S, const uint32_t *__restrict
     const float ig = 1.0f / g0;
     a[0] *= ig; a[1] *= ig; a[2] *= ig;
     if (P.relax) sc_relax<L>(f0, g0, a, v, S.omega[0], S.tau[0]);
-    sc_store<L, MODE>(P, d1out, gi, f0);
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) T.st1[i][t] = f0[i];
   }
   {
     float a[3] = {0.f, 0.f, 0.f};
@@ -209,8 +253,29 @@ sc_collide_fused(const DevParams P, const ScParams S, const uint32_t *__restrict
     const float ig = 1.0f / g1;
     a[0] *= ig; a[1] *= ig; a[2] *= ig;
     if (P.relax) sc_relax<L>(f1, g1, a, v, S.omega[1], S.tau[1]);
-    sc_store<L, MODE>(P, d2out, gi, f1);
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) T.st2[i][t] = f1[i];
   }
+}
+
+// mode: MODE_AB / MODE_AA_EVEN / MODE_AA_ODD as seen by load_node / sc_store
+template <class L>
+static inline ScTables<L> make_sc_tables(const DevParams &P, int mode, const float *d1in, float *d1out,
+                                         const float *d2in, float *d2out, const float *rho, const float *phi,
+                                         long long gi0) {
+  ScTables<L> T;
+  for (int i = 0; i < L::Q; i++) {
+    const long long off = (long long)L::ex(i) + P.sy * L::ey(i) + P.sz * L::ez(i);
+    const long long ld = mode == MODE_AA_ODD ? P.DS * L::opp(i) + gi0 - off : P.DS * i + gi0;
+    long long st;
+    if (!P.prop) st = P.DS * i + gi0;
+    else if (mode == MODE_AA_EVEN) st = P.DS * L::opp(i) + gi0;
+    else st = P.DS * i + gi0 + off;
+    T.ld1[i] = d1in + ld; T.ld2[i] = d2in + ld;
+    T.st1[i] = d1out + st; T.st2[i] = d2out + st;
+    T.g0[i] = rho + gi0 + off; T.g1[i] = phi + gi0 + off;
+  }
+  return T;
 }
 
 // SetInitialConditions of the binary model
