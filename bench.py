@@ -250,7 +250,7 @@ def main():
     alg_bytes = BYTES_PER_LUP['D3Q19'] * fluid_local
     achieved = alg_bytes / (kms * 1e-3) * 1e-9
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': None, 'kernel': 'collide_bulk<D3Q19,BGK> (+collide_boundary)', 'ms_per_launch': kms,
+                'traffic': None, 'kernel': 'collide_bulk_aa_tab<D3Q19,BGK> (+collide_boundary)', 'ms_per_launch': kms,
                 'algorithmic_bytes_per_launch': alg_bytes, 'peak_source': peak_src}
     tr = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tr):

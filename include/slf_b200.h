@@ -188,6 +188,12 @@ int  slf_run_steps(SlfPlan *plan, uint64_t map, uint64_t dist_a, uint64_t dist_b
                    uint64_t vx, uint64_t vy, uint64_t vz, uint32_t iteration, int nsteps,
                    int save_last, uint64_t stream);
 
+/* Output fast path: device side of SubdomainRunner._fields_to_host + LBOutput.mask_nonfluid_nodes
+ * (subdomain_runner.py:1141-1151, io.py:53-59).  Packs the real nodes of `field` (ghost layer and x
+ * padding stripped) into the dense float array `out` of (lat_nz-2)*(lat_ny-2)*(lat_nx-2) elements and
+ * stores NaN for nodes that are not wet; the host then only copies and writes. */
+int  slf_pack_field(SlfPlan *plan, uint64_t map, uint64_t field, uint64_t out, uint64_t stream);
+
 /* PrepareMacroFields(map, dist, rho, options, iteration)  lb_single_fluid.mako:129-159 */
 int  slf_prepare_macro_fields(SlfPlan *plan, uint64_t map, uint64_t dist, uint64_t rho,
                               int options, uint32_t iteration, uint64_t stream);

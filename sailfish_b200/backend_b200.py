@@ -58,6 +58,7 @@ _PROTOTYPES = {
     'slf_collide_and_propagate': [_vp, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _i, _u32, _i, _i, _u64],
     'slf_run_steps': [_vp, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u32, _i, _i, _u64],
     'slf_prepare_macro_fields': [_vp, _u64, _u64, _u64, _i, _u32, _u64],
+    'slf_pack_field': [_vp, _u64, _u64, _u64, _u64],
     'slf_sc_set_initial_conditions': [_vp, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64],
     'slf_sc_prepare_macro_fields': [_vp, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _i, _u32, _i, _i, _u64],
     'slf_sc_collide_and_propagate': [_vp, _i, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _u64, _i, _u32, _i, _i, _u64],

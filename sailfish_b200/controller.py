@@ -37,6 +37,10 @@ class LBSimulationController(object):
         g.add_argument('--from', dest='from_', type=int, default=0)
         g.add_argument('--max_iters', type=int, default=0, help='number of iterations to run (0 = run nothing)')
         g.add_argument('--output', type=str, default='', help='base name of the .npz output files')
+        g.add_argument('--sync_output', action='store_true', default=False,
+                       help='write output the way the reference does (synchronous copy of the padded fields, '
+                            'host-side masking, savez in the main thread) instead of the device-side pack + '
+                            'writer thread')
         g.add_argument('--seed', type=int, default=int(time.time()))
         g.add_argument('--gpus', type=int, nargs='+', default=[0])
         g.add_argument('--quiet', action='store_true', default=False)
@@ -180,6 +184,10 @@ class LBSimulationController(object):
 
     def run(self, ignore_cmdline=False):
         self.setup([] if ignore_cmdline else sys.argv[1:])
+        return self.run_loop()
+
+    def run_loop(self):
+        """The main loop of every local subdomain (after setup())."""
         cfg = self.config
         if cfg.max_iters <= 0:
             return self
@@ -194,8 +202,11 @@ class LBSimulationController(object):
             flags = [r.end_main_step() for r in self.runners]
             done = all(flags)
         self.sync()
+        for r in self.runners:
+            r.finish_output()
         self.barrier()
         dt = time.time() - t0
+        self.loop_seconds = dt
         if not cfg.quiet:
             nodes = sum(r.num_fluid_nodes for r in self.runners)
             print('Simulation completed after %d iterations: %.2f MLUPS (local subdomains)'

@@ -418,6 +418,20 @@ int slf_distribute_sparse_data(SlfPlan *pl, uint64_t idx_array, uint64_t dist, u
 
 
 
+// ---- output fast path ---------------------------------------------------------------------
+int slf_pack_field(SlfPlan *pl, uint64_t map, uint64_t field, uint64_t out, uint64_t stream) {
+  if (!pl) return fail(SLF_EINVAL, "null plan");
+  if (!map || !field || !out) return fail(SLF_EINVAL, "null buffer");
+  const DevParams &d = pl->dp;
+  const int rx = d.nx - 2, ry = d.ny - 2, rz = pl->D == 3 ? d.nz - 2 : 1;
+  if (rx <= 0 || ry <= 0 || rz <= 0) return 0;
+  dim3 grid((rx + 255) / 256, ry, rz);
+  pack_field<<<grid, 256, 0, (cudaStream_t)stream>>>(d, (const uint32_t *)map, (const float *)field, (float *)out,
+                                                      pl->D);
+  LAUNCH_OK("pack_field");
+  return 0;
+}
+
 // ---- multi-step driver -------------------------------------------------------------------
 // The reference pays ~10 Python calls + 1-2 pycuda launches per time step
 // (subdomain_runner.py:1673-1748); on small lattices (ldc_2d 256^2: ~66 k nodes, a few

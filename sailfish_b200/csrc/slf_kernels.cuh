@@ -654,3 +654,28 @@ __global__ void xfer_sparse(const uint32_t *__restrict__ idx_array, float *dist,
   if (gi == 0xffffffffu || gi >= limit) return;
   if (DISTRIBUTE) dist[gi] = buffer[idx]; else buffer[idx] = dist[gi];
 }
+
+// ----------------------------------------------------------------------------------------
+// Output fast path: the device side of _fields_to_host + mask_nonfluid_nodes
+// (subdomain_runner.py:1141-1151, io.py:53-59).  Packs the real (non-ghost, non-padding) nodes
+// of one field into a dense [nz-2][ny-2][nx-2] array and writes NaN where the node is not wet,
+// so that the host only has to hand the buffer to the file writer.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ bool is_wet_type(const DevParams &P, uint32_t type) {
+  return type == P.tid[SLF_NT_FLUID] || type == P.tid[SLF_NT_HALFBB_WALL] ||
+         type == P.tid[SLF_NT_EQUILIBRIUM_VELOCITY] || type == P.tid[SLF_NT_EQUILIBRIUM_DENSITY] ||
+         type == P.tid[SLF_NT_REGULARIZED_VELOCITY] || type == P.tid[SLF_NT_REGULARIZED_DENSITY] ||
+         type == P.tid[SLF_NT_DO_NOTHING];
+}
+
+static __global__ void __launch_bounds__(256)
+pack_field(const DevParams P, const uint32_t *__restrict__ map, const float *__restrict__ field,
+           float *__restrict__ out, int dim) {
+  const int rx = P.nx - 2, ry = P.ny - 2;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= rx) return;
+  const int y = blockIdx.y, z = blockIdx.z;                 // z = 0 in 2-D
+  const long long gi = (long long)(x + 1) + P.sy * (y + 1) + (dim == 3 ? P.sz * (z + 1) : 0);
+  const bool wet = is_wet_type(P, map[gi] & P.tmask);
+  out[(long long)x + (long long)rx * (y + (long long)ry * z)] = wet ? field[gi] : __int_as_float(0x7fc00000);
+}

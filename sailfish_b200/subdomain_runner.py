@@ -336,10 +336,35 @@ class SubdomainRunner(object):
 
     def begin_main_step(self):
         self._output_req = self._sim.need_output()
+        self._host_sync_req = bool(self._sim.need_sync_flag)     # a hook wants the fields on the host
         self._sync_req, self._fields_req = self._sim.need_sync_fields()
+
+    def _fast_output(self):
+        """The device-side pack + asynchronous writer (sailfish_b200/io.py) replaces the host round trip
+        unless the simulation asked for the fields on the host (need_sync_flag) or --sync_output."""
+        if getattr(self.config, 'sync_output', False) or not self._output.basename:
+            return None
+        if getattr(self, '_fast', None) is None:
+            from sailfish_b200.io import FastOutput
+            self._fast = FastOutput(self, self._output)
+        return self._fast
+
+    def finish_output(self):
+        if getattr(self, '_fast', None) is not None:
+            self._fast.close()
+            self._fast = None
 
     def end_main_step(self):
         output_req, sync_req = self._output_req, self._sync_req
+        if output_req and not self._host_sync_req and self._fast_output() is not None:
+            self._fast.save(self._sim.iteration)
+            quit_ = self.need_quit()
+            if quit_:
+                self.sync()
+                self.finish_output()
+                return True
+            self._sim.after_step(self)
+            return False
         if sync_req:
             self._fields_to_host()
         quit_ = self.need_quit()
