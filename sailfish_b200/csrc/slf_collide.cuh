@@ -4,18 +4,6 @@
 
 #include "slf_plan.cuh"
 
-#ifndef SLF_AA_TABLE
-#define SLF_AA_TABLE 1
-#endif
-#ifndef SLF_HINT
-#define SLF_HINT 1
-#endif
-
-static inline int slf_env_int(const char *name, int dflt) {
-  const char *v = getenv(name);
-  return v && *v ? atoi(v) : dflt;
-}
-
 // ---- dispatch helpers --------------------------------------------------------------------
 template <class L, int MODEL, int MODE, bool SAVE>
 static int launch_collide(SlfPlan *pl, const uint32_t *map, const float *din, float *dout, float *rho,
@@ -32,14 +20,9 @@ static int launch_collide(SlfPlan *pl, const uint32_t *map, const float *din, fl
     if constexpr (MODE != MODE_AB) {
       if (plain) {
         float *dist = dout;      // AA: dist_in == dist_out (checked by the caller)
-#if SLF_AA_TABLE
         collide_bulk_aa_tab<L, MODEL, SAVE><<<(unsigned)nb, bs, 0, s>>>(
             pl->dp, make_aa_table<L>(pl->dp, dist, gi0, MODE == MODE_AA_ODD), pl->d_fluid_mask, rho, vx, vy, vz,
             gi0, (unsigned)n);
-#else
-        collide_bulk_aa<L, MODEL, MODE, SAVE><<<(unsigned)nb, bs, 0, s>>>(
-            pl->dp, pl->d_fluid_mask, dist, rho, vx, vy, vz, gi0, gi1);
-#endif
         LAUNCH_OK("collide_bulk_aa");
       }
     }

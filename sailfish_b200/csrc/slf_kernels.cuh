@@ -106,9 +106,10 @@ collide_bulk(const DevParams P, const uint32_t *__restrict__ map, const uint32_t
 // that every address is computed once and shared by the load and the store, and needs only
 // the 1-bit fluid mask: full-way bounce-back walls are no-ops in this pattern (see
 // collide_bulk) and every other node type goes to the boundary kernel.
-// Launch shape (measured on B200, profiles/r01_exp_bulk_variants.txt): 128-thread blocks,
-// register budget for 10 resident blocks per SM (48 registers), default cache policy:
-// 6.0 TB/s of algorithmic traffic on D3Q19 BGK 512^3 = 91 % of the measured copy bandwidth.
+// Launch shape (measured on B200, profiles/r01_exp_bulk_variants.txt, r01_sweep_minb_mrt_q27.txt):
+// 128-thread blocks, register budget for 10 resident blocks per SM (48 registers; D3Q27: 8 blocks,
+// 64 registers), default cache policy: 6.2 TB/s of algorithmic traffic on D3Q19 BGK 512^3 = 94 % of
+// the measured copy bandwidth.
 #ifndef SLF_MINB_D3Q19_MRT
 #define SLF_MINB_D3Q19_MRT 10
 #endif
@@ -125,44 +126,9 @@ template <> struct BulkTuning<D3Q27, SLF_BGK> { static constexpr int MINB = SLF_
 template <> struct BulkTuning<D2Q9, SLF_BGK> { static constexpr int MINB = 10; };
 template <> struct BulkTuning<D2Q9, SLF_MRT> { static constexpr int MINB = 10; };
 
-template <class L, int MODEL, int MODE, bool SAVE>
-__global__ void __launch_bounds__(128, BulkTuning<L, MODEL>::MINB)
-collide_bulk_aa(const DevParams P, const uint32_t *__restrict__ fluid_mask, float *dist,
-                float *__restrict__ orho, float *__restrict__ ovx, float *__restrict__ ovy,
-                float *__restrict__ ovz, long long gi0, long long gi1) {
-  static_assert(MODE == MODE_AA_EVEN || MODE == MODE_AA_ODD, "AA kernel");
-  const long long gi = gi0 + (long long)blockIdx.x * 128 + threadIdx.x;
-  if (gi >= gi1) return;
-  if (!((fluid_mask[gi >> 5] >> (gi & 31)) & 1u)) return;
-
-  float f[L::Q];
-#pragma unroll
-  for (int i = 0; i < L::Q; i++) {
-    if (MODE == MODE_AA_ODD) f[i] = dist[gi - noff<L>(P, i) + P.DS * L::opp(i)];
-    else f[i] = dist[gi + P.DS * i];
-  }
-  float rho, v[3];
-  moments<L>(f, rho, v);
-  const float inv = 1.0f / rho;
-  v[0] *= inv; v[1] *= inv; v[2] *= inv;
-  // (body force presence is a run-time test on purpose: with it fixed at compile time ptxas
-  //  schedules the odd kernel into 112 bytes of spills under the same 48-register budget)
-  if (MODEL == SLF_MRT) collide_mrt<L, false>(P, v, f);
-  else collide_bgk<L>(P, rho, v, f);
-  if (SAVE) {
-    orho[gi] = rho; ovx[gi] = v[0]; ovy[gi] = v[1];
-    if (L::D == 3) ovz[gi] = v[2];
-  }
-#pragma unroll
-  for (int i = 0; i < L::Q; i++) {
-    if (MODE == MODE_AA_EVEN) dist[gi + P.DS * L::opp(i)] = f[i];
-    else dist[gi + noff<L>(P, i) + P.DS * i] = f[i];
-  }
-}
-
-// Same kernel with its Q addresses taken from a table of per-slot base pointers (kernel
-// parameters, i.e. the constant bank): address = table[i] + 4 * t with t the 32-bit offset of
-// the thread in the launch.  That is one LDC.64 + one IMAD.WIDE.U32 per access instead of the
+// The Q addresses come from a table of per-slot base pointers (kernel parameters, i.e. the
+// constant bank): address = table[i] + 4 * t with t the 32-bit offset of the thread in the
+// launch.  That is one LDC.64 + one IMAD.WIDE.U32 per access instead of the
 // 64-bit index arithmetic of `dist[gi +- noff(i) + DS * slot]` (about 60 % of the dynamic
 // instructions of the BGK kernel), and it folds the even/odd difference into the table:
 //   even: table[i] = dist + DS * i + gi0;   odd: table[i] = dist + DS * opp(i) + gi0 - noff(i);
