@@ -168,6 +168,9 @@ sc_collide(const DevParams P, const ScParams S, const uint32_t *__restrict__ map
 // populations the thread holds anyway, each psi-gradient is evaluated once instead of twice, and the
 // v fields are neither written by the macro pass nor read here: 2 Q x 4 B in, 2 Q x 4 B out, + rho, phi
 // = 312 B/LUP (D3Q19) against 2 x 172 for the two separate launches.  Same arithmetic, same order.
+// Measured alternatives that lost (profiles/r01_sweep_sc_fused.txt): re-reading component 2 instead of
+// holding it (64 registers, 8 blocks/SM: 8.9 GLUPS vs 9.2), and one half-block per component with the
+// moments / gradients exchanged through shared memory (48-64 registers: 7.0-7.6 GLUPS).
 // All addresses come from per-slot base pointers in the kernel parameters (see collide_bulk_aa_tab):
 // the access pattern (AB / AA even / AA odd / propagation off) lives in the tables, not in the code.
 #ifndef SLF_MINB_SC_FUSED
