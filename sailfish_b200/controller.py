@@ -18,7 +18,7 @@ import numpy as np
 from sailfish_b200 import backend_b200 as bk
 from sailfish_b200 import config as cfgmod
 from sailfish_b200.geo import LBGeometry2D, LBGeometry3D
-from sailfish_b200.subdomain_runner import HaloLink, SubdomainRunner, LBOutput
+from sailfish_b200.subdomain_runner import checkpoint_path, HaloLink, SubdomainRunner, LBOutput
 
 _u64 = ctypes.c_uint64
 
@@ -41,6 +41,13 @@ class LBSimulationController(object):
                        help='write output the way the reference does (synchronous copy of the padded fields, '
                             'host-side masking, savez in the main thread) instead of the device-side pack + '
                             'writer thread')
+        g.add_argument('--checkpoint_file', type=str, default='', help='base name of checkpoint files')
+        g.add_argument('--single_checkpoint', action='store_true', default=False)
+        g.add_argument('--restore_from', type=str, default='', help='checkpoint to start from')
+        g.add_argument('--norestore_time', action='store_false', dest='restore_time', default=True)
+        g.add_argument('--final_checkpoint', action='store_true', default=False)
+        g.add_argument('--checkpoint_every', type=int, default=0)
+        g.add_argument('--checkpoint_from', type=int, default=0)
         g.add_argument('--seed', type=int, default=int(time.time()))
         g.add_argument('--gpus', type=int, nargs='+', default=[0])
         g.add_argument('--quiet', action='store_true', default=False)
@@ -114,6 +121,9 @@ class LBSimulationController(object):
             r = runner_cls(sim, s, output=LBOutput(self.config, s.id), device=devices[s.id])
             r.initialize()
             self.runners.append(r)
+        for r in self.runners:
+            if self.config.restore_from:
+                r.restore_checkpoint(checkpoint_path(self.config.restore_from, r._spec.id))
         self._link(dist_mode, rank, ws)
         # nobody may push into a neighbour's buffers before that neighbour has finished uploading and
         # initialising them
@@ -204,6 +214,8 @@ class LBSimulationController(object):
         self.sync()
         for r in self.runners:
             r.finish_output()
+            if cfg.checkpoint_file and cfg.final_checkpoint and r._sim.iteration >= cfg.max_iters:
+                r.save_checkpoint()
         self.barrier()
         dt = time.time() - t0
         self.loop_seconds = dt

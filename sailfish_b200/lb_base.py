@@ -50,6 +50,19 @@ class LBSim(object):
     def fields(cls):
         return []
 
+    def get_state(self):
+        """lb_base.py:216-220: what a checkpoint stores besides the populations."""
+        return {'iteration': self.iteration}
+
+    def set_state(self, state):
+        self.iteration = state['iteration']
+
+    def need_checkpoint(self):
+        """lb_base.py:254-260."""
+        cfg = self.config
+        every = getattr(cfg, 'checkpoint_every', 0)
+        return every > 0 and (self.iteration % every) == 0 and self.iteration >= getattr(cfg, 'checkpoint_from', 0)
+
     def need_output(self):
         """lb_base.py:222-231."""
         if self.config.output_required:

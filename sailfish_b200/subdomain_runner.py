@@ -20,6 +20,22 @@ from sailfish_b200 import backend_b200 as bk
 from sailfish_b200 import params as P
 from sailfish_b200.subdomain import SubdomainSpec
 
+
+def checkpoint_filename(base, digits, subdomain_id, it):
+    """sailfish/io.py:190-191 (numpy appends '.npz')."""
+    return ('{0}.{1:0' + str(digits) + 'd}.{2}.cpoint').format(base, it, subdomain_id)
+
+
+def checkpoint_path(base, subdomain_id):
+    """sailfish/io.py:193-202: '<base>.last' picks a file by globbing, otherwise the name is literal."""
+    import glob
+    if base.endswith('.last'):
+        files = sorted(glob.glob('{0}.*.{1}.cpoint.npz'.format(base[:-5], subdomain_id)))
+        if not files:
+            raise IOError('no checkpoint matches %s' % base)
+        return files[0]
+    return '{0}.{1}.cpoint.npz'.format(base, subdomain_id)
+
 _u64 = ctypes.c_uint64
 
 
@@ -113,6 +129,7 @@ class SubdomainRunner(object):
         self._scalar_fields, self._vector_fields = [], []
         self._field_base = {}
         self._links = {}
+        self._first_iteration = 0      # no neighbour has pushed anything before this step (0 or a restored value)
         self._lib = bk.lib()
         self.float = np.float32
         if getattr(self.config, 'precision', 'single') != 'single':
@@ -211,12 +228,59 @@ class SubdomainRunner(object):
     def gpu_geo_map(self):
         return self._dev.d_map
 
-    def _debug_get_dist(self, output=True):
-        """[Q, (nz+2), ny+2, arr_nx] array of the lattice most recently written."""
-        return self._dev.get_dist()
+    def _debug_get_dist(self, output=True, grid_num=0):
+        """[Q, (nz+2), ny+2, arr_nx] raw copy of one lattice buffer (subdomain_runner.py:1363-1381):
+        ``output`` selects the buffer written by the last step."""
+        idx = self._sim.iteration & 1
+        if not output:
+            idx = 1 - idx
+        self.sync()
+        out = np.zeros([self._sim.grid.Q] + list(self._physical_size), dtype=np.float32)
+        self._lib.call('slf_memcpy_d2h', out.ctypes.data_as(bk._vp), int(self.gpu_dist(grid_num, idx)),
+                       int(out.nbytes))
+        return out
 
-    def _debug_set_dist(self, dist, output=True):
-        self._dev.set_dist(dist)
+    def _debug_set_dist(self, dist, output=True, grid_num=0):
+        """subdomain_runner.py:1383-1388."""
+        idx = self._sim.iteration & 1
+        if not output:
+            idx = 1 - idx
+        dist = np.ascontiguousarray(dist, dtype=np.float32)
+        if list(dist.shape) != [self._sim.grid.Q] + list(self._physical_size):
+            raise ValueError('checkpoint lattice has shape %s, this subdomain needs %s'
+                             % (dist.shape, [self._sim.grid.Q] + list(self._physical_size)))
+        self.sync()
+        self._lib.call('slf_memcpy_h2d', int(self.gpu_dist(grid_num, idx)), dist.ctypes.data_as(bk._vp),
+                       int(dist.nbytes))
+
+    # -- checkpoints (subdomain_runner.py:1414-1449) -----------------------------------------------
+    def save_checkpoint(self):
+        import pickle
+        cfg = self.config
+        if getattr(cfg, 'single_checkpoint', False):
+            fname = checkpoint_filename(cfg.checkpoint_file, 1, self._spec.id, 0)
+        else:
+            digits = str(int(np.log10(cfg.max_iters)) + 1) if cfg.max_iters else '7'
+            fname = checkpoint_filename(cfg.checkpoint_file, digits, self._spec.id, self._sim.iteration)
+        data = {'state': np.frombuffer(pickle.dumps(self._sim.get_state(), 2), dtype=np.uint8)}
+        for i in range(len(self._sim.grids)):
+            data['dist%da' % i] = self._debug_get_dist(True, i)
+            if cfg.access_pattern == 'AB':
+                data['dist%db' % i] = self._debug_get_dist(False, i)
+        np.savez(fname, **data)
+        return fname + '.npz'
+
+    def restore_checkpoint(self, fname):
+        import pickle
+        cp = np.load(fname)
+        self._sim.set_state(pickle.loads(cp['state'].tobytes()))
+        if not getattr(self.config, 'restore_time', True):
+            self._sim.iteration = 0
+        self._dev.iteration = self._first_iteration = self._sim.iteration
+        for k in cp.files:
+            if k.startswith('dist'):
+                self._debug_set_dist(cp[k], k.endswith('a'), int(k[4:-1]))
+        self.sync()
 
     @property
     def num_fluid_nodes(self):
@@ -260,7 +324,7 @@ class SubdomainRunner(object):
             dev.apply_pbc()
         else:
             cs, ds = self._calc_stream, self._data_stream
-            if it > 0:
+            if it > self._first_iteration:
                 # the neighbours' planes of the previous step must have landed (and, symmetrically,
                 # the neighbours are done with the layers this step's push overwrites)
                 self._wait_incoming(0, it - 1, cs)
@@ -364,6 +428,7 @@ class SubdomainRunner(object):
                 self.finish_output()
                 return True
             self._sim.after_step(self)
+            self._maybe_checkpoint()
             return False
         if sync_req:
             self._fields_to_host()
@@ -379,7 +444,12 @@ class SubdomainRunner(object):
         elif sync_req:
             self._output.mask_nonfluid_nodes()
         self._sim.after_step(self)
+        self._maybe_checkpoint()
         return False
+
+    def _maybe_checkpoint(self):
+        if getattr(self.config, 'checkpoint_file', '') and self._sim.need_checkpoint():
+            self.save_checkpoint()
 
     def sync(self):
         self._calc_stream.synchronize()
@@ -440,9 +510,6 @@ class NNSubdomainRunner(SubdomainRunner):
         a, b = self._dev.d_dist[num]
         return a if (copy == 0 or b is None) else b
 
-    def _debug_get_dist(self, output=True, grid_num=0):
-        return self._dev.get_dist(grid_num)
-
     def export_buffers(self):
         d = self._dev
         out = {'rho': int(d.d_rho), 'phi': int(d.d_phi), 'sems': int(self._sems)}
@@ -465,7 +532,7 @@ class NNSubdomainRunner(SubdomainRunner):
         it = dev.iteration
         cs = self._calc_stream
         links = self._links
-        if links and it > 0:
+        if links and it > self._first_iteration:
             self._wait_incoming(0, it - 1, cs)
         dev.macro(stream=cs, with_v=bool(sync_req))
         dev.macro_pbc(stream=cs)
