@@ -530,11 +530,18 @@ int orc_set_initial_conditions(const SlfParams *P, REAL *dist, const REAL *ivx, 
   (void)map;
   Ctx Cs; int rc = ctx_init(&Cs, P); if (rc) return rc;
   const Ctx *C = &Cs; const Lat *L = C->L;
-  for (int z = 0; z < C->nz; z++) for (int y = 0; y < C->ny; y++) for (int x = 0; x < C->nx; x++) {
-    long long gi = x + C->stride[1] * y + C->stride[2] * z;
-    REAL v[3], feq[MAXQ]; v[0] = ivx[gi]; v[1] = ivy[gi]; v[2] = L->D == 3 ? ivz[gi] : (REAL)0;
-    feq_all(L, irho[gi], v, feq);
-    for (int i = 0; i < L->Q; i++) dist[gi + C->DS * i] = feq[i];
+  /* same row decomposition and static schedule as the step: on a multi-socket host every thread
+   * first-touches the rows it will later stream through */
+  const long long rows = (long long)C->nz * C->ny;
+#pragma omp parallel for schedule(static)
+  for (long long row = 0; row < rows; row++) {
+    const int z = (int)(row / C->ny), y = (int)(row % C->ny);
+    for (int x = 0; x < C->nx; x++) {
+      long long gi = x + C->stride[1] * y + C->stride[2] * z;
+      REAL v[3], feq[MAXQ]; v[0] = ivx[gi]; v[1] = ivy[gi]; v[2] = L->D == 3 ? ivz[gi] : (REAL)0;
+      feq_all(L, irho[gi], v, feq);
+      for (int i = 0; i < L->Q; i++) dist[gi + C->DS * i] = feq[i];
+    }
   }
   return 0;
 }
