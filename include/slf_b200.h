@@ -251,6 +251,16 @@ int  slf_collect_sparse_data(SlfPlan *plan, uint64_t idx_array, uint64_t dist, u
 int  slf_distribute_sparse_data(SlfPlan *plan, uint64_t idx_array, uint64_t dist, uint64_t buffer,
                                 int max_idx, uint64_t stream);
 
+/* Collect/DistributeContinuousMacroData(field, face, base_gx, base_other, max_lx, max_other, buffer)
+ * kernel_utils.mako:838-953 (call sites subdomain_runner.py:1984-2058): ghost-layer exchange of a
+ * scalar field through y and z faces; collect reads the first/last real layer, distribute writes the
+ * ghost layer.  2-D (reference signature field, base_gx, max_lx, gy, buffer): pass gy as base_other,
+ * face is ignored, max_other = 1.  Buffer rows are dense, [max_other][max_lx]. */
+int  slf_collect_continuous_macro_data(SlfPlan *plan, uint64_t field, int face, int base_gx, int base_other,
+                                       int max_lx, int max_other, uint64_t buffer, uint64_t stream);
+int  slf_distribute_continuous_macro_data(SlfPlan *plan, uint64_t field, int face, int base_gx, int base_other,
+                                          int max_lx, int max_other, uint64_t buffer, uint64_t stream);
+
 /* ---- halo exchange between the GPUs of one box (subdomains split along the outermost
  * axis: conn_axis = z in 3-D, y in 2-D) -------------------------------------------------
  * Replaces SubdomainRunner._send_dists/_recv_dists + the collect/distribute kernels + the

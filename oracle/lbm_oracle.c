@@ -745,6 +745,36 @@ int orc_distribute_continuous_data(const SlfParams *P, REAL *dist, int face, int
   return xfer(P, dist, face, base_gx, base_other, max_lx, max_other, (REAL *)buffer, with_swap, 1);
 }
 
+/* Collect/DistributeContinuousMacroData, kernel_utils.mako:838-953: collect reads layer
+ * lat_linear_macro[face] (first/last real layer), distribute writes lat_linear[face] (ghost layer);
+ * 2-D kernels take the row explicitly (passed in base_other).  Buffer [other][x], dense rows. */
+static int xfer_macro(const SlfParams *P, REAL *field, int face, int base_gx, int base_other, int max_lx,
+                      int max_other, REAL *buffer, int distribute) {
+  Ctx Cs; int rc = ctx_init(&Cs, P); if (rc) return rc;
+  const Ctx *C = &Cs; const Lat *L = C->L;
+  if (L->D == 2) max_other = 1;
+  else if (face < 2 || face > 5) return SLF_EINVAL;
+  for (int o = 0; o < max_other; o++) for (int x = 0; x < max_lx; x++) {
+    int c[3] = {base_gx + x, 0, 0};
+    if (L->D == 2) c[1] = base_other;
+    else {
+      int layer = face_layer(C, face, distribute ? 0 : 1);
+      if (face / 2 == 1) { c[1] = layer; c[2] = base_other + o; } else { c[1] = base_other + o; c[2] = layer; }
+    }
+    long long gi = gidx(C, c), bi = (long long)o * max_lx + x;
+    if (distribute) field[gi] = buffer[bi]; else buffer[bi] = field[gi];
+  }
+  return 0;
+}
+int orc_collect_continuous_macro_data(const SlfParams *P, const REAL *field, int face, int base_gx, int base_other,
+                                      int max_lx, int max_other, REAL *buffer) {
+  return xfer_macro(P, (REAL *)field, face, base_gx, base_other, max_lx, max_other, buffer, 0);
+}
+int orc_distribute_continuous_macro_data(const SlfParams *P, REAL *field, int face, int base_gx, int base_other,
+                                         int max_lx, int max_other, const REAL *buffer) {
+  return xfer_macro(P, field, face, base_gx, base_other, max_lx, max_other, (REAL *)buffer, 1);
+}
+
 int orc_sizeof_real(void) { return (int)sizeof(REAL); }
 
 /* ------------------------------------------------------------------------------------

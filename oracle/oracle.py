@@ -86,6 +86,18 @@ def distribute(params, dist, face, base_gx, base_other, max_lx, max_other, buf, 
                                             max_lx, max_other, _p(buf), int(with_swap)), 'distribute')
 
 
+def collect_macro(params, field, face, base_gx, base_other, max_lx, max_other, buf):
+    lib = _lib(field.dtype)
+    _chk(lib.orc_collect_continuous_macro_data(ctypes.byref(params), _p(field), face, base_gx, base_other, max_lx,
+                                               max_other, _p(buf)), 'collect_macro')
+
+
+def distribute_macro(params, field, face, base_gx, base_other, max_lx, max_other, buf):
+    lib = _lib(field.dtype)
+    _chk(lib.orc_distribute_continuous_macro_data(ctypes.byref(params), _p(field), face, base_gx, base_other, max_lx,
+                                                  max_other, _p(buf)), 'distribute_macro')
+
+
 def lattice_info(lattice_id):
     lib = _lib(np.float32)
     Q, D = ctypes.c_int(), ctypes.c_int()

@@ -68,6 +68,8 @@ _PROTOTYPES = {
     'slf_apply_periodic_boundary_conditions': [_vp, _u64, _i, _i, _u64],
     'slf_collect_continuous_data': [_vp, _u64, _i, _i, _i, _i, _i, _u64, _i, _u64],
     'slf_distribute_continuous_data': [_vp, _u64, _i, _i, _i, _i, _i, _u64, _i, _u64],
+    'slf_collect_continuous_macro_data': [_vp, _u64, _i, _i, _i, _i, _i, _u64, _u64],
+    'slf_distribute_continuous_macro_data': [_vp, _u64, _i, _i, _i, _i, _i, _u64, _u64],
     'slf_collect_sparse_data': [_vp, _u64, _u64, _u64, _i, _u64],
     'slf_distribute_sparse_data': [_vp, _u64, _u64, _u64, _i, _u64],
     'slf_halo_push': [_vp, _u64, _i, _u64, _i, _i, _i, _u64],
@@ -269,6 +271,17 @@ class Kernel(object):
                 dist, face, base_gx, max_lx, buf = a[:5]
                 ndists = b._face_ndists()
                 l.call(fn, plan, int(dist), int(face), int(base_gx), 0, int(max_lx) // ndists, 1, int(buf), swap, s)
+        elif n in ('CollectContinuousMacroData', 'DistributeContinuousMacroData'):
+            # 3-D: field, face, base_gx, base_other, max_lx, max_other, buffer;  2-D: field, base_gx, max_lx, gy, buffer
+            # (subdomain_runner.py:1984-2058)
+            fn = 'slf_collect_continuous_macro_data' if n.startswith('Collect') else 'slf_distribute_continuous_macro_data'
+            if dim == 3:
+                field, face, base_gx, base_other, max_lx, max_other, buf = a[:7]
+            else:
+                field, base_gx, max_lx, base_other, buf = a[:5]
+                face, max_other = 0, 1
+            l.call(fn, plan, int(field), int(face), int(base_gx), int(base_other), int(max_lx), int(max_other),
+                   int(buf), s)
         elif n in ('CollectSparseData', 'DistributeSparseData'):
             idx, dist, buf, max_idx = a[:4]
             fn = 'slf_collect_sparse_data' if n.startswith('Collect') else 'slf_distribute_sparse_data'
@@ -290,7 +303,25 @@ class B200Backend(object):
 
     @classmethod
     def add_options(cls, group):
-        return 0
+        """Accepts the CUDA backend's flags (backend_cuda.py:45-83) so that scripts and regtests written
+        for it run unchanged; they configure pycuda / nvcc and have no effect here."""
+        import argparse
+        for flag, dest, action, default in (
+                ('--cuda-kernel-stats', 'cuda_kernel_stats', 'store_true', False),
+                ('--cuda_nvcc', 'cuda_nvcc', 'store', 'nvcc'),
+                ('--cuda-nvcc-opts', 'cuda_nvcc_opts', 'store', ''),
+                ('--cuda-keep-temp', 'cuda_keep_temp', 'store_true', False),
+                ('--cuda-fermi-highprec', 'cuda_fermi_highprec', 'store_true', False),
+                ('--cuda-disable-l1', 'cuda_disable_l1', 'store_true', False),
+                ('--nocuda_cache', 'cuda_cache', 'store_false', True),
+                ('--cuda-sched-yield', 'cuda_sched_yield', 'store_true', False),
+                ('--cuda-minimize-cpu-usage', 'cuda_minimize_cpu', 'store_true', False)):
+            try:
+                group.add_argument(flag, dest=dest, action=action, default=default,
+                                   help='accepted for compatibility with the CUDA backend; ignored')
+            except argparse.ArgumentError:      # the CUDA backend is installed too and owns the flag
+                pass
+        return 1
 
     def __init__(self, options=None, gpu_id=0):
         self.options = options
@@ -400,6 +431,9 @@ class B200Backend(object):
             params = source
         elif isinstance(source, dict):
             params = P.from_context(source)
+            # boundary_size > 0: the reference runner issues a boundary and a bulk launch per step
+            # (subdomain_runner.py:394-479, 1010-1047); see _region_for
+            self.split_enabled = bool(source.get('boundary_size', 0))
         else:
             raise B200Error('backend_b200.build() expects the code-generation context, '
                             'not rendered source text (got %s)' % type(source).__name__)

@@ -418,6 +418,42 @@ int slf_distribute_sparse_data(SlfPlan *pl, uint64_t idx_array, uint64_t dist, u
 
 
 
+// ---- Collect/DistributeContinuousMacroData ---------------------------------------------------
+static int xfer_macro_launch(SlfPlan *pl, uint64_t field, int face, int base_gx, int base_other, int max_lx,
+                             int max_other, uint64_t buffer, bool distribute, uint64_t stream) {
+  if (!pl) return fail(SLF_EINVAL, "null plan");
+  if (!field || !buffer) return fail(SLF_EINVAL, "null buffer");
+  const DevParams &d = pl->dp;
+  if (pl->D == 2) {
+    max_other = 1;
+    if (base_other < 0 || base_other >= d.ny) return fail(SLF_EINVAL, "row outside the lattice");
+  } else {
+    if (face < 2 || face > 5) return fail(SLF_EINVAL, "macro data moves through y and z faces (x faces use the sparse kernels)");
+    const int lim_o = (face >> 1) == 1 ? d.nz : d.ny;
+    if (base_other < 0 || max_other < 0 || base_other + max_other > lim_o) return fail(SLF_EINVAL, "rows outside the lattice");
+  }
+  if (base_gx < 0 || max_lx < 0 || base_gx + max_lx > d.nx) return fail(SLF_EINVAL, "columns outside the lattice");
+  if (max_lx == 0 || max_other == 0) return 0;
+  dim3 grid((max_lx + 127) / 128, max_other);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (distribute)
+    xfer_macro<true><<<grid, 128, 0, s>>>(d, (float *)field, pl->D, face, base_gx, base_other, max_lx, max_other, (float *)buffer);
+  else
+    xfer_macro<false><<<grid, 128, 0, s>>>(d, (float *)field, pl->D, face, base_gx, base_other, max_lx, max_other, (float *)buffer);
+  LAUNCH_OK("xfer_macro");
+  return 0;
+}
+
+int slf_collect_continuous_macro_data(SlfPlan *pl, uint64_t field, int face, int base_gx, int base_other, int max_lx,
+                                      int max_other, uint64_t buffer, uint64_t stream) {
+  return xfer_macro_launch(pl, field, face, base_gx, base_other, max_lx, max_other, buffer, false, stream);
+}
+
+int slf_distribute_continuous_macro_data(SlfPlan *pl, uint64_t field, int face, int base_gx, int base_other, int max_lx,
+                                         int max_other, uint64_t buffer, uint64_t stream) {
+  return xfer_macro_launch(pl, field, face, base_gx, base_other, max_lx, max_other, buffer, true, stream);
+}
+
 // ---- output fast path ---------------------------------------------------------------------
 int slf_pack_field(SlfPlan *pl, uint64_t map, uint64_t field, uint64_t out, uint64_t stream) {
   if (!pl) return fail(SLF_EINVAL, "null plan");

@@ -621,6 +621,32 @@ __global__ void xfer_sparse(const uint32_t *__restrict__ idx_array, float *dist,
   if (DISTRIBUTE) dist[gi] = buffer[idx]; else buffer[idx] = dist[gi];
 }
 
+// Collect/DistributeContinuousMacroData (kernel_utils.mako:838-953): one scalar field, faces >= 2.
+// Collect reads the first/last real layer (lat_linear_macro), distribute writes the ghost layer
+// (lat_linear).  2-D: the row is passed explicitly (the reference's `gy` argument) in base_other.
+// Buffer rows are dense ([other][x], row length max_lx = the shape the reference allocates,
+// subdomain_connection.py:530-534).
+template <bool DISTRIBUTE>
+static __global__ void __launch_bounds__(128)
+xfer_macro(const DevParams P, float *field, int dim, int face, int base_gx, int base_other, int max_lx,
+           int max_other, float *buffer) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int o = blockIdx.y;
+  if (x >= max_lx || o >= max_other) return;
+  long long gi;
+  if (dim == 2) {
+    gi = (long long)(base_gx + x) + P.sy * base_other;
+  } else {
+    const int lim[3] = {P.nx, P.ny, P.nz};
+    const int axis = face >> 1, hi = face & 1, n = lim[axis];
+    const int layer = DISTRIBUTE ? (hi ? n - 1 : 0) : (hi ? n - 2 : 1);
+    const int c1 = axis == 1 ? layer : base_other + o, c2 = axis == 1 ? base_other + o : layer;
+    gi = (long long)(base_gx + x) + P.sy * c1 + P.sz * c2;
+  }
+  const long long bi = (long long)o * max_lx + x;
+  if (DISTRIBUTE) field[gi] = buffer[bi]; else buffer[bi] = field[gi];
+}
+
 // ----------------------------------------------------------------------------------------
 // Output fast path: the device side of _fields_to_host + mask_nonfluid_nodes
 // (subdomain_runner.py:1141-1151, io.py:53-59).  Packs the real (non-ghost, non-padding) nodes

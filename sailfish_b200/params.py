@@ -87,6 +87,8 @@ def make_params(lattice, model, access_pattern, lat_size, arr_size, periodic,
     class name -> remapped id."""
     p = SlfParams()
     p.struct_bytes = ctypes.sizeof(SlfParams)
+    if lattice not in LATTICE_IDS:
+        raise UnsupportedConfiguration('lattice %s (supported: %s)' % (lattice, ', '.join(sorted(LATTICE_IDS))))
     p.lattice = LATTICE_IDS[lattice]
     p.model = MODEL_IDS[model]
     p.access_pattern = ACCESS_IDS[access_pattern]

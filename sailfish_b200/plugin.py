@@ -15,13 +15,16 @@ What install() does:
   3. replaces ``BlockCodeGenerator.get_code`` (codegen.py:104-180), which would render the Mako
      templates into CUDA source, by a function that returns the *context* dictionary the templates
      would have received (codegen.py:195-204); ``B200Backend.build`` turns it into a plan.
+With ``default=True`` the backend is also tried first whatever ``--backends`` says (the reference's
+default is 'cuda,opencl', and its option parser only asks *those* backends for their flags,
+controller.py:452-455): scripts and regtests that never mention a backend then run on it unchanged.
 Nothing in the reference tree is modified.
 """
 import sys
 import types
 
 
-def install(reference_root=None):
+def install(reference_root=None, default=False):
     from sailfish_b200 import compat
     compat.install(reference_root)
     import sailfish  # noqa: F401  (the reference)
@@ -39,4 +42,16 @@ def install(reference_root=None):
         return ctx
 
     codegen.BlockCodeGenerator.get_code = get_code
+
+    if default:
+        from sailfish import util
+        if not getattr(util.get_backends, '_b200_first', False):
+            stock = util.get_backends
+
+            def get_backends(backends=('cuda', 'opencl')):
+                names = ['b200'] + [b for b in backends if b != 'b200']
+                return stock(names)
+
+            get_backends._b200_first = True
+            util.get_backends = get_backends
     return mod

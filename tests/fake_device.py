@@ -136,6 +136,50 @@ class FakeLib(object):
         orc.apply_pbc(p, self._arr(dist, np.float32, p.dist_size * p.Q), int(axis), bool(swap))
         self.launches += 1
 
+    # -- ghost-layer pack / unpack (the reference's own halo path in plugin mode) ---------------------
+    def _xfer(self, fn, plan, dist, face, base_gx, base_other, max_lx, max_other, buf, swap):
+        p = self._p(plan)
+        nd = {3: 1, 5: 3, 9: 3, 19: 5, 27: 9}[p.Q]
+        d = self._arr(dist, np.float32, p.dist_size * p.Q)
+        b = self._arr(buf, np.float32, nd * int(max_lx) * int(max_other))
+        fn(p, d, int(face), int(base_gx), int(base_other), int(max_lx), int(max_other), b, bool(swap))
+        self.launches += 1
+
+    def _slf_collect_continuous_data(self, plan, dist, face, base_gx, base_other, max_lx, max_other, buf, swap, stream):
+        self._xfer(orc.collect, plan, dist, face, base_gx, base_other, max_lx, max_other, buf, swap)
+
+    def _slf_distribute_continuous_data(self, plan, dist, face, base_gx, base_other, max_lx, max_other, buf, swap,
+                                        stream):
+        self._xfer(orc.distribute, plan, dist, face, base_gx, base_other, max_lx, max_other, buf, swap)
+
+    def _slf_collect_sparse_data(self, plan, idx, dist, buf, max_idx, stream):
+        p = self._p(plan)
+        n = int(max_idx)
+        i = self._arr(idx, np.uint32, n)
+        self._arr(buf, np.float32, n)[:] = self._arr(dist, np.float32, p.dist_size * p.Q)[i]
+        self.launches += 1
+
+    def _slf_distribute_sparse_data(self, plan, idx, dist, buf, max_idx, stream):
+        p = self._p(plan)
+        n = int(max_idx)
+        i = self._arr(idx, np.uint32, n)
+        self._arr(dist, np.float32, p.dist_size * p.Q)[i] = self._arr(buf, np.float32, n)
+        self.launches += 1
+
+    def _xfer_macro(self, fn, plan, field, face, base_gx, base_other, max_lx, max_other, buf):
+        p = self._p(plan)
+        mo = 1 if p.dim == 2 else int(max_other)
+        fn(p, self._arr(field, np.float32, p.dist_size), int(face), int(base_gx), int(base_other), int(max_lx), mo,
+           self._arr(buf, np.float32, int(max_lx) * mo))
+        self.launches += 1
+
+    def _slf_collect_continuous_macro_data(self, plan, field, face, base_gx, base_other, max_lx, max_other, buf, stream):
+        self._xfer_macro(orc.collect_macro, plan, field, face, base_gx, base_other, max_lx, max_other, buf)
+
+    def _slf_distribute_continuous_macro_data(self, plan, field, face, base_gx, base_other, max_lx, max_other, buf,
+                                              stream):
+        self._xfer_macro(orc.distribute_macro, plan, field, face, base_gx, base_other, max_lx, max_other, buf)
+
     # -- binary Shan-Chen ------------------------------------------------------------------------
     def _v(self, p, vx, vy, vz):
         f, n = np.float32, p.dist_size

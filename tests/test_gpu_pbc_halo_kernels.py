@@ -77,6 +77,57 @@ def test_collect_distribute_bit_exact(oracle, case, swap):
         assert np.array_equal(g, o.reshape(shape)), face
 
 
+@pytest.mark.parametrize('case', ['ldc2d_bgk_AA', 'ldc3d_bgk_AA'])
+def test_macro_collect_distribute_bit_exact(oracle, case):
+    """Collect/DistributeContinuousMacroData on a scalar field (the rho field of the lattice object)."""
+    c, p, dev = _dev(case)
+    rng = np.random.RandomState(13)
+    shape = c['map'].shape
+    lat = [int(x) for x in c['lat']]
+    f0 = rng.rand(*shape).astype(np.float32)
+
+    def put(a):
+        dev.lib.call('slf_memcpy_h2d', int(dev.d_rho), a.ctypes.data_as(ctypes.c_void_p), a.nbytes)
+
+    def get():
+        out = np.zeros(shape, np.float32)
+        dev.sync()
+        dev.lib.call('slf_memcpy_d2h', out.ctypes.data_as(ctypes.c_void_p), int(dev.d_rho), out.nbytes)
+        return out
+
+    faces = [None] if p.dim == 2 else [2, 3, 4, 5]
+    for face in faces:
+        max_lx = lat[0] - 3
+        if p.dim == 2:
+            rows = [(1, 1), (lat[1] - 2, 1), (0, 1)]          # (gy, max_other)
+        else:
+            rows = [(1, (lat[2] if face // 2 == 1 else lat[1]) - 3)]
+        for base_other, max_other in rows:
+            nbuf = max_lx * max_other
+            dbuf = dev.be.alloc_buf(size=nbuf * 4)
+            put(f0)
+            dev.lib.call('slf_collect_continuous_macro_data', dev.plan, int(dev.d_rho), face or 0, 2, base_other, max_lx,
+                         max_other, int(dbuf), dev.stream.handle)
+            dev.sync()
+            gbuf = np.zeros(nbuf, np.float32)
+            dev.lib.call('slf_memcpy_d2h', gbuf.ctypes.data_as(ctypes.c_void_p), int(dbuf), nbuf * 4)
+            obuf = np.zeros(nbuf, np.float32)
+            oracle.collect_macro(p, f0.reshape(-1), face or 0, 2, base_other, max_lx, max_other, obuf)
+            assert np.array_equal(gbuf, obuf), (face, base_other)
+            src = rng.rand(nbuf).astype(np.float32)
+            dev.lib.call('slf_memcpy_h2d', int(dbuf), src.ctypes.data_as(ctypes.c_void_p), nbuf * 4)
+            dev.lib.call('slf_distribute_continuous_macro_data', dev.plan, int(dev.d_rho), face or 0, 2, base_other,
+                         max_lx, max_other, int(dbuf), dev.stream.handle)
+            o = f0.copy().reshape(-1)
+            oracle.distribute_macro(p, o, face or 0, 2, base_other, max_lx, max_other, src)
+            assert np.array_equal(get(), o.reshape(shape)), (face, base_other)
+    # out-of-range requests are refused, not clipped
+    from sailfish_b200.backend_b200 import B200Error
+    with pytest.raises(B200Error):
+        dev.lib.call('slf_collect_continuous_macro_data', dev.plan, int(dev.d_rho), 2, 2, 1, lat[0], 1, int(dbuf),
+                     dev.stream.handle)
+
+
 @pytest.mark.parametrize('case', ['ldc2d_bgk_AA', 'ldc3d_bgk_AA', 'ldc3d_q27_AA'])
 @pytest.mark.parametrize('swap', [0, 1])
 def test_halo_push_matches_host_statement(case, swap):
