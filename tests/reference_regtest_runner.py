@@ -1,5 +1,5 @@
 """Runs one of the reference's own regression tests (regtest/subdomains/*.py), UNCHANGED, on the b200
-backend:  python tests/reference_regtest_runner.py <reference root> <module> <AB|AA> [max_iters]
+backend:  python tests/reference_regtest_runner.py <reference root> <module | path/in/reference.py> <AB|AA> [max_iters]
 
 The reference's multi-process machinery (LBMachineMaster, one process per subdomain, ZeroMQ connectors,
 collect/distribute kernels, sparse index exchange for x faces, edges and corners) runs as is;
@@ -31,7 +31,8 @@ def main():
     orc.build()
     fake_device.install_fake()
 
-    spec = importlib.util.spec_from_file_location('regtest_mod', os.path.join(ref_root, 'regtest', 'subdomains', name + '.py'))
+    path = os.path.join(ref_root, name) if name.endswith('.py') else os.path.join(ref_root, 'regtest', 'subdomains', name + '.py')
+    spec = importlib.util.spec_from_file_location('regtest_mod', path)
     mod = importlib.util.module_from_spec(spec)
     sys.modules['regtest_mod'] = mod
     spec.loader.exec_module(mod)

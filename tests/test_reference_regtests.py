@@ -4,7 +4,8 @@ items 3 and 4), run UNCHANGED on the b200 backend through sailfish_b200.plugin:
 * 2d_/3d_propagation.py -- literal known-answer vectors for streaming across subdomain faces, edges and
   corners, periodic and partially periodic boxes, misaligned blocks, AA with 2 and 4 subdomains;
 * 2d_/3d_ldc.py (3 / 4 / 8 blocks), 2d_cylinder.py -- decomposition invariance to 6 decimals;
-* 2d_binary.py -- the Shan-Chen mixture on 2 and 4 blocks (macro-field halo kernels).
+* 2d_binary.py -- the Shan-Chen mixture on 2 and 4 blocks (macro-field halo kernels);
+* tests/gpu/do_nothing_node.py -- AA == AB with the do-nothing outflow node.
 
 The whole reference stack runs as is (controller, machine master, one OS process per subdomain, ZeroMQ
 connectors, Collect/Distribute{Continuous,Sparse}[Macro]Data[WithSwap] through the C entry points'
@@ -31,6 +32,7 @@ RUNS = {
     '2d_ldc': ('AA', 100),
     '2d_cylinder': ('AB', 100),
     '2d_binary': ('AB', 100),
+    'tests/gpu/do_nothing_node.py': ('AB', None),     # AA == AB with the do-nothing outflow node, 1000 steps
 }
 if os.environ.get('SLF_ALL_REGTESTS'):
     RUNS.update({'3d_sphere': ('AB', 100), 'binary_pbc': ('AB', 100), '3d_ldc_ab': ('AB', 100), '2d_ldc_ab': ('AB', 100)})
