@@ -13,7 +13,6 @@ import inspect
 import numpy as np
 from scipy.ndimage import convolve
 
-from sailfish_b200 import lattice as lat
 from sailfish_b200 import node_type as nt
 
 

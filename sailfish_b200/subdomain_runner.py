@@ -11,14 +11,11 @@ and the same per-step order (boundary slabs -> halo -> bulk -> PBC), but
     device-side semaphores -- the host never touches halo data.
 """
 import ctypes
-import os
-import time
 
 import numpy as np
 
 from sailfish_b200 import backend_b200 as bk
 from sailfish_b200 import params as P
-from sailfish_b200.subdomain import SubdomainSpec
 
 
 def checkpoint_filename(base, digits, subdomain_id, it):

@@ -7,7 +7,6 @@ import ctypes
 import numpy as np
 
 from oracle import oracle as orc
-from sailfish_b200 import params as P
 
 
 class FakeLib(object):

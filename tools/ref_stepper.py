@@ -416,7 +416,6 @@ class RefShanChenStepper(object):
     NNSubdomainRunner.step (subdomain_runner.py:2102-2197).  fp64, all-wet or FullBB geometries."""
 
     def __init__(self, runner, ctx):
-        from functools import partial
         self.base = RefStepper.__new__(RefStepper)
         b = self.base
         # reuse geometry decoding of RefStepper
