@@ -153,7 +153,10 @@ def run_reference_arm(args):
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * per_step_budget, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'ldc_3d D3Q19 BGK AA, CPU arm on a bounded %d^3 sample of the 512^3/GPU workload' % size,
+        'config': {'workload': 'examples/ldc_3d D3Q19 BGK, AA access pattern, %d^3 per GPU (global %dx%dx%d, z-split)'
+                               % (args.size, args.size, args.size, args.size * args.gpus),
+                   'visc': 0.03175,
+                   'sample': 'each step = a bounded %d^3 run of the same cavity on the host cores' % size,
                    'note': 'reference has no CPU path (backend_dummy is a no-op) and its GPU path needs Mako+pycuda; '
                            'this is the CPU restatement of its kernels (oracle/), all host threads'},
         'cpu_baseline': {'value': value, 'unit': 'MLUPS', 'cores': cores, 'kind': 'port', 'sample': sample},
