@@ -90,6 +90,8 @@ def make_params(lattice, model, access_pattern, lat_size, arr_size, periodic,
     if lattice not in LATTICE_IDS:
         raise UnsupportedConfiguration('lattice %s (supported: %s)' % (lattice, ', '.join(sorted(LATTICE_IDS))))
     p.lattice = LATTICE_IDS[lattice]
+    if model not in MODEL_IDS:
+        raise UnsupportedConfiguration('relaxation model %s (supported: %s)' % (model, ', '.join(sorted(MODEL_IDS))))
     p.model = MODEL_IDS[model]
     p.access_pattern = ACCESS_IDS[access_pattern]
     p.lat_nx, p.lat_ny, p.lat_nz = [int(x) for x in lat_size]
