@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SLF_ABI_VERSION 2
+#define SLF_ABI_VERSION 3
 
 /* error codes (negative; positive values are cudaError_t) */
 #define SLF_EINVAL      (-1)   /* bad argument / unsupported configuration          */
@@ -113,6 +113,10 @@ typedef struct SlfParams {
   double   sc_g[4];             /* G11, G12, G21, G22  (constants(), lb_binary.py:387-393) */
   int32_t  sc_potential;        /* SLF_SC_LINEAR | SLF_SC_CLASSIC (sym.py:896-908)       */
   int32_t  reserved1;
+  /* binary models: `accel` above acts on the first component, accel1 on the second
+   * (add_body_force(..., grid=1), lb_base.py:331-370; relaxation_common.mako:24-33: the body
+   * acceleration is added to the Shan-Chen acceleration of that component) */
+  double   accel1[3];
 } SlfParams;
 
 typedef struct SlfPlan SlfPlan;

@@ -1005,6 +1005,10 @@ int orc_sc_collide_and_propagate(const SlfParams *P, int grid_idx, const uint32_
           for (int d = 0; d < D; d++) a[d] += force[d] * (-psi0 * G[k]);
         }
         for (int d = 0; d < D; d++) a[d] /= gm;
+        /* body_force(), relaxation_common.mako:24-33: the constant acceleration of this component is
+         * added to the Shan-Chen one */
+        for (int d = 0; d < D; d++)
+          a[d] += grid_idx == 0 ? (P->force_enabled ? (REAL)P->accel[d] : (REAL)0) : (REAL)P->accel1[d];
       }
       REAL f[MAXQ], v[3] = {0, 0, 0};
       for (int i = 0; i < Q; i++) f[i] = odd ? din[gi - off[i] + C->DS * L->opp[i]] : din[gi + C->DS * i];

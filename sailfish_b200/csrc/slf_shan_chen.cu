@@ -19,6 +19,10 @@ static ScParams make_sc(const SlfPlan *pl) {
   S.tau[0] = tauf; S.tau[1] = tphi;
   for (int k = 0; k < 4; k++) S.g[k] = (float)pl->hp.sc_g[k];
   S.potential = pl->hp.sc_potential;
+  for (int d = 0; d < 3; d++) {
+    S.body[0][d] = pl->hp.force_enabled ? (float)pl->hp.accel[d] : 0.f;
+    S.body[1][d] = (float)pl->hp.accel1[d];
+  }
   return S;
 }
 

@@ -20,6 +20,7 @@ struct ScParams {
   float tau[2];
   float g[4];                 // G11, G12, G21, G22
   int potential;
+  float body[2][3];           // constant body acceleration of each component (add_body_force(grid=k))
 };
 
 __device__ __forceinline__ float sc_ppot(int pot, float x) {
@@ -158,7 +159,7 @@ sc_collide(const DevParams P, const ScParams S, const uint32_t *__restrict__ map
     sc_add_force(S.potential, gm, G, grad, a);
   }
   const float ig = 1.0f / gm;
-  a[0] *= ig; a[1] *= ig; a[2] *= ig;
+  a[0] = fmaf(a[0], ig, S.body[GRID][0]); a[1] = fmaf(a[1], ig, S.body[GRID][1]); a[2] = fmaf(a[2], ig, S.body[GRID][2]);
   const float v[3] = {ovx[gi], ovy[gi], L::D == 3 ? ovz[gi] : 0.f};
   if (P.relax) sc_relax<L>(f, gm, a, v, S.omega[GRID], S.tau[GRID]);
   sc_store<L, MODE>(P, dout, gi, f);
@@ -244,7 +245,7 @@ sc_collide_fused(const DevParams P, const ScParams S, const ScTables<L> T, const
     if (S.g[0] != 0.0f) sc_add_force(S.potential, g0, S.g[0], grad0, a);
     if (S.g[1] != 0.0f) sc_add_force(S.potential, g0, S.g[1], grad1, a);
     const float ig = 1.0f / g0;
-    a[0] *= ig; a[1] *= ig; a[2] *= ig;
+    a[0] = fmaf(a[0], ig, S.body[0][0]); a[1] = fmaf(a[1], ig, S.body[0][1]); a[2] = fmaf(a[2], ig, S.body[0][2]);
     if (P.relax) sc_relax<L>(f0, g0, a, v, S.omega[0], S.tau[0]);
 #pragma unroll
     for (int i = 0; i < L::Q; i++) T.st1[i][t] = f0[i];
@@ -254,7 +255,7 @@ sc_collide_fused(const DevParams P, const ScParams S, const ScTables<L> T, const
     if (S.g[2] != 0.0f) sc_add_force(S.potential, g1, S.g[2], grad0, a);
     if (S.g[3] != 0.0f) sc_add_force(S.potential, g1, S.g[3], grad1, a);
     const float ig = 1.0f / g1;
-    a[0] *= ig; a[1] *= ig; a[2] *= ig;
+    a[0] = fmaf(a[0], ig, S.body[1][0]); a[1] = fmaf(a[1], ig, S.body[1][1]); a[2] = fmaf(a[2], ig, S.body[1][2]);
     if (P.relax) sc_relax<L>(f1, g1, a, v, S.omega[1], S.tau[1]);
 #pragma unroll
     for (int i = 0; i < L::Q; i++) T.st2[i][t] = f1[i];

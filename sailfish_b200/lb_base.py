@@ -91,8 +91,8 @@ class LBSim(object):
 
 
 class LBForcedSim(LBSim):
-    """Body forces (lb_base.py:305-394).  Only constant accelerations on grid 0 with the Guo
-    scheme are on the hot path (force-driven Poiseuille)."""
+    """Body forces (lb_base.py:305-394).  Constant accelerations with the Guo scheme are on the hot path: on the
+    single lattice (force-driven Poiseuille) and on either component of a binary mixture."""
 
     def __init__(self, config):
         super(LBForcedSim, self).__init__(config)
@@ -105,13 +105,15 @@ class LBForcedSim(LBSim):
     def add_body_force(self, force, grid=0, accel=True):
         dim = self.grid.dim
         assert len(force) == dim
-        if grid != 0 or not accel:
-            raise ValueError('B200 hot path: constant accelerations on grid 0 only')
-        cur = self._forces.setdefault(0, np.zeros(dim, np.float64))
-        self._forces[0] = cur + np.float64(force)
+        if not accel:
+            raise ValueError('B200 hot path: acceleration-type body forces only (accel=True)')
+        if grid < 0 or grid >= len(self.grids):
+            raise ValueError('no lattice %d in this model' % grid)
+        cur = self._forces.setdefault(grid, np.zeros(dim, np.float64))
+        self._forces[grid] = cur + np.float64(force)
 
-    def body_acceleration(self):
-        if 0 not in self._forces:
+    def body_acceleration(self, grid=0):
+        if grid not in self._forces:
             return None
-        a = self._forces[0]
+        a = self._forces[grid]
         return [float(x) for x in a] + [0.0] * (3 - len(a))

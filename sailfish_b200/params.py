@@ -57,6 +57,7 @@ class SlfParams(ctypes.Structure):
         ('sc_g', ctypes.c_double * 4),
         ('sc_potential', ctypes.c_int32),
         ('reserved1', ctypes.c_int32),
+        ('accel1', ctypes.c_double * 3),
     ]
 
     # keeps the node_params array alive
@@ -122,6 +123,8 @@ def make_params(lattice, model, access_pattern, lat_size, arr_size, periodic,
         p.tau_phi = float(shan_chen.get('tau_phi', 1.0))
         for i, k in enumerate(('G11', 'G12', 'G21', 'G22')):
             p.sc_g[i] = float(shan_chen.get(k, 0.0))
+        for i, a in enumerate(shan_chen.get('accel1') or ()):
+            p.accel1[i] = float(a)
         p.sc_potential = SC_POTENTIAL_IDS[shan_chen.get('potential', 'linear')]
     return p
 
@@ -155,7 +158,7 @@ def from_context(ctx):
     type_ids = {}
     for nt_class in ctx['node_types']:
         type_ids[nt_class.__name__] = int(remap[nt_class.id])
-    accel = None
+    accel = accel1 = None
     forces = ctx.get('forces')
     if forces is not None and not isinstance(forces, type(NotImplemented)):
         numeric = getattr(forces, 'numeric', None) or {}
@@ -163,11 +166,16 @@ def from_context(ctx):
         if symbolic:
             raise UnsupportedConfiguration('symbolic body forces are out of scope')
         if numeric:
-            if set(numeric.keys()) != {0} or set(numeric[0].keys()) != {True}:
-                raise UnsupportedConfiguration('only acceleration-type body forces on grid 0')
+            grids_ok = {0, 1} if simtype == 'shan-chen' else {0}
+            if not set(numeric.keys()) <= grids_ok or any(set(v.keys()) != {True} for v in numeric.values()):
+                raise UnsupportedConfiguration('only acceleration-type body forces (on grid 0; on both components '
+                                               'of the binary Shan-Chen model)')
             if ctx.get('force_implementation', 'guo') != 'guo':
                 raise UnsupportedConfiguration('only --force_implementation=guo')
-            accel = [float(a) for a in numeric[0][True]] + [0.0] * (3 - len(numeric[0][True]))
+            if 0 in numeric:
+                accel = [float(a) for a in numeric[0][True]] + [0.0] * (3 - len(numeric[0][True]))
+            if 1 in numeric:
+                accel1 = [float(a) for a in numeric[1][True]] + [0.0] * (3 - len(numeric[1][True]))
     shan_chen = None
     if simtype == 'shan-chen':
         if len(ctx.get('grids', [])) != 2:
@@ -175,7 +183,7 @@ def from_context(ctx):
         consts = ctx.get('constants', {})
         shan_chen = dict(tau_phi=ctx['tau_phi'], potential=ctx.get('sc_potential', 'linear'),
                          G11=consts.get('G11', 0.0), G12=consts.get('G12', 0.0),
-                         G21=consts.get('G21', 0.0), G22=consts.get('G22', 0.0))
+                         G21=consts.get('G21', 0.0), G22=consts.get('G22', 0.0), accel1=accel1)
     elif ctx.get('force_couplings'):
         raise UnsupportedConfiguration('force couplings without the Shan-Chen model')
     dim = 2 if name == 'D2Q9' else 3

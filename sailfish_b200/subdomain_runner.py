@@ -480,8 +480,10 @@ class NNSubdomainRunner(SubdomainRunner):
                                              % sorted(unsupported))
         return P.make_params(
             g.name, 'bgk', cfg.access_pattern, lat, arr, per, sd.bits, sd.type_ids_by_name(),
-            sd.node_params, cfg.visc, None, use_link_tags=getattr(cfg, 'use_link_tags', True),
+            sd.node_params, cfg.visc, self._sim.body_acceleration(0),
+            use_link_tags=getattr(cfg, 'use_link_tags', True),
             shan_chen=dict(tau_phi=cfg.tau_phi, G11=cfg.G11, G12=cfg.G12, G21=cfg.G12, G22=cfg.G22,
+                           accel1=self._sim.body_acceleration(1),
                            potential=cfg.sc_potential))
 
     def _init_compute(self):

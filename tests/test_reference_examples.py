@@ -15,14 +15,14 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'examples'))
 
 RUNS = ['cylinder', 'duct_flow', 'external_geometry', 'fs_gaussian', 'ldc_2d', 'ldc_3d', 'poiseuille', 'sphere_3d',
         'taylor_green_2d', 'binary_fluid/sc_capillary_wave_2d', 'binary_fluid/sc_laplace_2d',
-        'binary_fluid/sc_separation_2d', 'binary_fluid/sc_separation_3d', 'binary_fluid/sc_separation_3d_walls']
+        'binary_fluid/sc_separation_2d', 'binary_fluid/sc_separation_3d', 'binary_fluid/sc_separation_3d_walls',
+        'binary_fluid/sc_capillary', 'binary_fluid/sc_rayleigh_taylor_2d']
 # example -> fragment of the refusal message
 REFUSED = {
     'binary_fluid/binary_microchannel': 'free-energy', 'binary_fluid/fe_capillary_wave_2d': 'free-energy',
     'binary_fluid/fe_poiseuille_2d': 'free-energy', 'binary_fluid/fe_separation_2d': 'free-energy',
     'binary_fluid/fe_separation_3d': 'free-energy', 'binary_fluid/fe_viscous_fingering': 'free-energy',
-    'binary_fluid/sc_capillary': 'body forces', 'binary_fluid/sc_poiseuille_2d': 'body forces',
-    'binary_fluid/sc_rayleigh_taylor_2d': 'body forces', 'four_rolls_mill': 'symbolic body forces',
+    'binary_fluid/sc_poiseuille_2d': 'force_implementation=guo', 'four_rolls_mill': 'symbolic body forces',
     'ldc_2d_entropic': 'relaxation model elbm', 'poiseuille_3d': 'lattice D3Q13',     # its default grid
     'poiseuille_pulsatile': 'time/space dependent', 'sc_drop': 'single-component Shan-Chen',
     'sc_phase_separation': 'single-component Shan-Chen', 'turbulence/kida_vortex': 'minimize_roundoff',

@@ -23,7 +23,8 @@ def params_from_case(c, access_pattern=None):
     if 'simtype' in c.files and str(c['simtype']) == 'shan-chen':
         g = [float(x) for x in c['sc_g']]
         shan_chen = dict(tau_phi=float(c['tau_phi']), G11=g[0], G12=g[1], G21=g[2], G22=g[3],
-                         potential=str(c['sc_potential']))
+                         potential=str(c['sc_potential']),
+                         accel1=[float(a) for a in c['accel1']] if 'accel1' in c.files else None)
     return P.make_params(
         str(c['grid']), str(c['model']), access_pattern or str(c['access_pattern']),
         [int(x) for x in c['lat']], [int(x) for x in c['arr']], [int(x) for x in c['periodic']],
@@ -54,6 +55,6 @@ def rel_linf(a, b):
     return float(np.max(d) / scale) if scale > 0 else float(np.max(d))
 
 
-SC_CASES = ['sc3d', 'sc3d_walls', 'sc2d_classic']
+SC_CASES = ['sc3d', 'sc3d_walls', 'sc2d_classic', 'sc2d_gravity', 'sc3d_gravity']
 CASES = ['ldc2d_bgk', 'ldc2d_mrt', 'ldc3d_bgk', 'ldc3d_mrt', 'ldc3d_q27', 'poi3d_press_mrt',
          'poi3d_force_bgk', 'poi3d_force_mrt', 'box3d_bgk', 'box3d_q27', 'box2d_bgk']

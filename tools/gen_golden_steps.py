@@ -89,7 +89,7 @@ def pack_ctx(ctx):
     ids = [int(remap[c.id]) for c in sorted(ctx['node_types'], key=lambda c: c.__name__)]
     accel = np.zeros(3)
     forces = ctx.get('forces')
-    if forces is not None and getattr(forces, 'numeric', None):
+    if forces is not None and getattr(forces, 'numeric', None) and 0 in forces.numeric:
         a = forces.numeric[0][True]
         accel[:len(a)] = a
     dim = ctx['grid'].dim
@@ -171,12 +171,13 @@ def gen_split_geometry():
 
 
 
-def gen_shan_chen():
+def gen_shan_chen(only=None):
     """Binary Shan-Chen goldens (BASELINE config 5, examples/binary_fluid/sc_separation_3d.py)."""
     from ref_stepper import RefShanChenStepper
     ex3 = ref_harness.load_example('examples/binary_fluid/sc_separation_3d.py')
     from sailfish.subdomain import Subdomain3D, Subdomain2D
     from sailfish.lb_binary import LBBinaryFluidShanChen
+    from sailfish.lb_base import LBForcedSim
     from sailfish.node_type import NTFullBBWall
     from sailfish.geo import LBGeometry3D, LBGeometry2D
 
@@ -212,8 +213,40 @@ def gen_shan_chen():
             defaults.update({'lat_nx': 14, 'lat_ny': 12, 'grid': 'D2Q9', 'G12': 1.1, 'visc': 1.0 / 6.0,
                              'periodic_x': True, 'periodic_y': True, 'sc_potential': 'classic'})
 
+    class GravityDomain2D(Subdomain2D):
+        def initial_conditions(self, sim, hx, hy):
+            sim.rho[:] = 1.0 + 0.02 * np.sin(2 * np.pi * hx / self.gx) * np.cos(np.pi * hy / self.gy)
+            sim.phi[:] = 1.0 - 0.02 * np.sin(2 * np.pi * hx / self.gx) * np.cos(np.pi * hy / self.gy)
+
+        def boundary_conditions(self, hx, hy):
+            self.set_node((hy == 0) | (hy == self.gy - 1), NTFullBBWall)
+
+    class GravitySim2D(LBBinaryFluidShanChen, LBForcedSim):
+        """Both components pushed along x between two walls (examples/binary_fluid/sc_poiseuille_2d.py)."""
+        subdomain = GravityDomain2D
+
+        @classmethod
+        def update_defaults(cls, defaults):
+            defaults.update({'lat_nx': 16, 'lat_ny': 12, 'grid': 'D2Q9', 'G12': 0.9, 'visc': 0.12, 'tau_phi': 0.8,
+                             'periodic_x': True})
+
+        def __init__(self, config):
+            super(GravitySim2D, self).__init__(config)
+            self.add_body_force((1e-4, 0.0), grid=0)
+            self.add_body_force((2e-4, -5e-5), grid=1)
+
+    class GravitySim3D(WalledSim, LBForcedSim):
+        """Only the second component feels the force (examples/binary_fluid/sc_rayleigh_taylor_2d.py)."""
+        def __init__(self, config):
+            super(GravitySim3D, self).__init__(config)
+            self.add_body_force((1e-4, 0.0, -2e-4), grid=1)
+
     cases = []
     for ap in ('AB', 'AA'):
+        if only and 'gravity' in only:
+            cases.append(('sc2d_gravity_' + ap, GravitySim2D, LBGeometry2D, ['--seed=1234', '--access_pattern=' + ap], 12))
+            cases.append(('sc3d_gravity_' + ap, GravitySim3D, LBGeometry3D, ['--seed=1234', '--access_pattern=' + ap], 12))
+            continue
         cases.append(('sc3d_' + ap, ex3.SeparationSCSim, LBGeometry3D,
                       ['--lat_nx=12', '--lat_ny=10', '--lat_nz=9', '--seed=1234', '--access_pattern=' + ap], 12))
         cases.append(('sc3d_walls_' + ap, WalledSim, LBGeometry3D, ['--seed=1234', '--access_pattern=' + ap], 12))
@@ -228,6 +261,11 @@ def gen_shan_chen():
         c = ctx['constants']
         out['sc_g'] = np.array([c['G11'], c['G12'], c['G21'], c['G22']], dtype=np.float64)
         out['sc_potential'] = ctx['sc_potential']
+        a1 = np.zeros(3)
+        fr = ctx.get('forces')
+        if fr is not None and getattr(fr, 'numeric', None) and 1 in fr.numeric:
+            a1[:len(fr.numeric[1][True])] = fr.numeric[1][True]
+        out['accel1'] = a1
         out['map'] = r._subdomain.encoded_map().astype(np.uint32)
         sim = r._sim
         rho0 = r.field_base(sim.rho).astype(np.float64)
@@ -258,3 +296,5 @@ if __name__ == '__main__':
         gen_split_geometry()
     if 'sc' in what:
         gen_shan_chen()
+    if 'sc_gravity' in what:
+        gen_shan_chen(only='gravity')

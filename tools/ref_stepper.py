@@ -529,6 +529,11 @@ class RefShanChenStepper(object):
                 acc += force * (-self.ppot(gm) * Gc)
             with np.errstate(all='ignore'):
                 acc = np.where(wet, acc / gm, 0.0)
+            # body_force(), relaxation_common.mako:24-33: ea<grid>[j] += body_force_accel(grid, j, forces)
+            forces = self.ctx.get('forces')
+            if forces is not None and getattr(forces, 'numeric', None) and gidx in forces.numeric:
+                for d in range(D):
+                    acc[d] += np.where(wet, float(sym_force.body_force_accel(gidx, d, forces, accel=True)), 0.0)
             f = self._load(din, idx, odd)
             v = np.array([self.v[d][idx] for d in range(D)])
             if wall.any():
