@@ -1,102 +1,105 @@
 #!/usr/bin/env python
-"""3D Poiseuille flow in a pipe: user code of the reference's examples/poiseuille_3d.py:14-200
-(BASELINE config 3): full-way bounce-back pipe wall, equilibrium-density inlet/outlet
-(--drive=pressure) or Guo body force with a periodic axis (--drive=force)."""
+"""Poiseuille flow through a circular pipe (BASELINE config 3; same set-up as the reference's
+examples/poiseuille_3d.py): full-way bounce-back pipe wall; the flow is driven either by a density
+difference between equilibrium-density inlet and outlet planes (--drive=pressure) or by a Guo body
+force with the pipe axis periodic (--drive=force)."""
 import numpy as np
 
-from sailfish_b200.geo import EqualSubdomainsGeometry3D
-from sailfish_b200.subdomain import Subdomain3D
-from sailfish_b200.node_type import NTFullBBWall, NTEquilibriumDensity
 from sailfish_b200.controller import LBSimulationController
-from sailfish_b200.lb_single import LBFluidSim
+from sailfish_b200.geo import EqualSubdomainsGeometry3D
 from sailfish_b200.lb_base import LBForcedSim
+from sailfish_b200.lb_single import LBFluidSim
+from sailfish_b200.node_type import NTEquilibriumDensity, NTFullBBWall
+from sailfish_b200.subdomain import Subdomain3D
+
+AXES = 'xyz'
 
 
-class PoiseuilleSubdomain(Subdomain3D):
-    max_v = 0.02
+def _lat_sizes(config):
+    return dict(x=config.lat_nx, y=config.lat_ny, z=config.lat_nz)
+
+
+class Pipe(Subdomain3D):
+    max_v = 0.02                 # centre-line velocity of the analytic profile
     wall_bc = NTFullBBWall
 
-    @property
-    def channel_length(self):
-        return {'x': self.config.lat_nx, 'y': self.config.lat_ny, 'z': self.config.lat_nz}[
-            self.config.flow_direction] - 1
-
-    @property
-    def pressure_delta(self):
-        return (self.max_v * (16.0 * self.config.visc) * self.channel_length /
-                (self.channel_width(self.config) ** 2))
-
-    def _set_pressure_bc(self, hx, hy, hz, wall_map):
-        not_wall = np.logical_not(wall_map)
-        h, n = {'x': (hx, self.gx), 'y': (hy, self.gy), 'z': (hz, self.gz)}[self.config.flow_direction]
-        inlet_map = (h == 0) & not_wall
-        outlet_map = (h == n - 1) & not_wall
-        pressure = self.pressure_delta
-        self.set_node(inlet_map, NTEquilibriumDensity(1.0 + 3.0 * pressure / 2.0))
-        self.set_node(outlet_map, NTEquilibriumDensity(1.0 - 3.0 * pressure / 2.0))
-
-    def boundary_conditions(self, hx, hy, hz):
-        radiussq = (self.channel_width(self.config) / 2.0) ** 2
-        fd = self.config.flow_direction
-        if fd == 'z':
-            wall_map = (hx - (self.gx / 2 - 0.5)) ** 2 + (hy - (self.gy / 2 - 0.5)) ** 2 >= radiussq
-        elif fd == 'y':
-            wall_map = (hx - (self.gx / 2 - 0.5)) ** 2 + (hz - (self.gz / 2 - 0.5)) ** 2 >= radiussq
-        else:
-            wall_map = (hy - (self.gy / 2 - 0.5)) ** 2 + (hz - (self.gz / 2 - 0.5)) ** 2 >= radiussq
-        self.set_node(wall_map, self.wall_bc)
-        if self.config.drive == 'pressure':
-            self._set_pressure_bc(hx, hy, hz, wall_map)
-
-    def initial_conditions(self, sim, hx, hy, hz):
-        sim.rho[:] = 1.0
-        if not self.config.stationary:
-            return
-        if self.config.drive == 'pressure':
-            pressure = self.pressure_delta
-            h, n = {'x': (hx, self.gx), 'y': (hy, self.gy), 'z': (hz, self.gz)}[self.config.flow_direction]
-            sim.rho[:] = 1.0 + 3.0 * pressure * (n / 2.0 - h)
+    # -- analytic relations -------------------------------------------------------------------------
+    @classmethod
+    def width(cls, config):
+        """Edge of the square cross-section the pipe is inscribed in."""
+        sizes = _lat_sizes(config)
+        return min(sizes[a] for a in AXES if a != config.flow_direction)
 
     @classmethod
     def channel_width(cls, config):
+        """Hydraulic diameter: the wall sits `location` nodes inside the first / last wall node."""
         return cls.width(config) - 1 - 2 * cls.wall_bc.location
 
     @classmethod
-    def width(cls, config):
-        if config.flow_direction == 'x':
-            return min(config.lat_ny, config.lat_nz)
-        elif config.flow_direction == 'y':
-            return min(config.lat_nx, config.lat_nz)
-        return min(config.lat_nx, config.lat_ny)
+    def driving_gradient(cls, config):
+        """dp/dx (= body acceleration for rho = 1) of Hagen-Poiseuille flow with centre velocity max_v."""
+        return cls.max_v * (16.0 * config.visc) / cls.channel_width(config) ** 2
+
+    @property
+    def pressure_delta(self):
+        length = _lat_sizes(self.config)[self.config.flow_direction] - 1
+        # (same association of the products as the analytic expression in the reference example, so
+        #  that the imposed densities agree to the last bit)
+        return self.max_v * (16.0 * self.config.visc) * length / self.channel_width(self.config) ** 2
+
+    # -- geometry -----------------------------------------------------------------------------------
+    def _along(self, hx, hy, hz):
+        """Coordinate array and extent along the pipe axis."""
+        return dict(x=(hx, self.gx), y=(hy, self.gy), z=(hz, self.gz))[self.config.flow_direction]
+
+    def _outside_pipe(self, hx, hy, hz):
+        coords = dict(x=(hx, self.gx), y=(hy, self.gy), z=(hz, self.gz))
+        (a, na), (b, nb) = [coords[ax] for ax in AXES if ax != self.config.flow_direction]
+        radius_sq = (self.channel_width(self.config) / 2.0) ** 2
+        return (a - (na / 2 - 0.5)) ** 2 + (b - (nb / 2 - 0.5)) ** 2 >= radius_sq
+
+    def boundary_conditions(self, hx, hy, hz):
+        solid = self._outside_pipe(hx, hy, hz)
+        self.set_node(solid, self.wall_bc)
+        if self.config.drive != 'pressure':
+            return
+        h, n = self._along(hx, hy, hz)
+        open_section = np.logical_not(solid)
+        half = 3.0 * self.pressure_delta / 2.0
+        self.set_node((h == 0) & open_section, NTEquilibriumDensity(1.0 + half))
+        self.set_node((h == n - 1) & open_section, NTEquilibriumDensity(1.0 - half))
+
+    def initial_conditions(self, sim, hx, hy, hz):
+        sim.rho[:] = 1.0
+        if self.config.stationary and self.config.drive == 'pressure':
+            h, n = self._along(hx, hy, hz)                 # start from the linear pressure drop
+            sim.rho[:] = 1.0 + 3.0 * self.pressure_delta * (n / 2.0 - h)
 
 
 class PoiseuilleSim(LBFluidSim, LBForcedSim):
-    subdomain = PoiseuilleSubdomain
+    subdomain = Pipe
 
     @classmethod
     def update_defaults(cls, defaults):
-        defaults.update({'lat_nx': 64, 'lat_ny': 64, 'lat_nz': 64, 'visc': 0.1, 'grid': 'D3Q19'})
+        defaults.update(dict(grid='D3Q19', lat_nx=64, lat_ny=64, lat_nz=64, visc=0.1))
 
     @classmethod
     def add_options(cls, group, dim):
-        group.add_argument('--flow_direction', type=str, default='x', choices=['x', 'y', 'z'])
+        group.add_argument('--flow_direction', choices=list(AXES), default='x', type=str)
+        group.add_argument('--drive', choices=['force', 'pressure'], default='force', type=str)
         group.add_argument('--stationary', action='store_true', default=False)
-        group.add_argument('--drive', type=str, default='force', choices=['force', 'pressure'])
 
     @classmethod
     def modify_config(cls, config):
-        if config.drive == 'force':
-            config.periodic_x = config.flow_direction == 'x'
-            config.periodic_y = config.flow_direction == 'y'
-            config.periodic_z = config.flow_direction == 'z'
+        if config.drive == 'force':        # the pipe closes on itself along its axis
+            for axis in AXES:
+                setattr(config, 'periodic_' + axis, axis == config.flow_direction)
 
     def __init__(self, config):
         super(PoiseuilleSim, self).__init__(config)
         if config.drive == 'force':
-            cw = self.subdomain.channel_width(config)
-            accel = self.subdomain.max_v * (16.0 * config.visc) / cw ** 2
-            self.add_body_force({'x': (accel, 0.0, 0.0), 'y': (0.0, accel, 0.0), 'z': (0.0, 0.0, accel)}[
-                config.flow_direction])
+            g = self.subdomain.driving_gradient(config)
+            self.add_body_force(tuple(g if axis == config.flow_direction else 0.0 for axis in AXES))
 
 
 if __name__ == '__main__':
