@@ -538,7 +538,7 @@ int orc_set_initial_conditions(const SlfParams *P, REAL *dist, const REAL *ivx, 
     const int z = (int)(row / C->ny), y = (int)(row % C->ny);
     for (int x = 0; x < C->nx; x++) {
       long long gi = x + C->stride[1] * y + C->stride[2] * z;
-      REAL v[3], feq[MAXQ]; v[0] = ivx[gi]; v[1] = ivy[gi]; v[2] = L->D == 3 ? ivz[gi] : (REAL)0;
+      REAL feq[MAXQ], v[3] = {ivx[gi], ivy[gi], L->D == 3 ? ivz[gi] : (REAL)0};
       feq_all(L, irho[gi], v, feq);
       for (int i = 0; i < L->Q; i++) dist[gi + C->DS * i] = feq[i];
     }
@@ -914,7 +914,7 @@ int orc_sc_set_initial_conditions(const SlfParams *P, const uint32_t *map, REAL 
       for (int i = 0; i < L->Q; i++) { d1[gi + C->DS * i] = (REAL)INFINITY; d2[gi + C->DS * i] = (REAL)INFINITY; }
       continue;
     }
-    REAL v[3], feq[MAXQ]; v[0] = ivx[gi]; v[1] = ivy[gi]; v[2] = L->D == 3 ? ivz[gi] : (REAL)0;
+    REAL feq[MAXQ], v[3] = {ivx[gi], ivy[gi], L->D == 3 ? ivz[gi] : (REAL)0};
     feq_all(L, irho[gi], v, feq);
     for (int i = 0; i < L->Q; i++) d1[gi + C->DS * i] = feq[i];
     feq_all(L, iphi[gi], v, feq);
