@@ -192,18 +192,26 @@ int slf_plan_create(const SlfParams *p, SlfPlan **out) {
   return 0;
 }
 
+static void purge_graphs(const SlfPlan *plan);
+
 int slf_plan_set_links(SlfPlan *plan, int link_low, int link_high) {
   if (!plan) return fail(SLF_EINVAL, "null plan");
+  purge_graphs(plan);
   plan->link_lo = link_low != 0; plan->link_hi = link_high != 0;
   return 0;
 }
 
-int slf_plan_destroy(SlfPlan *plan) {
-  if (!plan) return 0;
+// Step graphs capture kernel arguments by value (mask pointers, link flags): drop them whenever those change.
+static void purge_graphs(const SlfPlan *plan) {
   for (size_t k = 0; k < g_graphs.size();) {
     if (g_graphs[k].first == plan) { cudaGraphExecDestroy(g_graphs[k].second.exec); g_graphs.erase(g_graphs.begin() + k); }
     else k++;
   }
+}
+
+int slf_plan_destroy(SlfPlan *plan) {
+  if (!plan) return 0;
+  purge_graphs(plan);
   if (plan->d_node_params) cudaFree(plan->d_node_params);
   if (plan->d_fluid_mask) cudaFree(plan->d_fluid_mask);
   if (plan->d_wall_mask) cudaFree(plan->d_wall_mask);
@@ -220,6 +228,7 @@ int slf_plan_destroy(SlfPlan *plan) {
 // generic scanning kernels.
 int slf_plan_bind_map(SlfPlan *pl, uint64_t map) {
   if (!pl) return fail(SLF_EINVAL, "null plan");
+  purge_graphs(pl);
   const DevParams &d = pl->dp;
   if (d.DS >= (1ll << 32)) return fail(SLF_EUNSUPPORTED, "node lists use 32-bit indices");
   pl->bound_map = 0;
