@@ -631,7 +631,12 @@ static int pbc_corner_target(const Ctx *C, int axis, int opposite, const int *e,
   return 0;
 }
 
-int orc_apply_periodic_boundary_conditions(const SlfParams *P, REAL *dist, int axis, int with_swap) {
+/* link_lo / link_hi: this subdomain has a neighbour across the low / high face of the outermost (split) axis
+ * that delivers whole, PBC-completed planes (slf_halo_push): after in-place steps (with_swap) into the ghost
+ * layer, after streaming steps into the crossing slots of the first / last real layer.  Those cells belong to
+ * the neighbour and are left alone (same rule as apply_pbc in slf_kernels.cuh). */
+int orc_apply_periodic_boundary_conditions_linked(const SlfParams *P, REAL *dist, int axis, int with_swap,
+                                                  int link_lo, int link_hi) {
   Ctx Cs; int rc = ctx_init(&Cs, P); if (rc) return rc;
   const Ctx *C = &Cs; const Lat *L = C->L; const int D = L->D, Q = L->Q;
   if (axis < 0 || axis >= D) return D == 2 && axis == 2 ? 0 : SLF_EINVAL;
@@ -650,10 +655,15 @@ int orc_apply_periodic_boundary_conditions(const SlfParams *P, REAL *dist, int a
     cl[axis] = with_swap ? 1 : 0;
     ch[axis] = with_swap ? lim[axis] - 1 : lim[axis] - 2;
     const long long gi_low = gidx(C, cl), gi_high = gidx(C, ch);
+    const int so = D - 1;                                   /* split axis */
+    const int io = oth[0] == so ? i1 : ((D == 3 && oth[1] == so) ? i2 : -1), no = lim[so];
+    if (with_swap && io >= 0 && ((link_lo && io == 0) || (link_hi && io == no - 1))) continue;
+    const int skip_e = (with_swap || io < 0) ? 0 : ((link_lo && io == 1) ? 1 : ((link_hi && io == no - 2) ? -1 : 0));
     /* low -> high: populations with e[axis] == -1 */
     REAL val[MAXQ];
     for (int i = 1; i < Q; i++) if (L->e[i][axis] == -1) { int j = with_swap ? L->opp[i] : i; val[i] = dist[gi_low + C->DS * j]; }
     for (int i = 1; i < Q; i++) if (L->e[i][axis] == -1) {
+      if (skip_e != 0 && L->e[i][so] == skip_e) continue;
       const int j = with_swap ? L->opp[i] : i; const REAL fv = val[i];
       const int n2e = L->e[i][0]*L->e[i][0] + L->e[i][1]*L->e[i][1] + L->e[i][2]*L->e[i][2];
       if (!isfinite(fv)) continue;
@@ -672,6 +682,7 @@ int orc_apply_periodic_boundary_conditions(const SlfParams *P, REAL *dist, int a
     /* high -> low: populations with e[axis] == +1 */
     for (int i = 1; i < Q; i++) if (L->e[i][axis] == 1) { int j = with_swap ? L->opp[i] : i; val[i] = dist[gi_high + offset + C->DS * j]; }
     for (int i = 1; i < Q; i++) if (L->e[i][axis] == 1) {
+      if (skip_e != 0 && L->e[i][so] == skip_e) continue;
       const int j = with_swap ? L->opp[i] : i; const REAL fv = val[i];
       const int n2e = L->e[i][0]*L->e[i][0] + L->e[i][1]*L->e[i][1] + L->e[i][2]*L->e[i][2];
       if (!isfinite(fv)) continue;
@@ -689,6 +700,10 @@ int orc_apply_periodic_boundary_conditions(const SlfParams *P, REAL *dist, int a
     }
   }
   return 0;
+}
+
+int orc_apply_periodic_boundary_conditions(const SlfParams *P, REAL *dist, int axis, int with_swap) {
+  return orc_apply_periodic_boundary_conditions_linked(P, dist, axis, with_swap, 0, 0);
 }
 
 /* ------------------------------------------------------------------------------------
@@ -1039,7 +1054,8 @@ int orc_sc_collide_and_propagate(const SlfParams *P, int grid_idx, const uint32_
   return 0;
 }
 
-int orc_apply_macro_periodic_boundary_conditions(const SlfParams *P, REAL *field, int axis) {
+int orc_apply_macro_periodic_boundary_conditions_linked(const SlfParams *P, REAL *field, int axis, int link_lo,
+                                                        int link_hi) {
   Ctx Cs; int rc = ctx_init(&Cs, P); if (rc) return rc;
   const Ctx *C = &Cs; const int D = C->L->D;
   if (axis < 0 || axis >= D) return D == 2 && axis == 2 ? 0 : SLF_EINVAL;
@@ -1050,6 +1066,9 @@ int orc_apply_macro_periodic_boundary_conditions(const SlfParams *P, REAL *field
   for (int i2 = 0; i2 < n2; i2++) for (int i1 = 0; i1 < n1; i1++) {
     int c[3] = {0, 0, 0};
     c[o1] = i1; if (D == 3) c[o2] = i2;
+    /* ghost layers across a split face are delivered by the neighbour (slf_halo_push_field) */
+    const int so = D - 1, io = o1 == so ? i1 : ((D == 3 && o2 == so) ? i2 : -1);
+    if (axis != so && io >= 0 && ((link_lo && io == 0) || (link_hi && io == lim[so] - 1))) continue;
     long long g0, g1;
     c[axis] = 0; g0 = gidx(C, c); c[axis] = lim[axis] - 2; g1 = gidx(C, c);
     if (isfinite(field[g1])) field[g0] = field[g1];
@@ -1057,4 +1076,8 @@ int orc_apply_macro_periodic_boundary_conditions(const SlfParams *P, REAL *field
     if (isfinite(field[g0])) field[g1] = field[g0];
   }
   return 0;
+}
+
+int orc_apply_macro_periodic_boundary_conditions(const SlfParams *P, REAL *field, int axis) {
+  return orc_apply_macro_periodic_boundary_conditions_linked(P, field, axis, 0, 0);
 }

@@ -68,10 +68,11 @@ def prepare_macro_fields(params, node_map, dist, rho, options, iteration):
                                       ctypes.c_int(options), ctypes.c_uint32(iteration)), 'prepare_macro')
 
 
-def apply_pbc(params, dist, axis, with_swap):
+def apply_pbc(params, dist, axis, with_swap, links=(0, 0)):
+    """links: neighbours across the low / high face of the split axis (see the C function)."""
     lib = _lib(dist.dtype)
-    _chk(lib.orc_apply_periodic_boundary_conditions(ctypes.byref(params), _p(dist), ctypes.c_int(axis),
-                                                    ctypes.c_int(int(with_swap))), 'apply_pbc')
+    _chk(lib.orc_apply_periodic_boundary_conditions_linked(ctypes.byref(params), _p(dist), int(axis), int(with_swap),
+                                                           int(links[0]), int(links[1])), 'apply_pbc')
 
 
 def collect(params, dist, face, base_gx, base_other, max_lx, max_other, buf, with_swap):
@@ -184,9 +185,10 @@ def sc_collide_and_propagate(params, grid_idx, node_map, din, dout, rho, phi, v,
                                           ctypes.c_uint32(iteration), int(z_begin), int(z_end)), 'sc_collide')
 
 
-def apply_macro_pbc(params, field, axis):
+def apply_macro_pbc(params, field, axis, links=(0, 0)):
     lib = _lib(field.dtype)
-    _chk(lib.orc_apply_macro_periodic_boundary_conditions(ctypes.byref(params), _p(field), int(axis)), 'macro_pbc')
+    _chk(lib.orc_apply_macro_periodic_boundary_conditions_linked(ctypes.byref(params), _p(field), int(axis),
+                                                                 int(links[0]), int(links[1])), 'macro_pbc')
 
 
 class ShanChenSimulation(object):

@@ -500,10 +500,6 @@ apply_pbc(const DevParams P, float *dist, int axis, int per0, int per1, int per2
   if (SWAP && io >= 0 && ((link_lo && io == 0) || (link_hi && io == no - 1))) return;
   const int skip_e = (SWAP || io < 0) ? 0 : ((link_lo && io == 1) ? 1 : ((link_hi && io == no - 2) ? -1 : 0));
   float val[L::Q];
-#ifdef SLF_DEBUG_PBC
-  if (i1 == 3 && i2 == 0) printf("pbc D=%d swap=%d axis=%d n1=%d n2=%d oth=%d,%d gi_low=%lld gi_high=%lld off=%lld DS=%lld lim=%d,%d,%d\n",
-      L::D, (int)SWAP, axis, n1, n2, oth[0], oth[1], gi_low, gi_high, offset, P.DS, lim[0], lim[1], lim[2]);
-#endif
   // low -> high
 #pragma unroll
   for (int i = 1; i < L::Q; i++) {
@@ -528,9 +524,6 @@ apply_pbc(const DevParams P, float *dist, int axis, int per0, int per1, int per2
           dist[gidx3<L>(P, tgt[0], tgt[1], tgt[2]) + P.DS * j] = fv;
       }
     } else {
-#ifdef SLF_DEBUG_PBC
-      if (i1 == 3 && i2 == 0) printf("  l2h i=%d j=%d fv=%f -> %lld\n", i, j, fv, gi_high + P.DS * j);
-#endif
       dist[gi_high + P.DS * j] = fv;
     }
   }

@@ -7,12 +7,14 @@ import ctypes
 import numpy as np
 
 from oracle import oracle as orc
+from sailfish_b200 import params as P
 
 
 class FakeLib(object):
     def __init__(self):
         self.bufs = {}          # address -> numpy byte array (keeps memory alive)
         self.plans = {}
+        self.links = {}         # plan key -> (low, high)
         self.launches = 0
         self.calls = []
 
@@ -108,8 +110,17 @@ class FakeLib(object):
     def _slf_plan_bind_map(self, plan, m):
         pass
 
+    def _key(self, plan):
+        return plan.value if hasattr(plan, 'value') else int(plan)
+
     def _p(self, plan):
-        return self.plans[plan.value if hasattr(plan, 'value') else int(plan)]
+        return self.plans[self._key(plan)]
+
+    def _slf_plan_destroy(self, plan):
+        self.plans.pop(self._key(plan), None)
+
+    def _slf_plan_set_links(self, plan, lo, hi):
+        self.links[self._key(plan)] = (int(bool(lo)), int(bool(hi)))
 
     def _slf_set_initial_conditions(self, plan, dist, vx, vy, vz, rho, m, stream):
         p = self._p(plan)
@@ -132,7 +143,69 @@ class FakeLib(object):
         p = self._p(plan)
         if axis >= p.dim:
             return
-        orc.apply_pbc(p, self._arr(dist, np.float32, p.dist_size * p.Q), int(axis), bool(swap))
+        orc.apply_pbc(p, self._arr(dist, np.float32, p.dist_size * p.Q), int(axis), bool(swap),
+                      self.links.get(self._key(plan), (0, 0)))
+        self.launches += 1
+
+    # -- native runner: step replay, peer-to-peer planes, output packing --------------------------------
+    def _slf_run_steps(self, plan, m, da, db, rho, vx, vy, vz, iteration, nsteps, save_last, stream):
+        """Same sequence as one_step() in slf_api.cu, nsteps times."""
+        p = self._p(plan)
+        aa = p.access_pattern == 1
+        for k in range(int(nsteps)):
+            it = int(iteration) + k
+            din, dout = (da, da) if aa else ((da, db) if (it & 1) == 0 else (db, da))
+            self._slf_collide_and_propagate(plan, m, din, dout, rho, vx, vy, vz,
+                                            1 if (save_last and k == nsteps - 1) else 0, it, 0, -1, stream)
+            for axis in range(p.dim):
+                if p.periodic[axis]:
+                    self._slf_apply_periodic_boundary_conditions(plan, dout, axis, int(aa and (it & 1) == 0), stream)
+
+    def _outer(self, p):
+        return p.arr_nz if p.dim == 3 else p.arr_ny
+
+    def _slf_halo_push(self, plan, dist, face, peer_dist, peer_lat_n, peer_arr_n, with_swap, stream):
+        """sailfish_b200.halo.face_transfer is the host statement of this copy."""
+        from sailfish_b200 import halo, lattice
+        p = self._p(plan)
+        plane = p.dist_size // self._outer(p)
+        lat_n = p.lat_nz if p.dim == 3 else p.lat_ny
+        grid = lattice.get({0: 'D2Q9', 1: 'D3Q19', 2: 'D3Q27'}[p.lattice])
+        slots, src, dst = halo.face_transfer(grid, int(face), bool(with_swap), lat_n, int(peer_lat_n))
+        mine = self._arr(dist, np.float32, p.dist_size * p.Q).reshape(p.Q, self._outer(p), plane)
+        peer = self._arr(peer_dist, np.float32, plane * int(peer_arr_n) * p.Q).reshape(p.Q, int(peer_arr_n), plane)
+        for s_ in slots:
+            peer[s_, dst] = mine[s_, src]
+        self.launches += 1
+
+    def _slf_halo_push_field(self, plan, field, face, peer_field, peer_lat_n, stream):
+        p = self._p(plan)
+        plane = p.dist_size // self._outer(p)
+        lat_n = p.lat_nz if p.dim == 3 else p.lat_ny
+        hi = int(face) & 1
+        mine = self._arr(field, np.float32, p.dist_size).reshape(self._outer(p), plane)
+        peer = self._arr(peer_field, np.float32, plane * int(peer_lat_n)).reshape(int(peer_lat_n), plane)
+        peer[0 if hi else int(peer_lat_n) - 1] = mine[lat_n - 2 if hi else 1]
+        self.launches += 1
+
+    def _slf_sem_signal(self, sem, stream):
+        pass
+
+    def _slf_sem_wait(self, ready, consumed, stream):
+        pass
+
+    def _slf_pack_field(self, plan, m, field, out, stream):
+        p = self._p(plan)
+        shape = ((p.arr_nz,) if p.dim == 3 else ()) + (p.arr_ny, p.arr_nx)
+        lat = ((p.lat_nz,) if p.dim == 3 else ()) + (p.lat_ny, p.lat_nx)
+        real = tuple(slice(1, n - 1) for n in lat)
+        f = self._arr(field, np.float32, p.dist_size).reshape(shape)[real]
+        types = (self._arr(m, np.uint32, p.dist_size).reshape(shape)[real]) & ((1 << p.bits_type) - 1)
+        wet_ids = [p.type_id[P.NODE_CLASS_NAMES.index(n)] for n in (
+            '_NTFluid', 'NTHalfBBWall', 'NTEquilibriumVelocity', 'NTEquilibriumDensity', 'NTRegularizedVelocity',
+            'NTRegularizedDensity', 'NTDoNothing')]
+        dense = np.where(np.isin(types, wet_ids), f, np.float32(np.nan)).astype(np.float32)
+        self._arr(out, np.float32, dense.size)[:] = dense.reshape(-1)
         self.launches += 1
 
     # -- ghost-layer pack / unpack (the reference's own halo path in plugin mode) ---------------------
@@ -209,11 +282,29 @@ class FakeLib(object):
                                      self._v(p, vx, vy, vz), int(options), int(iteration), int(z0), int(z1))
         self.launches += 1
 
+    def _slf_sc_collide_and_propagate_fused(self, plan, m, d1i, d1o, d2i, d2o, rho, phi, vx, vy, vz, options,
+                                            iteration, z0, z1, stream):
+        """The fused kernel recomputes the common velocity from the populations; here: the oracle's macro pass
+        into scratch fields (or into vx.. when the velocity is to be saved), then the two collide passes."""
+        p = self._p(plan)
+        f, n = np.float32, p.dist_size
+        mp = self._arr(m, np.uint32, n)
+        a1, a2 = self._arr(d1i, f, n * p.Q), self._arr(d2i, f, n * p.Q)
+        r, ph = self._arr(rho, f, n), self._arr(phi, f, n)
+        save = int(options) & 1
+        v = self._v(p, vx, vy, vz) if save else [np.zeros(n, f) for _ in range(p.dim)]
+        r2, ph2 = r.copy(), ph.copy()       # the macro pass must not disturb the (halo-completed) density fields
+        orc.sc_prepare_macro_fields(p, mp, a1, a2, r2, ph2, v, 0, int(iteration), int(z0), int(z1))
+        orc.sc_collide_and_propagate(p, 0, mp, a1, self._arr(d1o, f, n * p.Q), r, ph, v, 0, int(iteration), int(z0), int(z1))
+        orc.sc_collide_and_propagate(p, 1, mp, a2, self._arr(d2o, f, n * p.Q), r, ph, v, 0, int(iteration), int(z0), int(z1))
+        self.launches += 1
+
     def _slf_apply_macro_periodic_boundary_conditions(self, plan, field, axis, stream):
         p = self._p(plan)
         if axis >= p.dim:
             return
-        orc.apply_macro_pbc(p, self._arr(field, np.float32, p.dist_size), int(axis))
+        orc.apply_macro_pbc(p, self._arr(field, np.float32, p.dist_size), int(axis),
+                            self.links.get(self._key(plan), (0, 0)))
         self.launches += 1
 
 
