@@ -115,7 +115,10 @@ class Subdomain(object):
     def set_node(self, where, node_type):
         """subdomain.py:532-562."""
         assert not self._type_map_encoded
-        where_idx = np.where(where)
+        # one index computation shared by the assignments below (flat indices: cheaper than a tuple of
+        # per-axis index arrays on a 10^8-node map)
+        base = self._type_map_base
+        where_idx = np.flatnonzero(np.broadcast_to(np.asarray(where, dtype=bool), base.shape))
         if inspect.isclass(node_type):
             assert issubclass(node_type, nt.LBNodeType)
             node_type = node_type()
@@ -128,14 +131,15 @@ class Subdomain(object):
                 continue
             raise ValueError('Unsupported node parameter %r (%s): the B200 hot path takes numbers '
                              'and constant vectors' % (name, type(param).__name__))
-        self._type_map_base[where_idx] = node_type.id
+        base.reshape(-1)[where_idx] = node_type.id
         key = hash((node_type.id, self._hashable_params(node_type.params)))
-        assert np.all(self._param_map_base[where_idx] == 0), 'Overriding previously set nodes is not allowed.'
-        self._param_map_base[where_idx] = key
+        pm = self._param_map_base.reshape(-1)
+        assert not pm[where_idx].any(), 'Overriding previously set nodes is not allowed.'
+        pm[where_idx] = key
         self._params[key] = node_type
         self._seen_types.add(node_type.id)
         if getattr(node_type, 'orientation', None) is not None:
-            self._orientation_base[where_idx] = node_type.orientation
+            self._orientation_base.reshape(-1)[where_idx] = node_type.orientation
         elif node_type.needs_orientation:
             self._needs_orientation = True
 
@@ -143,11 +147,18 @@ class Subdomain(object):
     def _lat_view(self, arr):
         return arr[..., :self.lat_shape[-1]]
 
+    @staticmethod
+    def _member(type_map, ids):
+        """np.isin(type_map, ids) for small non-negative type ids, as a table look-up (one pass)."""
+        ids = [int(i) for i in ids]
+        lut = np.zeros(max([int(type_map.max()) if type_map.size else 0] + ids) + 1, dtype=bool)
+        lut[ids] = True
+        return lut[type_map]
+
     def _fluid_map(self, wet, allow_unused=None):
         src = self._lat_view(self._type_map_base)
         if wet:
-            ids = nt.get_wet_node_type_ids(allow_unused=allow_unused)
-            return np.isin(src, ids)
+            return self._member(src, nt.get_wet_node_type_ids(allow_unused=allow_unused))
         return src == 0
 
     def _lattice_kernel(self, zero=1):
@@ -188,7 +199,7 @@ class Subdomain(object):
             return False
         tm = tm_full[ngs]
         ob = ob_full[ngs]
-        orient_map = np.isin(tm, orient_types) & (ob == 0)
+        orient_map = self._member(tm, orient_types) & (ob == 0)
         l = self.dim - 1
         for i, vec in enumerate(self.grid.basis[1:]):
             shifted = tm
@@ -196,7 +207,7 @@ class Subdomain(object):
                 if shift == 0:
                     continue
                 shifted = np.roll(shifted, int(-shift), axis=l - j)
-            idx = orient_map & np.isin(shifted, wet)
+            idx = orient_map & self._member(shifted, wet)
             ob[idx] |= np.uint32(1 << i)
         return True
 
