@@ -137,3 +137,40 @@ def test_fast_output_equals_reference_style_output(fake, tmp_path, monkeypatch, 
         for k in fa.files:
             np.testing.assert_array_equal(fa[k], fb[k])
     assert 'slf_pack_field' in fake.calls
+
+
+def test_random_decompositions(fake):
+    """Seeded sample of random sizes / models / lattices / subdomain counts (uneven remainders, thin slabs):
+    split == single, bit for bit."""
+    import random
+    rng = random.Random(20240924)
+    for _ in range(16):
+        kind = rng.choice(['ldc3d', 'ldc2d', 'pipe', 'sc3d'])
+        ap = rng.choice(['AA', 'AB'])
+        steps = rng.randint(1, 6)
+        if kind == 'ldc3d':
+            nz = rng.randint(6, 18)
+            args = ['--lat_nx=%d' % rng.randint(4, 12), '--lat_ny=%d' % rng.randint(4, 10), '--lat_nz=%d' % nz, '--visc=0.04']
+            args += rng.choice([['--model=bgk'], ['--model=mrt'], ['--grid=D3Q27']])
+            cls, geo, outer = ldc_3d.LDCSim, EqualSubdomainsGeometry3D, nz
+        elif kind == 'ldc2d':
+            outer = rng.randint(6, 22)
+            args = ['--lat_nx=%d' % rng.randint(5, 36), '--lat_ny=%d' % outer, '--visc=0.05', '--model=' + rng.choice(['bgk', 'mrt'])]
+            cls, geo = ldc_2d.LDCSim, EqualSubdomainsGeometry2D
+        elif kind == 'pipe':
+            outer = rng.randint(8, 16)
+            args = ['--lat_nx=%d' % rng.randint(8, 12), '--lat_ny=%d' % rng.randint(8, 12), '--lat_nz=%d' % outer,
+                    '--flow_direction=' + rng.choice('xyz'), '--drive=' + rng.choice(['force', 'pressure']),
+                    '--model=' + rng.choice(['bgk', 'mrt'])]
+            cls, geo = poiseuille_3d.PoiseuilleSim, EqualSubdomainsGeometry3D
+        else:
+            outer = rng.randint(6, 12)
+            args = ['--lat_nx=%d' % rng.randint(4, 9), '--lat_ny=%d' % rng.randint(4, 9), '--lat_nz=%d' % outer, '--seed=1',
+                    '--G11=%g' % rng.choice([0.0, -0.2])]
+            cls, geo = sc_separation_3d.SeparationSCSim, EqualSubdomainsGeometry3D
+        nsub = rng.randint(2, max(2, min(5, outer // 2)))
+        args += ['--access_pattern=' + ap]
+        one = run(cls, geo, args + ['--subdomains=1'], steps)
+        many = run(cls, geo, args + ['--subdomains=%d' % nsub], steps)
+        for a, b in zip(one, many):
+            np.testing.assert_array_equal(a, b, err_msg='%s %s nsub=%d steps=%d' % (kind, args, nsub, steps))
