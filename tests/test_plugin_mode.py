@@ -110,3 +110,56 @@ def test_reference_shan_chen_runs_on_b200_backend(reference, oracle, monkeypatch
         want = c[k][inner][..., :12]
         assert res[k].shape == want.shape
         assert np.abs(res[k] - want).max() / np.abs(want).max() < 5e-6, k
+
+
+NATIVE = {
+    'ldc3d': ('examples/ldc_3d.py', 'LDCSim', 'ldc_3d', None, ['--lat_nx=12', '--lat_ny=10', '--lat_nz=11', '--visc=0.04']),
+    'ldc3d_mrt': ('examples/ldc_3d.py', 'LDCSim', 'ldc_3d', None,
+                  ['--lat_nx=12', '--lat_ny=10', '--lat_nz=11', '--visc=0.04', '--model=mrt']),
+    'ldc2d': ('examples/ldc_2d.py', 'LDCSim', 'ldc_2d', None, ['--lat_nx=16', '--lat_ny=14', '--visc=0.05']),
+    'pipe_pressure': ('examples/poiseuille_3d.py', 'PoiseuilleSim', 'poiseuille_3d', 'EqualSubdomainsGeometry3D',
+                      ['--grid=D3Q19', '--lat_nx=12', '--lat_ny=12', '--lat_nz=16', '--flow_direction=z', '--drive=pressure',
+                       '--stationary', '--model=mrt', '--visc=0.1']),
+    'pipe_force': ('examples/poiseuille_3d.py', 'PoiseuilleSim', 'poiseuille_3d', 'EqualSubdomainsGeometry3D',
+                   ['--grid=D3Q19', '--lat_nx=14', '--lat_ny=12', '--lat_nz=12', '--flow_direction=x', '--drive=force',
+                    '--visc=0.1']),
+    'sc3d': ('examples/binary_fluid/sc_separation_3d.py', 'SeparationSCSim', 'sc_separation_3d', 'LBGeometry3D',
+             ['--lat_nx=12', '--lat_ny=10', '--lat_nz=9', '--seed=1234']),
+}
+
+
+@pytest.mark.parametrize('name', sorted(NATIVE))
+@pytest.mark.parametrize('ap', ['AB', 'AA'])
+def test_native_host_stack_equals_reference_host_stack(reference, oracle, monkeypatch, tmp_path, name, ap):
+    """The same set-up through the two host stacks above the C ABI -- the unmodified reference (its example,
+    controller, runner, output writer) and this package's own (sailfish_b200.examples, controller, runner) --
+    on the same (fake) device: the output files must be identical, bit for bit, NaN mask included."""
+    import importlib
+    import fake_device
+    fake_device.install_fake(monkeypatch)
+    script, cls_name, native_mod, geo_name, args = NATIVE[name]
+    steps = 10
+    common = args + ['--access_pattern=' + ap, '--max_iters=%d' % steps, '--every=%d' % steps, '--quiet']
+    # reference stack
+    mod = reference.load_example(script)
+    from sailfish.controller import LBSimulationController as RefController
+    from sailfish import geo as refgeo
+    out_ref = str(tmp_path / 'ref')
+    monkeypatch.setattr(sys, 'argv', [script] + common + ['--backends=b200', '--debug_single_process', '--output=' + out_ref])
+    RefController(getattr(mod, cls_name), getattr(refgeo, geo_name) if geo_name else None).run()
+    # native stack
+    from sailfish_b200 import geo as mygeo
+    from sailfish_b200.controller import LBSimulationController
+    nat = importlib.import_module('sailfish_b200.examples.' + native_mod)
+    out_nat = str(tmp_path / 'nat')
+    native_args = [a for a in common if not a.startswith('--grid=')] + ['--output=' + out_nat, '--sync_output']
+    monkeypatch.setattr(sys, 'argv', ['x'] + native_args)
+    geo_cls = getattr(mygeo, geo_name, None) if geo_name else None
+    LBSimulationController(getattr(nat, cls_name), geo_cls).run()
+    fr = sorted(glob.glob(out_ref + '.0.*%d.npz' % steps))
+    fn = sorted(glob.glob(out_nat + '.0.*%d.npz' % steps))
+    assert fr and fn
+    a, b = np.load(fr[-1]), np.load(fn[-1])
+    assert sorted(a.files) == sorted(b.files)
+    for k in a.files:
+        np.testing.assert_array_equal(a[k], b[k])
