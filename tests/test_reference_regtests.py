@@ -4,7 +4,8 @@ items 3 and 4), run UNCHANGED on the b200 backend through sailfish_b200.plugin:
 * 2d_/3d_propagation.py -- literal known-answer vectors for streaming across subdomain faces, edges and
   corners, periodic and partially periodic boxes, misaligned blocks, AA with 2 and 4 subdomains;
 * 2d_/3d_ldc.py (3 / 4 / 8 blocks), 2d_cylinder.py -- decomposition invariance to 6 decimals;
-* 2d_binary.py -- the Shan-Chen mixture on 2 and 4 blocks (macro-field halo kernels);
+* 2d_binary.py, binary_pbc.py -- the Shan-Chen mixture on 2 and 4 blocks and in shifted periodic boxes
+  (macro-field halo kernels); 3d_sphere.py -- flow past a sphere on several blocks;
 * tests/gpu/do_nothing_node.py -- AA == AB with the do-nothing outflow node.
 
 The whole reference stack runs as is (controller, machine master, one OS process per subdomain, ZeroMQ
@@ -32,10 +33,12 @@ RUNS = {
     '2d_ldc': ('AA', 100),
     '2d_cylinder': ('AB', 100),
     '2d_binary': ('AB', 100),
+    '3d_sphere': ('AB', 100),
+    'binary_pbc': ('AB', None),
     'tests/gpu/do_nothing_node.py': ('AB', None),     # AA == AB with the do-nothing outflow node, 1000 steps
 }
 if os.environ.get('SLF_ALL_REGTESTS'):
-    RUNS.update({'3d_sphere': ('AB', 100), 'binary_pbc': ('AB', 100), '3d_ldc_ab': ('AB', 100), '2d_ldc_ab': ('AB', 100)})
+    RUNS.update({'3d_ldc_ab': ('AB', 100), '2d_ldc_ab': ('AB', 100)})
 OUT_OF_SCOPE = ('Q15', 'FreeEnergy', 'FEInterblock')
 
 
