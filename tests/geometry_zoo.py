@@ -1,0 +1,94 @@
+"""Geometry set-ups shared by the golden generator (run with the REFERENCE's classes, tools/gen_golden_steps.py
+zoo) and tests/test_host_geometry.py (run with this package's mirror): same user code, two implementations of
+Subdomain.reset() + encoding.  The scenarios follow the reference's tests/subdomain.py (solid interior nodes,
+duct, channels with periodic directions, link tagging) and add the node types the examples do not use."""
+import numpy as np
+
+
+def make_cases(ns):
+    """ns: namespace with Subdomain2D, Subdomain3D, LBFluidSim, LBForcedSim and the NT* node types."""
+    S2, S3, Sim = ns['Subdomain2D'], ns['Subdomain3D'], ns['LBFluidSim']
+    NTFullBBWall, NTHalfBBWall = ns['NTFullBBWall'], ns['NTHalfBBWall']
+    NTEquilibriumVelocity, NTEquilibriumDensity = ns['NTEquilibriumVelocity'], ns['NTEquilibriumDensity']
+    NTRegularizedVelocity, NTRegularizedDensity = ns['NTRegularizedVelocity'], ns['NTRegularizedDensity']
+    NTDoNothing = ns['NTDoNothing']
+
+    def sim(sub, **defaults):
+        class _Sim(Sim):
+            subdomain = sub
+
+            @classmethod
+            def update_defaults(cls, d):
+                d.update(defaults)
+        return _Sim
+
+    class SolidBox2D(S2):
+        """A half-way bounce-back block inside a periodic box: shell stays, inside becomes propagation-only /
+        unused."""
+        def boundary_conditions(self, hx, hy):
+            self.set_node((hx >= 5) & (hx <= 10) & (hy >= 4) & (hy <= 9), NTHalfBBWall)
+
+        def initial_conditions(self, sim, hx, hy):
+            sim.rho[:] = 1.0 + 0.01 * np.cos(0.4 * hx) * np.sin(0.3 * hy)
+            sim.vx[:] = 0.02 * np.sin(0.5 * hy)
+            sim.vy[:] = -0.01 * np.cos(0.3 * hx)
+
+    class Channel2D(S2):
+        """Velocity inlet, do-nothing outlet, full-way walls, a step on the lower wall."""
+        def boundary_conditions(self, hx, hy):
+            wall = (hy == 0) | (hy == self.gy - 1) | ((hx >= 6) & (hx <= 9) & (hy <= 3))
+            self.set_node(wall, NTFullBBWall)
+            self.set_node((hx == 0) & np.logical_not(wall), NTEquilibriumVelocity((0.03, 0.0)))
+            self.set_node((hx == self.gx - 1) & np.logical_not(wall), NTDoNothing)
+
+        def initial_conditions(self, sim, hx, hy):
+            sim.rho[:] = 1.0
+            sim.vx[:] = 0.03
+
+    class Duct3D(S3):
+        """Half-way walls on the y and z faces, periodic along x (link tags, orientation on edges)."""
+        def boundary_conditions(self, hx, hy, hz):
+            self.set_node((hy == 0) | (hy == self.gy - 1) | (hz == 0) | (hz == self.gz - 1), NTHalfBBWall)
+
+        def initial_conditions(self, sim, hx, hy, hz):
+            sim.rho[:] = 1.0 + 0.005 * np.sin(2 * np.pi * hx / self.gx)
+            sim.vx[:] = 0.03 * np.sin(np.pi * hy / (self.gy - 1)) * np.sin(np.pi * hz / (self.gz - 1))
+            sim.vz[:] = 0.005 * np.cos(2 * np.pi * hx / self.gx)
+
+    class PressureBox3D(S3):
+        """Regularised density planes at both x ends, regularised velocity on the z = top plane, full-way walls
+        elsewhere, a full-way obstacle in the middle."""
+        def boundary_conditions(self, hx, hy, hz):
+            wall = (hy == 0) | (hy == self.gy - 1) | (hz == 0)
+            wall |= (abs(hx - self.gx // 2) <= 1) & (abs(hy - self.gy // 2) <= 1) & (hz <= 3)
+            wall |= (hz == self.gz - 1) & ((hx == 0) | (hx == self.gx - 1))     # no open edge between lid and x planes
+            lid = (hz == self.gz - 1) & np.logical_not(wall)
+            self.set_node(wall, NTFullBBWall)
+            self.set_node(lid, NTRegularizedVelocity((0.0, 0.02, 0.0)))
+            free = np.logical_not(wall | lid)
+            self.set_node((hx == 0) & free, NTRegularizedDensity(1.01))
+            self.set_node((hx == self.gx - 1) & free, NTRegularizedDensity(0.99))
+
+        def initial_conditions(self, sim, hx, hy, hz):
+            sim.rho[:] = 1.0 + 0.01 * (self.gx / 2.0 - hx) / self.gx
+
+    class SlabPeriodicYZ(S3):
+        """Full-way walls at both x ends, periodic in y and z, equilibrium-density patch on one wall."""
+        def boundary_conditions(self, hx, hy, hz):
+            patch = (hx == 0) & (hy >= 3) & (hy <= 5) & (hz >= 2) & (hz <= 4)
+            self.set_node(((hx == 0) | (hx == self.gx - 1)) & np.logical_not(patch), NTFullBBWall)
+            self.set_node(patch, NTEquilibriumDensity(1.02))
+
+        def initial_conditions(self, sim, hx, hy, hz):
+            sim.rho[:] = 1.0
+
+    return {
+        'solid_box2d': (sim(SolidBox2D, lat_nx=16, lat_ny=14, grid='D2Q9', periodic_x=True, periodic_y=True), []),
+        'channel2d': (sim(Channel2D, lat_nx=20, lat_ny=12, grid='D2Q9'), []),
+        'duct3d': (sim(Duct3D, lat_nx=9, lat_ny=8, lat_nz=7, grid='D3Q19', periodic_x=True), []),
+        'duct3d_notags': (sim(Duct3D, lat_nx=9, lat_ny=8, lat_nz=7, grid='D3Q19', periodic_x=True), ['--nouse_link_tags']),
+        'pressure_box3d': (sim(PressureBox3D, lat_nx=12, lat_ny=10, lat_nz=9, grid='D3Q19'), []),
+        'pressure_box3d_q27': (sim(PressureBox3D, lat_nx=12, lat_ny=10, lat_nz=9, grid='D3Q27'), []),
+        'slab_periodic_yz': (sim(SlabPeriodicYZ, lat_nx=8, lat_ny=9, lat_nz=7, grid='D3Q19', periodic_y=True,
+                                 periodic_z=True), []),
+    }

@@ -99,3 +99,29 @@ def test_periodic_box_equals_wraparound_streaming(oracle, name):
     assert steps % 2 == 0   # AA: populations are back in natural slots
     d = sim.current_dist().reshape(c['dist'].shape)
     assert np.abs(d[:, m] - f.reshape(L.Q, -1)).max() < 1e-13
+
+
+@pytest.mark.parametrize('case', util.ZOO_STEP_CASES)
+def test_zoo_fp64_oracle_reproduces_reference_stepper(oracle, case):
+    """Node types the examples do not use (tests/geometry_zoo.py)."""
+    c = util.load_case(case)
+    e_dist, e_rho, e_v = _errors(_run(oracle, c, np.float64), c)
+    assert e_dist < 1e-12 and e_rho < 1e-12 and e_v < 1e-11, (e_dist, e_rho, e_v)
+    e_dist, e_rho, e_v = _errors(_run(oracle, c, np.float32), c)
+    assert e_dist < 5e-6 and e_rho < 5e-6 and e_v < 1e-4, (e_dist, e_rho, e_v)
+
+
+@pytest.mark.parametrize('name', sorted(set(c[:-3] for c in util.ZOO_STEP_CASES)))
+def test_zoo_aa_equals_ab(oracle, name):
+    ab = util.load_case(name + '_AB')
+    a = _run(oracle, ab, np.float64)
+    p = util.params_from_case(ab, access_pattern='AA')
+    b = oracle.Simulation(p, ab['map'], ab['rho0'], ab['v0'], dtype=np.float64)
+    b.run(int(ab['steps']))
+    m = util.real_mask(ab)
+    wet = np.zeros(m.shape, bool)
+    wet[m] = ab['fluid_map'].reshape(-1)
+    assert np.allclose(a.rho.reshape(m.shape)[wet], b.rho.reshape(m.shape)[wet], rtol=0, atol=1e-13)
+    for x, y in zip(a.v, b.v):
+        assert np.allclose(x.reshape(m.shape)[wet], y.reshape(m.shape)[wet], rtol=0, atol=1e-13)
+

@@ -58,3 +58,12 @@ def rel_linf(a, b):
 SC_CASES = ['sc3d', 'sc3d_walls', 'sc2d_classic', 'sc2d_gravity', 'sc3d_gravity']
 CASES = ['ldc2d_bgk', 'ldc2d_mrt', 'ldc3d_bgk', 'ldc3d_mrt', 'ldc3d_q27', 'poi3d_press_mrt',
          'poi3d_force_bgk', 'poi3d_force_mrt', 'box3d_bgk', 'box3d_q27', 'box2d_bgk']
+
+# step goldens on tests/geometry_zoo.py (half-way bounce-back, equilibrium velocity, regularised density,
+# do-nothing nodes, obstacles with unused cores): name_AP where tools/gen_golden_steps.py produced one.  The
+# duct (half-way walls on the outermost layer, no unused layer behind them -- the configuration the reference's
+# FIXME in binary_shan_chen.mako / boundary.mako warns about) is pinned in AB only; its AA run is covered by the
+# AA == AB invariant.
+ZOO_STEP_CASES = sorted(f[len('steps_'):-len('.npz')] for f in os.listdir(os.path.join(ROOT, 'tests', 'golden'))
+                        if f.startswith('steps_zoo_'))
+
