@@ -5,18 +5,25 @@
 
 Workload (BASELINE.json metric / north_star): examples/ldc_3d at 512^3 per GPU
 (`--access_pattern=AA --grid=D3Q19 --model=bgk`).  N>1 (torchrun, one rank per GPU): the
-domain is 512 x 512 x (512 N) split along z into N subdomains (weak scaling), ghost layers
-exchanged GPU-to-GPU every step.  A "step" is one CollideAndPropagate pass over the whole
-lattice (+ halo push).  MLUPS = fluid nodes x steps / time x 1e-6 (subdomain_runner.py:1699).
+headline `value` is WEAK scaling -- the domain is 512 x 512 x (512 N) split along z into N
+subdomains, ghost layers exchanged GPU-to-GPU every step -- and the line also carries a
+`strong` record: BASELINE config 4, the 512^3 cavity itself split N ways.  A "step" is one
+CollideAndPropagate pass over the whole lattice (+ halo push).  MLUPS = fluid nodes x steps /
+time x 1e-6 (subdomain_runner.py:1699).
 
 Printed JSON keys (one line, rank 0): see the task contract; `value` is device-resident
 throughput (CUDA events, max over ranks), `e2e` the same metric for a whole job through the
 public runner with HOST buffers (pinned host -> device upload of map/rho/v, initialisation,
 K steps, device -> host download of rho/v, all inside the timed region), `roofline` the
-bandwidth roofline of the collide kernel, `cpu_baseline` the oracle on the host cores.
+bandwidth roofline of the collide kernel, `cpu_baseline` the oracle on the host cores,
+`parity` the correctness evidence of THIS run: GPU vs the fp32/fp64 oracle on a 64^3 cavity
+and, for N>1, every layer the halo exchange can have influenced compared bit for bit with a
+single-subdomain run of the same global lattice (see verify_decomposition).  The process exits
+1 -- after printing the line -- when a result is non-finite or a parity check fails.
+
 `--impl reference` times the reference arm: the CPU restatement of the reference kernels
-(oracle/, all host threads) -- the reference itself has no CPU path and its GPU path needs
-Mako + pycuda.
+(oracle/, all host threads, pinned, first-touch placement) -- the reference itself has no CPU
+path and its GPU path needs Mako + pycuda.
 """
 import argparse
 import json
@@ -32,6 +39,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BYTES_PER_LUP = {'D3Q19': 152, 'D2Q9': 72, 'D3Q27': 216}   # Q*4 B read + Q*4 B written
+VISC = 0.03175                                              # Re = 400 at 256^3 (regtest/ldc_3d.py:37-40)
+PARITY_STEPS = 16
 
 
 def measured_peak():
@@ -64,7 +73,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append([x.strip() for x in out.split(',')])
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.1)
 
     def stop(self):
         self._stop_evt.set()
@@ -78,13 +87,16 @@ class ClockSampler(threading.Thread):
                 'sm_max_mhz': int(float(self.samples[0][1])), 'reasons': reasons, 'samples': len(self.samples)}
 
 
+# ---------------------------------------------------------------------------------------------
+# CPU arms (oracle/ is executed only here: cpu_baseline + --impl reference + the parity blocks)
+# ---------------------------------------------------------------------------------------------
 def build_oracle_case(size, dtype=np.float32):
     """ldc_3d geometry via the host mirror (no GPU needed) for the CPU arms."""
     from sailfish_b200.controller import LBSimulationController
     from sailfish_b200.examples.ldc_3d import LDCSim
     from sailfish_b200 import params as P
     ctrl = LBSimulationController(LDCSim)
-    args = ['--lat_nx=%d' % size, '--lat_ny=%d' % size, '--lat_nz=%d' % size, '--visc=0.03175',
+    args = ['--lat_nx=%d' % size, '--lat_ny=%d' % size, '--lat_nz=%d' % size, '--visc=%r' % VISC,
             '--access_pattern=AA', '--quiet']
     cfg = ctrl._parser.parse(args)
     ctrl.config = cfg
@@ -105,64 +117,232 @@ def build_oracle_case(size, dtype=np.float32):
     arr = list(reversed(sd.arr_shape))
     p = P.make_params('D3Q19', 'bgk', 'AA', lat, arr, [False] * 3, sd.bits, sd.type_ids_by_name(),
                       sd.node_params, cfg.visc)
-    return p, sd.encoded_map(), base[0], base[1:], sd.num_fluid_nodes
+    return p, sd.encoded_map(), base[0], base[1:], sd.num_fluid_nodes, sd.fluid_map(), spec._nonghost_slice
 
 
-def cpu_sample_size():
+def cpu_sample_size(ncpu):
     """Edge of the bounded CPU sample: 256^3 (1.5 GB lattice) keeps a many-core host busy, 160^3 is enough
     for a small one; both are far beyond the last-level cache."""
-    return 256 if (os.cpu_count() or 1) >= 32 else 160
+    return 256 if ncpu >= 32 else 160
 
 
-def cpu_run(size, budget_s, threads=None):
-    """Times the oracle (fp32, OpenMP over z) on ldc_3d size^3; returns MLUPS and a description."""
-    from oracle import oracle
-    oracle.build()
-    cores = threads or os.cpu_count() or 1
-    os.environ.setdefault('OMP_NUM_THREADS', str(cores))
-    p, node_map, rho, v, fluid = build_oracle_case(size)
-    sim = oracle.Simulation(p, node_map, rho, v, dtype=np.float32)
-    sim.step()
-    sim.step()                       # warm-up (both AA parities)
-    t0 = time.time()
-    n = 0
-    while True:
-        sim.step()
-        sim.step()
-        n += 2
-        if time.time() - t0 > budget_s or n >= 2000:
-            break
-    dt = time.time() - t0
-    return fluid * n / dt * 1e-6, cores, 'ldc_3d D3Q19 BGK AA %d^3, %d steps, %.1f s, oracle fp32 OpenMP' % (size, n, dt)
+class CpuArm(object):
+    """The oracle (fp32, OpenMP over (z, y) rows, threads pinned, first touch by the same rows) on a
+    bounded ldc_3d sample; one `sample()` = as many AA step pairs as fit in the budget."""
+
+    def __init__(self):
+        from oracle import oracle
+        oracle.build()
+        self.oracle = oracle
+        ncpu = len(oracle.HOST_CPUS)
+        # set explicitly: torchrun exports OMP_NUM_THREADS=1 and another library may already have
+        # initialised the OpenMP runtime with it
+        self.threads = oracle.omp_config(ncpu, pin=True)
+        self.size = cpu_sample_size(ncpu)
+        p, node_map, rho, v, fluid = build_oracle_case(self.size)[:5]
+        self.fluid = fluid
+        self.sim = oracle.Simulation(p, node_map, rho, v, dtype=np.float32)
+        self.sim.step()
+        self.sim.step()                       # warm-up (both AA parities)
+
+    def sample(self, budget_s):
+        t0 = time.time()
+        n = 0
+        while True:
+            self.sim.step()
+            self.sim.step()
+            n += 2
+            if time.time() - t0 > budget_s or n >= 4000:
+                break
+        dt = time.time() - t0
+        return self.fluid * n / dt * 1e-6, n, dt
+
+    def describe(self, n, dt):
+        return ('ldc_3d D3Q19 BGK AA %d^3, %d steps in %.1f s per sample, oracle fp32, %d OpenMP threads pinned to %d CPUs'
+                % (self.size, n, dt, self.threads, len(self.oracle.HOST_CPUS)))
+
+
+def workload_name(size, gpus):
+    return ('examples/ldc_3d D3Q19 BGK, AA access pattern, %d^3 per GPU (global %dx%dx%d, z-split)'
+            % (size, size, size, size * gpus))
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    size = cpu_sample_size()
-    per_step_budget = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
-    vals = []
+    arm = CpuArm()
+    total = max(1, args.steps + args.warmup)
+    budget = args.cpu_budget if args.cpu_budget > 0 else max(1.0, min(20.0, 100.0 / total))
+    vals, durs, nsteps = [], [], 0
     for k in range(args.warmup + args.steps):
-        mlups, cores, sample = cpu_run(size, per_step_budget)
+        mlups, n, dt = arm.sample(budget)
         if k >= args.warmup:
             vals.append(mlups)
-    value = float(np.mean(vals))
+            durs.append(dt)
+            nsteps = n
+    value = float(np.median(vals))
+    sample = arm.describe(nsteps, float(np.median(durs)))
     line = {
         'impl': 'reference', 'metric': 'MLUPS D3Q19 BGK', 'value': value, 'unit': 'MLUPS',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': 1e3 * per_step_budget, 'higher_is_better': True, 'scaling': 'weak',
+        'ms_per_step': 1e3 * float(np.median(durs)), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'examples/ldc_3d D3Q19 BGK, AA access pattern, %d^3 per GPU (global %dx%dx%d, z-split)'
-                               % (args.size, args.size, args.size, args.size * args.gpus),
-                   'visc': 0.03175,
-                   'sample': 'each step = a bounded %d^3 run of the same cavity on the host cores' % size,
+        'config': {'workload': workload_name(args.size, args.gpus), 'visc': VISC,
+                   'sample': 'each step = a bounded %d^3 run of the same cavity on the host cores (value = median over '
+                             'the %d timed samples; ms_per_step = median sample duration)' % (arm.size, len(vals)),
                    'note': 'reference has no CPU path (backend_dummy is a no-op) and its GPU path needs Mako+pycuda; '
                            'this is the CPU restatement of its kernels (oracle/), all host threads'},
-        'cpu_baseline': {'value': value, 'unit': 'MLUPS', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': value, 'min': float(np.min(vals)), 'max': float(np.max(vals)), 'unit': 'MLUPS',
+                         'cores': arm.threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'MLUPS', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line))
+
+
+def cpu_baseline_subprocess():
+    """The main arm's cpu_baseline runs the reference arm in a fresh process: this one has torch (and its
+    OpenMP runtime, configured by torchrun's OMP_NUM_THREADS=1) loaded."""
+    env = dict(os.environ)
+    for k in ('OMP_NUM_THREADS', 'RANK', 'LOCAL_RANK', 'WORLD_SIZE', 'CUDA_VISIBLE_DEVICES'):
+        env.pop(k, None)
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '3',
+                              '--warmup', '1', '--cpu_budget', '4'], env=env, capture_output=True, text=True,
+                             timeout=600)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith('{'):
+                return json.loads(ln)['cpu_baseline']
+        return {'error': (out.stderr or 'no output')[-300:]}
+    except Exception as e:                       # noqa: BLE001
+        return {'error': repr(e)[:300]}
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def make_ctrl(size, nz_global, nsub, local=False, geo=None):
+    from sailfish_b200.controller import LBSimulationController
+    from sailfish_b200.geo import EqualSubdomainsGeometry3D
+    from sailfish_b200.examples.ldc_3d import LDCSim
+    ctrl = LBSimulationController(LDCSim, geo or EqualSubdomainsGeometry3D)
+    ctrl.setup(['--lat_nx=%d' % size, '--lat_ny=%d' % size, '--lat_nz=%d' % nz_global, '--subdomains=%d' % nsub,
+                '--visc=%r' % VISC, '--access_pattern=AA', '--grid=D3Q19', '--model=bgk', '--quiet'], local=local)
+    return ctrl
+
+
+def window_geometry(zlo, zhi):
+    """A single subdomain covering the global layers [zlo, zhi) of the same global geometry."""
+    from sailfish_b200.geo import LBGeometry3D
+    from sailfish_b200.subdomain import SubdomainSpec
+
+    class WindowGeometry(LBGeometry3D):
+        @classmethod
+        def add_options(cls, group):
+            LBGeometry3D.add_options(group)
+            group.add_argument('--subdomains', type=int, default=1)
+
+        def subdomains(self, n=None):
+            return [SubdomainSpec((0, 0, zlo), (self.gx, self.gy, zhi - zlo), id_=0)]
+    return WindowGeometry
+
+
+def host_fields(r):
+    """[rho, vx, vy, vz] over the real nodes of the subdomain + the wet-node mask."""
+    sl = r._spec._nonghost_slice
+    f = np.array([np.array(r.field_base(r._sim.rho))[sl]] + [np.array(r.field_base(c))[sl] for c in r._sim.v])
+    return f, r._subdomain.fluid_map()
+
+
+def verify_decomposition(ctrl, size, nz_global, dist, steps=PARITY_STEPS):
+    """Decomposition invariance (regtest/subdomains/3d_ldc.py, util.py:27-30 -- there to 6 decimals, here
+    bit for bit).  The linked run is re-initialised and stepped `steps` times; each rank then recomputes, as
+    ONE subdomain without neighbours on its own GPU, a window of the global lattice around each of its
+    interfaces and compares its own layers with it.  Garbage enters a window through its cut faces at one
+    layer per step, so windows extend steps + 4 layers beyond the compared layers; halo data likewise
+    travels one layer per step, so comparing steps + 8 layers on this side of every interface covers
+    everything the exchange can have influenced."""
+    import torch
+    r = ctrl.runners[0]
+    ctrl.reinitialize(reset_fields=True)      # the host fields hold the results of the previous job
+    ctrl.run_steps(steps, save_last=True)
+    ctrl.sync()
+    r._fields_to_host()
+    mine, wet = host_fields(r)
+    z0 = r._spec.location[2]
+    nz = r._spec.size[2]
+    z1 = z0 + nz
+    m, c = steps + 4, steps + 8
+    ranges = []                                    # global layer ranges [a, b) of this rank to check
+    if 4 in r._spec._face_conn:
+        ranges.append((z0, min(z1, z0 + c)))
+    if 5 in r._spec._face_conn:
+        ranges.append((max(z0, z1 - c), z1))
+    if len(ranges) == 2 and ranges[0][1] >= ranges[1][0]:
+        ranges = [(z0, z1)]
+    bad, maxdiff, layers, finite = 0, 0.0, 0, True
+    for a, b in ranges:
+        zlo, zhi = max(0, a - m), min(nz_global, b + m)
+        w = make_ctrl(size, nz_global, 1, local=True, geo=window_geometry(zlo, zhi))
+        wr = w.runners[0]
+        wr.run_steps(steps, save_last=True)
+        w.sync()
+        wr._fields_to_host()
+        ref, _ = host_fields(wr)
+        mask = wet[a - z0:b - z0]
+        x = mine[:, a - z0:b - z0][:, mask]
+        y = ref[:, a - zlo:b - zlo][:, mask]
+        finite = finite and bool(np.isfinite(x).all()) and bool(np.isfinite(y).all())
+        neq = x != y
+        bad += int(neq.sum())
+        if neq.any():
+            maxdiff = max(maxdiff, float(np.nanmax(np.abs(x[neq] - y[neq]))))
+        layers += b - a
+        del w, wr
+    finite = finite and bool(np.isfinite(mine[:, wet]).all())
+    t = torch.tensor([bad, layers, 0 if finite else 1], dtype=torch.int64, device='cuda')
+    dist.all_reduce(t)
+    d = torch.tensor([maxdiff], dtype=torch.float64, device='cuda')
+    dist.all_reduce(d, op=dist.ReduceOp.MAX)
+    bad, layers, nonfinite = (int(v) for v in t.tolist())
+    return {'steps': steps, 'reference': 'single-subdomain run of the same global lattice (windows around every interface)',
+            'layers_compared': layers, 'values_differing': bad, 'max_abs_diff': float(d.item()),
+            'bit_identical': bad == 0, 'result_finite': nonfinite == 0, 'ok': bad == 0 and nonfinite == 0}
+
+
+def verify_oracle(size=64, steps=20):
+    """GPU (public runner) vs the fp32 and fp64 oracles on ldc_3d size^3: the fp32 oracle's own deviation
+    from exact arithmetic is printed beside the GPU's (relative max norm over wet nodes)."""
+    from oracle import oracle
+    oracle.build()
+    p, node_map, rho, v, _, fluid_map, sl = build_oracle_case(size)
+    ctrl = make_ctrl(size, size, 1, local=True)
+    r = ctrl.runners[0]
+    r.run_steps(steps, save_last=True)
+    ctrl.sync()
+    r._fields_to_host()
+    g, wet = host_fields(r)
+    out = {}
+    res = {}
+    for name, dt in (('f32', np.float32), ('f64', np.float64)):
+        sim = oracle.Simulation(p, node_map, rho, v, dtype=dt)
+        sim.run(steps)
+        res[name] = np.array([sim.rho.reshape(node_map.shape)[sl]] + [c.reshape(node_map.shape)[sl] for c in sim.v],
+                             dtype=np.float64)
+
+    def rel(a, b, k):
+        a, b = (a[0][wet], b[0][wet]) if k == 'rho' else (a[1:][:, wet], b[1:][:, wet])
+        return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+    g64 = g.astype(np.float64)
+    for k in ('rho', 'v'):
+        out['gpu_vs_f64_' + k] = rel(g64, res['f64'], k)
+        out['f32oracle_vs_f64_' + k] = rel(res['f32'], res['f64'], k)
+        out['gpu_vs_f32oracle_' + k] = rel(g64, res['f32'], k)
+    out['config'] = 'ldc_3d D3Q19 BGK AA %d^3, %d steps, relative max norm over wet nodes' % (size, steps)
+    # the reference computes in fp32: the GPU must be as close to exact arithmetic as the fp32 restatement is
+    out['ok'] = bool(out['gpu_vs_f64_rho'] <= max(1e-6, 2 * out['f32oracle_vs_f64_rho']) and
+                     out['gpu_vs_f64_v'] <= max(1e-6, 2 * out['f32oracle_vs_f64_v']))
+    return out
 
 
 def main():
@@ -172,8 +352,11 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--size', type=int, default=512, help='cube edge per GPU')
     ap.add_argument('--impl', type=str, default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--cpu_budget', type=float, default=0.0, help='seconds per CPU sample (reference arm)')
     ap.add_argument('--no_cpu_baseline', action='store_true')
     ap.add_argument('--no_e2e', action='store_true')
+    ap.add_argument('--no_strong', action='store_true')
+    ap.add_argument('--no_parity', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference_arm(args)
@@ -192,57 +375,64 @@ def main():
         dist.init_process_group('cpu:gloo,cuda:nccl', device_id=torch.device('cuda', local_rank))
 
     from sailfish_b200 import backend_b200 as bk
-    from sailfish_b200.controller import LBSimulationController
-    from sailfish_b200.geo import EqualSubdomainsGeometry3D
-    from sailfish_b200.examples.ldc_3d import LDCSim
 
     S, N = args.size, max(1, ws)
-    W = max(3, args.warmup)
+    W = max(4, args.warmup + (args.warmup & 1))      # even: the timed region starts on the parity the graph was recorded on
     K = max(1, args.steps)
-    ctrl = LBSimulationController(LDCSim, EqualSubdomainsGeometry3D)
-    t_setup = time.time()
-    ctrl.setup(['--lat_nx=%d' % S, '--lat_ny=%d' % S, '--lat_nz=%d' % (S * N), '--subdomains=%d' % N,
-                '--visc=0.03175', '--access_pattern=AA', '--grid=D3Q19', '--model=bgk', '--quiet'])
-    r = ctrl.runners[0]
-    t_setup = time.time() - t_setup
     lib = bk.lib()
-    fluid_local = r.num_fluid_nodes
-    fluid_total = fluid_local
-    if ws > 1:
-        t = torch.tensor([fluid_local], dtype=torch.int64, device='cuda')
-        dist.all_reduce(t)
-        fluid_total = int(t.item())
+    failed = []
 
-    def barrier():
+    def allmax(x):
         if ws > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ctrl.sync()
+            t = torch.tensor([x], dtype=torch.float64, device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
 
-    # ---- device-resident throughput -----------------------------------------------------
-    for _ in range(W):
-        r.step(False)
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    launches0 = lib.launch_count()
-    ev0 = r.backend.make_event(r._calc_stream, timing=True)
-    for _ in range(K):
-        r.step(False)
-    ev1 = r.backend.make_event(r._calc_stream, timing=True)
-    barrier()
-    ms = ev1.time_since(ev0)
-    launches = lib.launch_count() - launches0
-    clocks = sampler.stop() if sampler else None
-    if ws > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    def allsum(x):
+        if ws > 1:
+            t = torch.tensor([x], dtype=torch.int64, device='cuda')
+            dist.all_reduce(t)
+            return int(t.item())
+        return x
+
+    def timed(ctrl, warm, steps, sampler_box=None):
+        """`warm` untimed + `steps` timed steps through the public runner (graph replay of step pairs);
+        device time on the launching stream, max over ranks."""
+        r = ctrl.runners[0]
+
+        def barrier():
+            if ws > 1 and not ctrl._local:
+                dist.barrier()
+            torch.cuda.synchronize()
+            ctrl.sync()
+        ctrl.run_steps(warm)
+        barrier()
+        if sampler_box is not None and rank == 0:
+            sampler_box.append(ClockSampler(local_rank))
+            sampler_box[0].start()
+        l0 = lib.launch_count()
+        ev0 = r.backend.make_event(r._calc_stream, timing=True)
+        ctrl.run_steps(steps)
+        ev1 = r.backend.make_event(r._calc_stream, timing=True)
+        barrier()
+        ms = ev1.time_since(ev0)
+        return (allmax(ms) if not ctrl._local else ms), lib.launch_count() - l0
+
+    # ---- weak scaling (headline): 512^3 per GPU ------------------------------------------------------
+    t_setup = time.time()
+    ctrl = make_ctrl(S, S * N, N)
+    t_setup = time.time() - t_setup
+    r = ctrl.runners[0]
+    dev = r._dev
+    fluid_local = r.num_fluid_nodes
+    fluid_total = allsum(fluid_local)
+    box = []
+    ms, launches = timed(ctrl, W, K, box)
     value = fluid_total * K / (ms * 1e-3) * 1e-6
 
     # ---- roofline of the collide kernel on this rank (whole-lattice launches, single stream) ----
-    dev = r._dev
+    ctrl.quiesce()
     for _ in range(4):
         dev.collide()
         dev.iteration += 1
@@ -254,6 +444,7 @@ def main():
         dev.iteration += 1
     e1 = r.backend.make_event(r._calc_stream, timing=True)
     ctrl.sync()
+    clocks = box[0].stop() if box else None
     kms = e1.time_since(e0) / reps
     peak, peak_src = measured_peak()
     alg_bytes = BYTES_PER_LUP['D3Q19'] * fluid_local
@@ -264,66 +455,105 @@ def main():
     tr = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tr):
         try:
-            roofline['traffic'] = json.load(open(tr)).get('dram_bytes_per_launch')
+            tj = json.load(open(tr))
+            roofline['traffic'] = tj.get('dram_bytes_per_launch')
+            roofline['traffic_source'] = tj.get('source', 'profiles/traffic.json (ncu --set full capture of this kernel)')
         except Exception:
             pass
 
     # ---- end to end: whole job with host buffers ----------------------------------------------
     e2e = None
     if not args.no_e2e:
-        barrier()
         be = r.backend
         h_map = dev.h_map
         nb_up = h_map.nbytes + dev.h_rho.nbytes + sum(a.nbytes for a in dev.h_v)
         nb_down = dev.h_rho.nbytes + sum(a.nbytes for a in dev.h_v)
-        # pinned staging copy of the map (fields are pinned already)
-        p_map = be.alloc_async_host_buf(h_map.shape, np.uint32)
+        p_map = be.alloc_async_host_buf(h_map.shape, np.uint32)     # pinned staging copy of the map
         p_map[:] = h_map
+        ctrl.quiesce()                      # everybody idle: the neighbours' pushes of the last step have landed
         t0 = time.time()
         ee0 = be.make_event(r._calc_stream, timing=True)
         lib.call('slf_memcpy_h2d_async', int(dev.d_map), p_map.ctypes.data, p_map.nbytes, r._calc_stream.handle)
-        be.to_buf_async(dev.d_rho, r._calc_stream)
-        for b in dev.d_v:
-            be.to_buf_async(b, r._calc_stream)
-        dev.set_initial_conditions()
-        r._sim.iteration = 0
-        for k in range(K):
-            r.step(k == K - 1)
+        r.reinitialize(upload=True)         # rho, v: pinned host -> device, SetInitialConditions
+        if ws > 1:
+            ctrl.quiesce()                  # nobody pushes into a lattice that is still being initialised
+        ctrl.run_steps(K, save_last=True)
         be.from_buf_async(dev.d_rho, r._calc_stream)
         for b in dev.d_v:
             be.from_buf_async(b, r._calc_stream)
         ee1 = be.make_event(r._calc_stream, timing=True)
-        barrier()
-        e_ms = ee1.time_since(ee0)
+        ctrl.quiesce()
+        e_ms = allmax(ee1.time_since(ee0))
         wall = time.time() - t0
-        if ws > 1:
-            t = torch.tensor([e_ms], dtype=torch.float64, device='cuda')
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e_ms = float(t.item())
-        finite = bool(np.isfinite(np.asarray(dev.h_rho)[r._spec._nonghost_slice][r._subdomain.fluid_map()]).all())
+        f, wet = host_fields(r)
+        finite = allsum(0 if bool(np.isfinite(f[:, wet]).all()) else 1) == 0
+        if not finite:
+            failed.append('e2e result non-finite')
         e2e = {'value': fluid_total * K / (e_ms * 1e-3) * 1e-6, 'unit': 'MLUPS',
                'h2d_bytes_per_step': int(nb_up // K), 'd2h_bytes_per_step': int(nb_down // K),
+               'bytes_note': 'whole-job copies (%d B up, %d B down per GPU) divided by the %d steps' % (nb_up, nb_down, K),
                'job': 'pinned host map+rho+v -> device, SetInitialConditions, %d steps, rho+v -> host' % K,
                'ms_job': e_ms, 'wall_ms_job': wall * 1e3, 'result_finite': finite}
 
+    # ---- correctness of THIS run ---------------------------------------------------------------------
+    parity = {}
+    if not args.no_parity:
+        if ws > 1:
+            parity['decomposition'] = verify_decomposition(ctrl, S, S * N, dist)
+            if not parity['decomposition']['ok']:
+                failed.append('weak-scaling run differs from the single-subdomain run')
+        if rank == 0:
+            parity['oracle'] = verify_oracle()
+            if not parity['oracle']['ok']:
+                failed.append('GPU vs oracle out of tolerance')
+
+    # ---- strong scaling: BASELINE config 4, the 512^3 cavity split N ways --------------------------------
+    strong = None
+    if ws > 1 and not args.no_strong:
+        sctrl = make_ctrl(S, S, N)
+        s_fluid = allsum(sctrl.runners[0].num_fluid_nodes)
+        s_ms, _ = timed(sctrl, W, K)
+        strong = {'value': s_fluid * K / (s_ms * 1e-3) * 1e-6, 'unit': 'MLUPS', 'ms_per_step': s_ms / K,
+                  'workload': 'examples/ldc_3d D3Q19 BGK AA, global %d^3 split into %d z-slabs of %d layers'
+                              % (S, N, S // N), 'fluid_nodes': s_fluid, 'scaling': 'strong'}
+        if not args.no_parity:
+            strong['parity'] = verify_decomposition(sctrl, S, S, dist)
+            if not strong['parity']['ok']:
+                failed.append('strong-scaling run differs from the single-subdomain run')
+        # the same lattice on ONE GPU, measured in this job on rank 0 (the other ranks wait)
+        if rank == 0:
+            one = make_ctrl(S, S, 1, local=True)
+            o_ms, _ = timed(one, W, K)
+            o_val = one.runners[0].num_fluid_nodes * K / (o_ms * 1e-3) * 1e-6
+            strong['one_gpu_value'] = o_val
+            strong['speedup_vs_one_gpu'] = strong['value'] / o_val
+        dist.barrier()
+
     if rank != 0:
-        return
+        if ws > 1:
+            dist.barrier()
+        sys.exit(1 if failed else 0)
     cpu = None
     if not args.no_cpu_baseline:
-        mlups, cores, sample = cpu_run(cpu_sample_size(), 12.0)
-        cpu = {'value': mlups, 'unit': 'MLUPS', 'cores': cores, 'kind': 'port', 'sample': sample}
+        cpu = cpu_baseline_subprocess()
     line = {
         'metric': 'MLUPS D3Q19 BGK', 'value': value, 'unit': 'MLUPS', 'n_gpus': N, 'steps': K, 'warmup': W,
         'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'examples/ldc_3d D3Q19 BGK, AA access pattern, %d^3 per GPU (global %dx%dx%d, z-split)'
-                               % (S, S, S, S * N),
-                   'visc': 0.03175, 'l2': 'lattice (%.1f GB/GPU) is larger than L2, no flush needed'
-                                          % (19 * 4 * dev.n / 1e9),
-                   'fluid_nodes': fluid_total, 'setup_s': round(t_setup, 1)},
+        'config': {'workload': workload_name(S, N), 'visc': VISC,
+                   'l2': 'lattice (%.1f GB/GPU) is larger than L2, no flush needed' % (19 * 4 * dev.n / 1e9),
+                   'fluid_nodes': fluid_total, 'setup_s': round(t_setup, 1),
+                   'stepping': 'CUDA-graph replay of step pairs (N=1: slf_run_steps; N>1: recorded from SubdomainRunner.step)'},
         'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
+        'parity': parity, 'strong': strong,
     }
+    if failed:
+        line['failed'] = failed
     print(json.dumps(line))
+    sys.stdout.flush()
+    if ws > 1:
+        dist.barrier()
+    sys.exit(1 if failed else 0)
 
 
 if __name__ == '__main__':

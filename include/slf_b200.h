@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SLF_ABI_VERSION 3
+#define SLF_ABI_VERSION 4
 
 /* error codes (negative; positive values are cudaError_t) */
 #define SLF_EINVAL      (-1)   /* bad argument / unsupported configuration          */
@@ -278,14 +278,34 @@ int  slf_distribute_continuous_macro_data(SlfPlan *plan, uint64_t field, int fac
  *   with_swap   1 after an AA even (in-place) step: first real layer, opposite slots ->
  *               neighbour's ghost layer; 0 after AB / AA-odd steps: ghost layer, natural
  *               slots -> neighbour's first real layer (the reference's WithSwap variants).
+ *   signal_sem  0, or the neighbour's `ready` word (peer pointer): the last block of the copy
+ *               kernel increments it after a system-scope fence, so copy + signal are one launch.
  */
 int  slf_halo_push(SlfPlan *plan, uint64_t dist, int face, uint64_t peer_dist, int peer_lat_n,
-                   int peer_arr_n, int with_swap, uint64_t stream);
-/* Stream-ordered counting semaphores in device memory for cross-GPU ordering of the pushes:
- * signal = system-scope fence + atomic increment of `sem` (may be a peer pointer);
- * wait   = spin until *sem > *consumed, then ++*consumed (both local uint32). */
+                   int peer_arr_n, int with_swap, uint64_t signal_sem, uint64_t stream);
+/* Stream-ordered counting semaphores in device memory for cross-GPU ordering of the pushes
+ * (they stand where the reference blocks in zmq recv, connector.py:73-117).  A subdomain owns a
+ * zero-initialised block of uint32 words: ready[channel][side] (incremented by the neighbour on
+ * that side after each push), seq[channel] (steps waited for so far) and two status words.
+ *   signal: system-scope fence + atomic increment of `sem` (a peer pointer);
+ *   wait  : spin (acquire loads, system scope) until ready_a and ready_b (either may be 0) have
+ *           reached *seq + ahead (ahead = 0: pushes of the previous steps, the population planes;
+ *           ahead = 1: of this step too, the mid-step field exchange), then ++*seq.  Nothing is ever reset: re-initialising or restoring a run
+ *           only needs a host barrier.  A wait that lasts longer than SLF_SEM_TIMEOUT_MS (default
+ *           30000) or sees status[1] != 0 stores 1 (timeout) / 2 (aborted) in status[0] and returns;
+ *   status: blocking read of status[0] on a private stream;  abort: sets status[1]. */
 int  slf_sem_signal(uint64_t sem, uint64_t stream);
-int  slf_sem_wait(uint64_t sem, uint64_t consumed, uint64_t stream);
+int  slf_sem_wait(uint64_t ready_a, uint64_t ready_b, uint64_t seq, uint64_t status, int ahead, uint64_t stream);
+int  slf_sem_status(uint64_t status, uint32_t *err);
+int  slf_sem_abort(uint64_t status);
+
+/* Stream capture for step replay of linked subdomains (SubdomainRunner.main() pays ~10 Python calls
+ * per step, subdomain_runner.py:1673-1748): everything issued on `stream` (and on streams forked from
+ * it with events) between begin and end is recorded instead of run; launch replays it. */
+int  slf_graph_begin_capture(uint64_t stream);
+int  slf_graph_end_capture(uint64_t stream, uint64_t *graph_exec);
+int  slf_graph_launch(uint64_t graph_exec, uint64_t stream);
+int  slf_graph_destroy(uint64_t graph_exec);
 
 /* CUDA IPC handles for the above (backend_cuda.py:122-126 wraps them but never calls them) */
 int  slf_ipc_get_handle(uint64_t dptr, void *handle64);      /* 64 bytes */

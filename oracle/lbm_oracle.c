@@ -37,7 +37,9 @@
  *   save_macro_fields                kernel_common.mako:213-240
  *   propagate                        propagation.mako:384-421 (+ :12-60 bounds)
  */
+#define _GNU_SOURCE
 #include <math.h>
+#include <sched.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -791,6 +793,32 @@ int orc_distribute_continuous_macro_data(const SlfParams *P, REAL *field, int fa
 }
 
 int orc_sizeof_real(void) { return (int)sizeof(REAL); }
+
+/* CPU-baseline plumbing (bench.py): the OpenMP runtime may have been initialised by another library
+ * with OMP_NUM_THREADS=1 (torchrun exports that), so the thread count is set -- and reported -- here,
+ * and each thread is pinned to one of the CPUs the process may use (first touch in
+ * orc_set_initial_conditions then places every thread's rows on its own NUMA node). */
+#ifdef _OPENMP
+#include <omp.h>
+int orc_omp_config(int nthreads, const int *cpus, int ncpu) {
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+  int used = 1;
+#pragma omp parallel
+  {
+#pragma omp single
+    used = omp_get_num_threads();
+    if (cpus && ncpu > 0) {
+      cpu_set_t one;
+      CPU_ZERO(&one);
+      CPU_SET(cpus[omp_get_thread_num() % ncpu], &one);
+      sched_setaffinity(0, sizeof(one), &one);
+    }
+  }
+  return used;
+}
+#else
+int orc_omp_config(int nthreads, const int *cpus, int ncpu) { (void)nthreads; (void)cpus; (void)ncpu; return 1; }
+#endif
 
 /* ------------------------------------------------------------------------------------
  * Formula-level hooks for tests/test_oracle_formulas.py (golden: tests/golden/formulas.npz,

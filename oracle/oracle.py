@@ -34,6 +34,18 @@ def _lib(dtype):
     return _LIBS[key]
 
 
+# the CPUs this process may use, read before any thread is pinned (pinning the main thread shrinks
+# what sched_getaffinity reports afterwards)
+HOST_CPUS = sorted(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else list(range(os.cpu_count() or 1))
+
+
+def omp_config(nthreads=0, pin=True, dtype=np.float32):
+    """Sets the OpenMP thread count of the oracle library (0 = leave), pins thread k to the k-th CPU the
+    process may use and returns the number of threads a parallel region really gets."""
+    cpus = (ctypes.c_int * len(HOST_CPUS))(*HOST_CPUS)
+    return int(_lib(dtype).orc_omp_config(int(nthreads), cpus if pin else None, len(HOST_CPUS) if pin else 0))
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 

@@ -72,9 +72,15 @@ _PROTOTYPES = {
     'slf_distribute_continuous_macro_data': [_vp, _u64, _i, _i, _i, _i, _i, _u64, _u64],
     'slf_collect_sparse_data': [_vp, _u64, _u64, _u64, _i, _u64],
     'slf_distribute_sparse_data': [_vp, _u64, _u64, _u64, _i, _u64],
-    'slf_halo_push': [_vp, _u64, _i, _u64, _i, _i, _i, _u64],
+    'slf_halo_push': [_vp, _u64, _i, _u64, _i, _i, _i, _u64, _u64],
     'slf_sem_signal': [_u64, _u64],
-    'slf_sem_wait': [_u64, _u64, _u64],
+    'slf_sem_wait': [_u64, _u64, _u64, _u64, _i, _u64],
+    'slf_sem_status': [_u64, ctypes.POINTER(_u32)],
+    'slf_sem_abort': [_u64],
+    'slf_graph_begin_capture': [_u64],
+    'slf_graph_end_capture': [_u64, ctypes.POINTER(_u64)],
+    'slf_graph_launch': [_u64, _u64],
+    'slf_graph_destroy': [_u64],
     'slf_ipc_get_handle': [_u64, _vp],
     'slf_ipc_open_handle': [_vp, ctypes.POINTER(_u64)],
     'slf_ipc_close_handle': [_u64],
@@ -110,7 +116,7 @@ class Lib(object):
             fn = getattr(self.cdll, name)
             fn.argtypes = argtypes
             fn.restype = restype
-        if self.cdll.slf_abi_version() != 3:
+        if self.cdll.slf_abi_version() != 4:
             raise B200Error('ABI version mismatch')
 
     def call(self, name, *args):

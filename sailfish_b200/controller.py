@@ -68,6 +68,7 @@ class LBSimulationController(object):
         if default_config is not None:
             self._parser.set_defaults(default_config)
         self.runners = []
+        self._local = False
 
     # -- set-up --------------------------------------------------------------------------------
     def _make_specs(self):
@@ -92,10 +93,15 @@ class LBSimulationController(object):
         return specs
 
     def _distributed(self):
+        if self._local:
+            return False, 0, 1, int(os.environ.get('LOCAL_RANK', '0'))
         ws = int(os.environ.get('WORLD_SIZE', '1'))
         return ws > 1, int(os.environ.get('RANK', '0')), ws, int(os.environ.get('LOCAL_RANK', '0'))
 
-    def setup(self, args=None):
+    def setup(self, args=None, local=False):
+        """local=True: this process drives every subdomain of the geometry itself on its own GPU even under
+        torchrun (verification runs beside a distributed job)."""
+        self._local = bool(local)
         self.config = self._parser.parse(list(args or []))
         self._lb_class.modify_config(self.config)
         np.random.seed(self.config.seed)
@@ -111,6 +117,8 @@ class LBSimulationController(object):
             mine = specs
             ngpu = max(1, bk.B200Backend.devices_count())
             gpus = [g for g in self.config.gpus if g < ngpu] or [0]
+            if self._local:
+                gpus = [local_rank]
             devices = dict((s.id, gpus[i % len(gpus)]) for i, s in enumerate(specs))
         if len(set(devices.values())) > 1:
             raise NotImplementedError('one process drives one GPU; use torchrun for multi-GPU runs')
@@ -125,6 +133,8 @@ class LBSimulationController(object):
             if self.config.restore_from:
                 r.restore_checkpoint(checkpoint_path(self.config.restore_from, r._spec.id))
         self._link(dist_mode, rank, ws)
+        for r in self.runners:
+            r._pre_checkpoint = self.quiesce
         # nobody may push into a neighbour's buffers before that neighbour has finished uploading and
         # initialising them
         self.sync()
@@ -174,6 +184,21 @@ class LBSimulationController(object):
             self.sync()
             self._dist.barrier()
 
+    def quiesce(self):
+        """Every local stream drained and every rank here: no halo plane is in flight anywhere."""
+        self.sync()
+        self.barrier()
+
+    def reinitialize(self, upload=True, reset_fields=False):
+        """Restarts the run from the host fields (rho, v[, phi]) on every subdomain.  The neighbours write
+        into each other's lattices, so nobody may start stepping (and pushing) before everybody has finished
+        re-initialising, and nobody may re-initialise before everybody has stopped stepping: rendezvous on
+        both sides.  The device semaphores need no reset (csrc/slf_halo.cuh)."""
+        self.quiesce()
+        for r in self.runners:
+            r.reinitialize(upload, reset_fields)
+        self.quiesce()
+
     def step_all(self, sync_req=False):
         """One time step on every local subdomain, phase by phase (a phase may end with an exchange
         the next phase of the *neighbours* depends on)."""
@@ -181,12 +206,12 @@ class LBSimulationController(object):
             for r in self.runners:
                 getattr(r, ph)(sync_req)
 
-    def run_steps(self, n):
+    def run_steps(self, n, save_last=False):
         if len(self.runners) == 1:
-            self.runners[0].run_steps(n)
+            self.runners[0].run_steps(n, save_last=save_last)
         else:
-            for _ in range(n):
-                self.step_all(False)
+            for k in range(n):
+                self.step_all(save_last and k == n - 1)
 
     def sync(self):
         for r in self.runners:

@@ -21,9 +21,6 @@ int slf_fail(int code, const std::string &msg) {
 }
 void slf_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-struct StepGraphKey { uint64_t map, a, b, rho; int parity; };
-struct StepGraph { StepGraphKey key; cudaGraphExec_t exec; uint64_t kernels; };
-static std::vector<std::pair<SlfPlan *, StepGraph>> g_graphs;
 
 
 extern "C" {
@@ -188,11 +185,14 @@ int slf_plan_create(const SlfParams *p, SlfPlan **out) {
   e = cudaMemcpy(pl->d_node_params, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { cudaFree(pl->d_node_params); delete pl; return fail((int)e, cudaGetErrorString(e)); }
   d.node_params = pl->d_node_params;
+  e = cudaMalloc((void **)&pl->d_push_done, 4 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(pl->d_push_done, 0, 4 * sizeof(unsigned int));
+  if (e != cudaSuccess) { cudaFree(pl->d_node_params); delete pl; return fail((int)e, cudaGetErrorString(e)); }
   *out = pl;
   return 0;
 }
 
-static void purge_graphs(const SlfPlan *plan);
+static void purge_graphs(SlfPlan *plan);
 
 int slf_plan_set_links(SlfPlan *plan, int link_low, int link_high) {
   if (!plan) return fail(SLF_EINVAL, "null plan");
@@ -202,11 +202,10 @@ int slf_plan_set_links(SlfPlan *plan, int link_low, int link_high) {
 }
 
 // Step graphs capture kernel arguments by value (mask pointers, link flags): drop them whenever those change.
-static void purge_graphs(const SlfPlan *plan) {
-  for (size_t k = 0; k < g_graphs.size();) {
-    if (g_graphs[k].first == plan) { cudaGraphExecDestroy(g_graphs[k].second.exec); g_graphs.erase(g_graphs.begin() + k); }
-    else k++;
-  }
+static void purge_graphs(SlfPlan *plan) {
+  std::lock_guard<std::mutex> lock(plan->graph_mutex);
+  for (auto &g : plan->graphs) cudaGraphExecDestroy(g.exec);
+  plan->graphs.clear();
 }
 
 int slf_plan_destroy(SlfPlan *plan) {
@@ -216,6 +215,7 @@ int slf_plan_destroy(SlfPlan *plan) {
   if (plan->d_fluid_mask) cudaFree(plan->d_fluid_mask);
   if (plan->d_wall_mask) cudaFree(plan->d_wall_mask);
   if (plan->d_list) cudaFree(plan->d_list);
+  if (plan->d_push_done) cudaFree(plan->d_push_done);
   delete plan;
   return 0;
 }
@@ -232,10 +232,6 @@ int slf_plan_bind_map(SlfPlan *pl, uint64_t map) {
   const DevParams &d = pl->dp;
   if (d.DS >= (1ll << 32)) return fail(SLF_EUNSUPPORTED, "node lists use 32-bit indices");
   pl->bound_map = 0;
-  for (size_t k = 0; k < g_graphs.size();) {    // captured launches hold the old mask/list pointers
-    if (g_graphs[k].first == pl) { cudaGraphExecDestroy(g_graphs[k].second.exec); g_graphs.erase(g_graphs.begin() + k); }
-    else k++;
-  }
   if (!map) return 0;
   std::vector<uint32_t> h((size_t)d.DS);
   CUDA_OK(cudaMemcpy(h.data(), (const void *)map, (size_t)d.DS * 4, cudaMemcpyDeviceToHost));
@@ -510,10 +506,11 @@ int slf_run_steps(SlfPlan *pl, uint64_t map, uint64_t dist_a, uint64_t dist_b, u
   const int plain = nsteps - (save_last ? 1 : 0);       // steps that may be replayed from a graph
   if (plain >= 4 && s != 0) {
     const int parity = iteration & 1;
+    std::lock_guard<std::mutex> lock(pl->graph_mutex);
     StepGraph *g = nullptr;
-    for (auto &e : g_graphs)
-      if (e.first == pl && e.second.key.map == map && e.second.key.a == dist_a && e.second.key.b == dist_b &&
-          e.second.key.rho == rho && e.second.key.parity == parity) g = &e.second;
+    for (auto &e : pl->graphs)
+      if (e.key.map == map && e.key.a == dist_a && e.key.b == dist_b && e.key.rho == rho && e.key.parity == parity)
+        g = &e;
     if (!g) {
       const uint64_t before = slf_launch_count();
       cudaGraph_t graph;
@@ -528,8 +525,8 @@ int slf_run_steps(SlfPlan *pl, uint64_t map, uint64_t dist_a, uint64_t dist_b, u
       ng.kernels = slf_launch_count() - before;          // kernels captured (counted, not yet run)
       CUDA_OK(cudaGraphInstantiate(&ng.exec, graph, 0));
       cudaGraphDestroy(graph);
-      g_graphs.push_back({pl, ng});
-      g = &g_graphs.back().second;
+      pl->graphs.push_back(ng);
+      g = &pl->graphs.back();
       for (uint64_t k = 0; k < ng.kernels; k++) g_launches.fetch_sub(1, std::memory_order_relaxed);
     }
     const int pairs = plain / 2;
@@ -543,6 +540,50 @@ int slf_run_steps(SlfPlan *pl, uint64_t map, uint64_t dist_a, uint64_t dist_b, u
     int rc = one_step(pl, map, dist_a, dist_b, rho, vx, vy, vz, iteration + k, save_last && k == nsteps - 1, stream);
     if (rc) return rc;
   }
+  return 0;
+}
+
+// ---- generic stream capture: the host-side runner records whatever its step() issues (collide slabs,
+// semaphore waits, plane pushes, fork/join events across its two streams) once per step parity and
+// replays it; every kernel argument depends on the iteration only through its parity, and the
+// semaphore kernels read their targets from device memory. ------------------------------------
+struct SlfGraph { cudaGraphExec_t exec; uint64_t kernels; };
+static thread_local uint64_t t_capture_base = 0;
+
+int slf_graph_begin_capture(uint64_t stream) {
+  t_capture_base = slf_launch_count();
+  CUDA_OK(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal));
+  return 0;
+}
+
+int slf_graph_end_capture(uint64_t stream, uint64_t *graph_exec) {
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture((cudaStream_t)stream, &graph);
+  const uint64_t kernels = slf_launch_count() - t_capture_base;
+  for (uint64_t k = 0; k < kernels; k++) g_launches.fetch_sub(1, std::memory_order_relaxed);   // recorded, not run
+  if (ce != cudaSuccess) { cudaGetLastError(); return fail((int)ce, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce)); }
+  SlfGraph *g = new SlfGraph();
+  g->kernels = kernels;
+  ce = cudaGraphInstantiate(&g->exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) { delete g; return fail((int)ce, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); }
+  *graph_exec = (uint64_t)g;
+  return 0;
+}
+
+int slf_graph_launch(uint64_t graph_exec, uint64_t stream) {
+  SlfGraph *g = (SlfGraph *)graph_exec;
+  if (!g) return fail(SLF_EINVAL, "null graph");
+  CUDA_OK(cudaGraphLaunch(g->exec, (cudaStream_t)stream));
+  g_launches.fetch_add(g->kernels, std::memory_order_relaxed);
+  return 0;
+}
+
+int slf_graph_destroy(uint64_t graph_exec) {
+  SlfGraph *g = (SlfGraph *)graph_exec;
+  if (!g) return 0;
+  cudaGraphExecDestroy(g->exec);
+  delete g;
   return 0;
 }
 

@@ -5,19 +5,37 @@
 // (subdomain_runner.py:1064-1139, kernel_utils.mako:526-794, connector.py:73-117).  With the
 // SoA layout a face message is |dists| whole planes that are already contiguous in the
 // lattice array, so "pack" and "unpack" disappear: one kernel copies the planes straight
-// from this GPU's lattice into the neighbour's lattice through the peer pointer.
+// from this GPU's lattice into the neighbour's lattice through the peer pointer and, when its
+// last block is done, raises the neighbour's `ready` counter (copy + signal are ONE launch).
 // Layer/slot selection follows the reference exactly:
 //   after an AB or AA-odd step : ghost layer, natural slots  -> neighbour's first real layer
 //   after an AA-even step      : first real layer, opposite slots -> neighbour's ghost layer
 // (lat_linear / lat_linear_macro / lat_linear_dist / lat_linear_with_swap,
 //  subdomain_runner.py:488-510).
+//
+// Ordering protocol (one semaphore block of SLF_SEM_WORDS uint32 per subdomain, zeroed once):
+//   ready[ch][side]  incremented by the neighbour on that side after each of its pushes on
+//                    channel ch (0: populations, 1: macroscopic fields);
+//   seq[ch]          number of steps this subdomain has waited for on channel ch.
+// Step s of a subdomain needs the neighbours' population pushes of their steps 0..s-1, i.e.
+// ready >= seq (fields, exchanged in mid-step: those of step s too, ready >= seq + 1 = `ahead`);
+// the wait kernel spins on that (acquire loads at system scope), then ++seq.  Both counters only
+// ever grow and are compared as differences, so a run may be re-initialised, restored from a
+// checkpoint or continued any number of times without resetting anything -- all that is needed
+// around a re-initialisation is a host-side barrier (every rank idle) before and after it.
+// A wait that exceeds the time limit (a dead or diverged peer) or sees the abort word set
+// records an error in status[0] and RETURNS: the stream drains and the host reports the error
+// at its next synchronisation instead of hanging in an uncancellable kernel.
 #pragma once
+#include <cstdlib>
 
 struct HaloArgs {
   const float *src[9];
   float *dst[9];
-  int n;                 // number of planes
-  long long plane;       // floats per plane (multiple of 4)
+  int n;                      // number of planes
+  long long plane;            // floats per plane (multiple of 4)
+  unsigned int *signal;       // neighbour's ready word (peer pointer) or null
+  unsigned int *done;         // local block counter for the last-block-signals pattern
 };
 
 __global__ void __launch_bounds__(256) halo_push_kernel(const HaloArgs a) {
@@ -28,6 +46,18 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const HaloArgs a) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
     d[i] = s[i];
   __threadfence_system();
+  if (a.signal) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int total = gridDim.x * gridDim.y;
+      const unsigned int prev = atomicAdd(a.done, 1u);
+      if (prev == total - 1u) {
+        *a.done = 0u;                     // ready for the next launch (launches on one stream are ordered)
+        __threadfence_system();
+        atomicAdd_system(a.signal, 1u);
+      }
+    }
+  }
 }
 
 __global__ void sem_signal_kernel(unsigned int *sem) {
@@ -35,17 +65,54 @@ __global__ void sem_signal_kernel(unsigned int *sem) {
   atomicAdd_system(sem, 1u);
 }
 
-__global__ void sem_wait_kernel(volatile unsigned int *sem, unsigned int *consumed) {
-  const unsigned int want = *consumed + 1u;
-  while (*sem < want) { __nanosleep(200); }
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// status[0]: error (0 ok, 1 timeout, 2 aborted), status[1]: abort request (host-settable)
+__global__ void sem_wait_kernel(const unsigned int *ready_a, const unsigned int *ready_b, unsigned int *seq,
+                                unsigned int *status, unsigned int ahead, unsigned long long timeout_ns) {
+  const unsigned int want = *seq + ahead;
+  const unsigned int *r[2] = {ready_a, ready_b};
+  const unsigned long long t0 = global_timer_ns();
+  unsigned int err = 0;
+  for (int k = 0; k < 2 && !err; k++) {
+    if (!r[k]) continue;
+    unsigned int spins = 0;
+    while ((int)(ld_acquire_sys(r[k]) - want) < 0) {
+      __nanosleep(64);
+      if ((++spins & 63u) == 0) {
+        if (ld_acquire_sys(status + 1)) { err = 2; break; }
+        if (global_timer_ns() - t0 > timeout_ns) { err = 1; break; }
+      }
+    }
+  }
+  if (err) atomicCAS(status, 0u, err);
   __threadfence_system();
-  *consumed = want;
+  *seq = want + 1u - ahead;
+}
+
+static unsigned long long sem_timeout_ns() {
+  static unsigned long long v = 0;
+  if (!v) {
+    const char *e = getenv("SLF_SEM_TIMEOUT_MS");
+    const double ms = e ? atof(e) : 30000.0;
+    v = (unsigned long long)((ms > 1.0 ? ms : 1.0) * 1e6);
+  }
+  return v;
 }
 
 extern "C" {
 
 int slf_halo_push(SlfPlan *pl, uint64_t dist, int face, uint64_t peer_dist, int peer_lat_n, int peer_arr_n,
-                  int with_swap, uint64_t stream) {
+                  int with_swap, uint64_t signal_sem, uint64_t stream) {
   if (!pl) return fail(SLF_EINVAL, "null plan");
   const DevParams &d = pl->dp;
   const int axis = pl->D - 1;                   // outermost axis
@@ -59,6 +126,9 @@ int slf_halo_push(SlfPlan *pl, uint64_t dist, int face, uint64_t peer_dist, int 
   const int dst_layer = with_swap ? (hi ? 0 : peer_lat_n - 1) : (hi ? 1 : peer_lat_n - 2);
   HaloArgs a;
   a.n = 0; a.plane = plane;
+  a.signal = (unsigned int *)signal_sem;
+  a.done = nullptr;
+  if (signal_sem) a.done = pl->d_push_done + hi;
   const int sgn = hi ? 1 : -1;
   const int Q = pl->Q;
   for (int i = 0; i < Q; i++) {
@@ -93,7 +163,7 @@ int slf_halo_push_field(SlfPlan *pl, uint64_t field, int face, uint64_t peer_fie
   const long long plane = axis == 2 ? d.sz : d.sy;
   if (plane % 4) return fail(SLF_EINVAL, "plane size must be a multiple of 4 floats");
   HaloArgs a;
-  a.n = 1; a.plane = plane;
+  a.n = 1; a.plane = plane; a.signal = nullptr; a.done = nullptr;
   a.src[0] = (const float *)field + plane * (hi ? n - 2 : 1);             // first / last real layer
   a.dst[0] = (float *)peer_field + plane * (hi ? 0 : peer_lat_n - 1);     // neighbour's ghost layer
   const long long n4 = plane / 4;
@@ -110,9 +180,37 @@ int slf_sem_signal(uint64_t sem, uint64_t stream) {
   return 0;
 }
 
-int slf_sem_wait(uint64_t sem, uint64_t consumed, uint64_t stream) {
-  sem_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((volatile unsigned int *)sem, (unsigned int *)consumed);
+int slf_sem_wait(uint64_t ready_a, uint64_t ready_b, uint64_t seq, uint64_t status, int ahead, uint64_t stream) {
+  if (!seq || !status) return fail(SLF_EINVAL, "null semaphore block");
+  if (!ready_a && !ready_b) return 0;
+  sem_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const unsigned int *)ready_a, (const unsigned int *)ready_b,
+                                                     (unsigned int *)seq, (unsigned int *)status, ahead ? 1u : 0u, sem_timeout_ns());
   LAUNCH_OK("sem_wait");
+  return 0;
+}
+
+// Blocking 4-byte reads/writes of the status words on a private stream (the compute streams may
+// be busy -- or stuck in a wait -- when the host looks).
+static cudaStream_t sem_side_stream() {
+  static cudaStream_t s = nullptr;
+  if (!s) cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+  return s;
+}
+
+int slf_sem_status(uint64_t status, uint32_t *err) {
+  if (!status || !err) return fail(SLF_EINVAL, "null argument");
+  cudaStream_t s = sem_side_stream();
+  CUDA_OK(cudaMemcpyAsync(err, (const void *)status, 4, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int slf_sem_abort(uint64_t status) {
+  if (!status) return fail(SLF_EINVAL, "null argument");
+  static const uint32_t one = 1;
+  cudaStream_t s = sem_side_stream();
+  CUDA_OK(cudaMemcpyAsync((void *)(status + 4), &one, 4, cudaMemcpyHostToDevice, s));
+  CUDA_OK(cudaStreamSynchronize(s));
   return 0;
 }
 

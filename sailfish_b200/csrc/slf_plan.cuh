@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -24,6 +25,10 @@ void slf_count_launch();
     slf_count_launch();                                                                       \
   } while (0)
 
+// step-pair graphs of slf_run_steps, owned by the plan (guarded by SlfPlan::graph_mutex)
+struct StepGraphKey { uint64_t map, a, b, rho; int parity; };
+struct StepGraph { StepGraphKey key; cudaGraphExec_t exec; uint64_t kernels; };
+
 struct SlfPlan {
   SlfParams hp;
   DevParams dp;
@@ -34,6 +39,9 @@ struct SlfPlan {
   uint32_t *d_fluid_mask = nullptr, *d_wall_mask = nullptr, *d_list = nullptr;
   std::vector<long long> layer_off;    // list offsets per outermost-axis layer (size n + 1)
   int link_lo = 0, link_hi = 0;        // neighbours across the low / high face of the split axis
+  std::vector<StepGraph> graphs;
+  std::mutex graph_mutex;
+  unsigned int *d_push_done = nullptr; // block counters of halo_push_kernel (last block signals), [2]
 };
 
 // one per lattice, each in its own translation unit (slf_collide_*.cu) so they build in parallel

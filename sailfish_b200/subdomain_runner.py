@@ -56,17 +56,18 @@ class HaloLink(object):
         self.my_sems = int(my_sems)
         self.peer_runner = peer_runner
 
-    # semaphore block layout (uint32 words): channel c in {0: populations, 1: macro fields}
-    #   ready[c][side] at 8*c + side, consumed[c][side] at 8*c + 2 + side
+    # semaphore block layout (uint32 words, csrc/slf_halo.cuh): channel c in {0: populations, 1: macro fields}
+    #   ready[c][side] at 8*c + side, seq[c] at 8*c + 2; status (error, abort) at 16, 17
     def my_ready(self, channel):
         return self.my_sems + 4 * (8 * channel + self.side)
-
-    def my_consumed(self, channel):
-        return self.my_sems + 4 * (8 * channel + 2 + self.side)
 
     def peer_ready(self, channel):
         # the neighbour receives through its opposite side
         return self.peer_sems + 4 * (8 * channel + (1 - self.side))
+
+
+SEM_BYTES = 256
+SEM_STATUS_WORD = 16
 
 
 class LBOutput(object):
@@ -126,7 +127,8 @@ class SubdomainRunner(object):
         self._scalar_fields, self._vector_fields = [], []
         self._field_base = {}
         self._links = {}
-        self._first_iteration = 0      # no neighbour has pushed anything before this step (0 or a restored value)
+        self._graphs = {}              # step parity -> captured pair of steps (linked subdomains)
+        self._pre_checkpoint = None    # set by the controller: quiesce all subdomains / ranks
         self._lib = bk.lib()
         self.float = np.float32
         if getattr(self.config, 'precision', 'single') != 'single':
@@ -203,9 +205,14 @@ class SubdomainRunner(object):
                                   host_fields=(self.field_base(sim.rho), [self.field_base(c) for c in sim.v]))
         self._calc_stream = self._dev.stream
         self._data_stream = self.backend.make_stream(high_priority=True)
-        self._sems = self.backend.alloc_buf(size=128)     # see HaloLink for the layout
+        self._init_sync_objects()
+
+    def _init_sync_objects(self):
+        self._sems = self.backend.alloc_buf(size=SEM_BYTES)     # see HaloLink for the layout
+        self._lib.call('slf_memset', int(self._sems), 0, SEM_BYTES, 0)
+        self._lib.call('slf_sync')
         self._push_events = [[self.backend.make_event(self._data_stream) for _ in range(2)] for _ in range(2)]
-        self._slab_event = self.backend.make_event(self._calc_stream)
+        self._fork_event = self.backend.make_event(self._calc_stream)
 
     def initialize(self):
         self._init_fields()
@@ -254,6 +261,12 @@ class SubdomainRunner(object):
     def save_checkpoint(self):
         import pickle
         cfg = self.config
+        # A neighbour's push of the step just finished lands in THIS lattice from the neighbour's stream
+        # (or rank); it is only awaited at the start of the next step.  Quiesce every subdomain and rank
+        # first, otherwise the file may miss one step of boundary data (all subdomains checkpoint at the
+        # same iterations, so the rendezvous is collective-safe).
+        if self._links and self._pre_checkpoint is not None:
+            self._pre_checkpoint()
         if getattr(cfg, 'single_checkpoint', False):
             fname = checkpoint_filename(cfg.checkpoint_file, 1, self._spec.id, 0)
         else:
@@ -273,7 +286,7 @@ class SubdomainRunner(object):
         self._sim.set_state(pickle.loads(cp['state'].tobytes()))
         if not getattr(self.config, 'restore_time', True):
             self._sim.iteration = 0
-        self._dev.iteration = self._first_iteration = self._sim.iteration
+        self._dev.iteration = self._sim.iteration
         for k in cp.files:
             if k.startswith('dist'):
                 self._debug_set_dist(cp[k], k.endswith('a'), int(k[4:-1]))
@@ -291,25 +304,84 @@ class SubdomainRunner(object):
 
     def add_link(self, link):
         self._links[link.face & 1] = link
+        self._drop_graphs()
         self._lib.call('slf_plan_set_links', self._dev.plan, int(0 in self._links), int(1 in self._links))
 
     def _outer_n(self):
         return self._lat_size[0]
 
+    def _uses_semaphores(self):
+        return bool(self._links) and all(l.peer_runner is None for l in self._links.values())
+
     def _wait_incoming(self, channel, it_prev, stream):
+        """Everything the neighbours pushed in their previous step has landed (events inside one process,
+        device semaphores across ranks: ONE wait kernel covers both sides)."""
+        ready = [0, 0]
         for side, link in self._links.items():
             if link.peer_runner is not None:
                 stream.wait_for_event(link.peer_runner._push_events[channel][it_prev & 1])
             else:
-                self._lib.call('slf_sem_wait', link.my_ready(channel), link.my_consumed(channel), stream.handle)
+                ready[side] = link.my_ready(channel)
+        if ready[0] or ready[1]:
+            sems = int(self._sems)
+            # populations: pushes of the previous steps; fields (channel 1): of this step too
+            self._lib.call('slf_sem_wait', ready[0], ready[1], sems + 4 * (8 * channel + 2),
+                           sems + 4 * SEM_STATUS_WORD, int(channel == 1), stream.handle)
+
+    def check_peers(self):
+        """Raises if a semaphore wait gave up (dead or diverged neighbour) since the last check."""
+        if self._uses_semaphores():
+            err = ctypes.c_uint32(0)
+            self._lib.call('slf_sem_status', int(self._sems) + 4 * SEM_STATUS_WORD, ctypes.byref(err))
+            if err.value:
+                raise bk.B200Error('subdomain %d: halo wait %s -- a neighbouring rank stopped pushing ghost layers'
+                                   % (self._spec.id, 'timed out' if err.value == 1 else 'was aborted'))
+
+    def abort_waits(self):
+        if self._uses_semaphores():
+            self._lib.call('slf_sem_abort', int(self._sems) + 4 * SEM_STATUS_WORD)
+
+    def reset_host_fields(self):
+        """The host fields as they were before the first step: inf in the envelope, zero inside, then the
+        subdomain's initial_conditions() (subdomain_runner.py:253-320, subdomain.py:455-470)."""
+        views = list(self._scalar_fields) + [c for v in self._vector_fields for c in v]
+        for view in views:
+            base = self.field_base(view)
+            if base.dtype == self.float:
+                base[:] = np.inf
+            view[:] = 0
+        self._subdomain.init_fields(self._sim)
+
+    def reinitialize(self, upload=True, reset_fields=False):
+        """Starts the run again from the host fields (as the caller left them, or reset to the initial
+        conditions): upload, SetInitialConditions, iteration 0.  With neighbours this must be bracketed by
+        rendezvous of all subdomains -- use LBSimulationController.reinitialize()."""
+        dev = self._dev
+        if reset_fields:
+            self.reset_host_fields()
+        if upload:
+            for b in [dev.d_rho] + list(dev.d_v) + ([dev.d_phi] if hasattr(dev, 'd_phi') else []):
+                self.backend.to_buf_async(b, self._calc_stream)
+        dev.set_initial_conditions()
+        self._sim.iteration = 0
 
     # -- stepping ---------------------------------------------------------------------------------
     def phases(self):
         return ['step']
 
     def step(self, sync_req):
-        """One time step: boundary slabs -> push planes to the neighbours (data stream) while the
-        interior is computed (calc stream) -> local PBC.  Cf. subdomain_runner.py:960-1058."""
+        """One time step.  Cf. subdomain_runner.py:960-1058 (boundary blocks -> send -> bulk -> receive).
+
+        With neighbours across the split axis the two layers next to them (slabs) and the interior run
+        CONCURRENTLY on two streams: in the AA pattern a node owns the Q addresses it reads and writes (and
+        in AB the written slots of different nodes are disjoint), incoming planes are only ever read by
+        slab nodes, and outgoing planes are only ever written by slab nodes.  So
+
+            data stream (high priority):  wait for the neighbours' planes of step t-1 -> slabs ->
+                                          push planes + signal (one launch per face)
+            calc stream                :  interior
+
+        fork at the start of the step, join at its end; nothing but the join is on the critical path."""
         dev = self._dev
         it = dev.iteration
         swap = int(dev.aa and (it & 1) == 0)
@@ -321,26 +393,24 @@ class SubdomainRunner(object):
             dev.apply_pbc()
         else:
             cs, ds = self._calc_stream, self._data_stream
-            if it > self._first_iteration:
-                # the neighbours' planes of the previous step must have landed (and, symmetrically,
-                # the neighbours are done with the layers this step's push overwrites)
-                self._wait_incoming(0, it - 1, cs)
             if local_pbc:
                 # periodic x/y inside a z-split: the PBC kernels need the whole step and must run
                 # before the planes leave (they complete the x/y ghost ring of those planes)
+                self._wait_incoming(0, it - 1, cs)
                 dev.collide(save_macro=sync_req, stream=cs)
                 dev.apply_pbc(stream=cs)
                 self._push_all(swap, cs, it)
             else:
+                self._fork_event.record(cs)
+                ds.wait_for_event(self._fork_event)
+                self._wait_incoming(0, it - 1, ds)
                 lo, hi = 1, n - 1
                 if 0 in links:
-                    dev.collide(save_macro=sync_req, z_begin=1, z_end=2, stream=cs)
+                    dev.collide(save_macro=sync_req, z_begin=1, z_end=2, stream=ds)
                     lo = 2
                 if 1 in links and n - 2 >= lo:
-                    dev.collide(save_macro=sync_req, z_begin=n - 2, z_end=n - 1, stream=cs)
+                    dev.collide(save_macro=sync_req, z_begin=n - 2, z_end=n - 1, stream=ds)
                     hi = n - 2
-                self._slab_event.record(cs)
-                ds.wait_for_event(self._slab_event)
                 self._push_all(swap, ds, it)
                 if hi > lo:
                     dev.collide(save_macro=sync_req, z_begin=lo, z_end=hi, stream=cs)
@@ -358,19 +428,57 @@ class SubdomainRunner(object):
                 # the neighbour's output lattice of this step has the same parity as ours
                 peer = link.peer_bufs['dist0b'] if (it & 1) == 0 else link.peer_bufs['dist0a']
             self._lib.call('slf_halo_push', dev.plan, int(dout), link.face, peer, link.peer_lat_n,
-                           link.peer_arr_n, swap, stream.handle)
-            if link.peer_runner is None:
-                self._lib.call('slf_sem_signal', link.peer_ready(0), stream.handle)
+                           link.peer_arr_n, swap, 0 if link.peer_runner is not None else link.peer_ready(0),
+                           stream.handle)
         self._push_events[0][it & 1].record(stream)
 
+    # -- step replay --------------------------------------------------------------------------------
+    def _drop_graphs(self):
+        for g in self._graphs.values():
+            self._lib.call('slf_graph_destroy', g)
+        self._graphs = {}
+
+    def _step_graph(self, parity):
+        """Two steps (one of each parity) recorded from step() itself: launches, fork/join events and the
+        semaphore kernels (whose targets live in device memory) depend on the iteration only through its
+        parity."""
+        g = self._graphs.get(parity)
+        if g is None:
+            dev, sim = self._dev, self._sim
+            it0, sit0 = dev.iteration, sim.iteration
+            self._lib.call('slf_graph_begin_capture', self._calc_stream.handle)
+            try:
+                self.step(False)
+                self.step(False)
+            finally:
+                h = _u64()
+                try:
+                    self._lib.call('slf_graph_end_capture', self._calc_stream.handle, ctypes.byref(h))
+                finally:
+                    dev.iteration, sim.iteration = it0, sit0
+            g = self._graphs[parity] = h.value
+        return g
+
     def run_steps(self, n, save_last=False):
-        """n steps without output; issued from C when the subdomain has no neighbours."""
-        if self._links:
-            for k in range(n):
-                self.step(save_last and k == n - 1)
-        else:
+        """n steps without output: replayed CUDA graphs of step pairs -- issued from C when the subdomain
+        has no neighbours, recorded from step() when its neighbours live in other ranks.  (Several
+        subdomains driven by one process order their pushes with events of the other runners and are
+        stepped one by one: LBSimulationController.run_steps.)"""
+        if not self._links:
             self._dev.run(n, save_last=save_last)
             self._sim.iteration += n
+            return
+        plain = n - (1 if save_last else 0)
+        done = 0
+        if self._uses_semaphores() and plain >= 4 and not getattr(self.config, 'no_step_graphs', False):
+            g = self._step_graph(self._dev.iteration & 1)
+            for _ in range(plain // 2):
+                self._lib.call('slf_graph_launch', g, self._calc_stream.handle)
+                self._dev.iteration += 2
+                self._sim.iteration += 2
+            done = 2 * (plain // 2)
+        for k in range(done, n):
+            self.step(save_last and k == n - 1)
 
     def _fields_to_host(self):
         self._dev.fields_to_host()
@@ -451,6 +559,7 @@ class SubdomainRunner(object):
     def sync(self):
         self._calc_stream.synchronize()
         self._data_stream.synchronize()
+        self.check_peers()
 
 
 class NNSubdomainRunner(SubdomainRunner):
@@ -496,9 +605,7 @@ class NNSubdomainRunner(SubdomainRunner):
                                           host_fields=(fb(sim.rho), fb(sim.phi), [fb(c) for c in sim.v]))
         self._calc_stream = self._dev.stream
         self._data_stream = self.backend.make_stream(high_priority=True)
-        self._sems = self.backend.alloc_buf(size=128)
-        self._push_events = [[self.backend.make_event(self._data_stream) for _ in range(2)] for _ in range(2)]
-        self._slab_event = self.backend.make_event(self._calc_stream)
+        self._init_sync_objects()
 
     def gpu_field(self, field):
         if isinstance(field, list):
@@ -531,7 +638,7 @@ class NNSubdomainRunner(SubdomainRunner):
         it = dev.iteration
         cs = self._calc_stream
         links = self._links
-        if links and it > self._first_iteration:
+        if links:
             self._wait_incoming(0, it - 1, cs)
         dev.macro(stream=cs, with_v=bool(sync_req))
         dev.macro_pbc(stream=cs)
@@ -562,14 +669,24 @@ class NNSubdomainRunner(SubdomainRunner):
                         peer = link.peer_bufs['dist%da' % g]
                     else:
                         peer = link.peer_bufs['dist%db' % g] if (it & 1) == 0 else link.peer_bufs['dist%da' % g]
+                    # the second lattice's copy carries the signal: both have landed when it fires
+                    sig = link.peer_ready(0) if (g == 1 and link.peer_runner is None) else 0
                     self._lib.call('slf_halo_push', dev.plan, int(dout), link.face, peer, link.peer_lat_n,
-                                   link.peer_arr_n, swap, cs.handle)
-                if link.peer_runner is None:
-                    self._lib.call('slf_sem_signal', link.peer_ready(0), cs.handle)
+                                   link.peer_arr_n, swap, sig, cs.handle)
             self._push_events[0][it & 1].record(cs)
         dev.iteration += 1
         self._sim.iteration += 1
 
     def run_steps(self, n, save_last=False):
-        for k in range(n):
+        plain = n - (1 if save_last else 0)
+        done = 0
+        if ((not self._links or self._uses_semaphores()) and plain >= 4
+                and not getattr(self.config, 'no_step_graphs', False)):
+            g = self._step_graph(self._dev.iteration & 1)
+            for _ in range(plain // 2):
+                self._lib.call('slf_graph_launch', g, self._calc_stream.handle)
+                self._dev.iteration += 2
+                self._sim.iteration += 2
+            done = 2 * (plain // 2)
+        for k in range(done, n):
             self.step(save_last and k == n - 1)

@@ -26,29 +26,18 @@ CASES = {
 }
 
 
-def run(cls, args, steps, single=False):
-    ctrl = LBSimulationController(cls, EqualSubdomainsGeometry3D)
-    if single:
-        saved = {k: os.environ.pop(k) for k in ('WORLD_SIZE', 'RANK') if k in os.environ}
-        os.environ['WORLD_SIZE'] = '1'
-    ctrl.setup(args + ['--quiet'])
-    if single:
-        os.environ.update(saved)
+def custom_state(ctrl):
+    """Decomposition-independent initial state for the mixture (the example's own is random)."""
     for r in ctrl.runners:
-        if hasattr(r._sim, 'phi'):       # decomposition-independent initial state for the mixture
+        if hasattr(r._sim, 'phi'):
             sim, spec = r._sim, r._spec
             hz, hy, hx = np.meshgrid(np.arange(spec.oz, spec.oz + spec.nz), np.arange(spec.ny), np.arange(spec.nx),
                                      indexing='ij')
             sim.rho[:] = 1.0 + 1e-3 * np.sin(0.7 * hx + 1.3 * hy + 0.4 * hz)
             sim.phi[:] = 1.0 + 1e-3 * np.cos(0.5 * hx - 0.9 * hy + 1.1 * hz)
-            for b in (r._dev.d_rho, r._dev.d_phi):
-                r._dev.be.to_buf(b)
-            r._dev.set_initial_conditions()
-    ctrl.sync()
-    ctrl.barrier()
-    for k in range(steps):
-        ctrl.step_all(k == steps - 1)
-    ctrl.sync()
+
+
+def collect(ctrl):
     out = []
     for r in ctrl.runners:
         r._fields_to_host()
@@ -57,6 +46,30 @@ def run(cls, args, steps, single=False):
         out.append((r._spec.location[2], np.array([np.array(r.field_base(r._sim.rho))[sl]] + extra +
                                                    [np.array(r.field_base(c))[sl] for c in r._sim.v])))
     return out
+
+
+def run(cls, args, steps, single=False):
+    """Returns the results of (a) `steps` steps issued one by one from Python and (b) the same run again
+    after LBSimulationController.reinitialize(), issued through run_steps() (CUDA-graph replay)."""
+    ctrl = LBSimulationController(cls, EqualSubdomainsGeometry3D)
+    ctrl.setup(args + ['--quiet'], local=single)
+    custom_state(ctrl)
+    ctrl.reinitialize(upload=True)
+    for k in range(steps):
+        ctrl.step_all(k == steps - 1)
+    ctrl.sync()
+    first = collect(ctrl)
+    # the host fields now hold results: start again from the initial conditions, twice (the second
+    # restart finds the semaphores where a completed run left them)
+    for _ in range(2):
+        for r in ctrl.runners:
+            r.reset_host_fields()
+        custom_state(ctrl)
+        ctrl.reinitialize(upload=True)
+        ctrl.run_steps(steps, save_last=True)
+        ctrl.sync()
+    second = collect(ctrl)
+    return first, second
 
 
 def main():
@@ -74,15 +87,19 @@ def main():
     steps = 21
     mine = run(cls, args + ['--subdomains=%d' % ws], steps)
     gathered = [None] * ws
-    dist.all_gather_object(gathered, mine[0])
+    dist.all_gather_object(gathered, (mine[0][0], mine[1][0]))
     ok = True
     if rank == 0:
-        gathered.sort(key=lambda t: t[0])
-        merged = np.concatenate([g[1] for g in gathered], axis=1)
-        one = run(cls, args + ['--subdomains=1'], steps, single=True)[0][1]
+        one = run(cls, args + ['--subdomains=1'], steps, single=True)[0][0][1]
         finite = np.isfinite(one)
-        ok = bool(np.array_equal(merged[finite], one[finite])) and bool((np.isfinite(merged) == finite).all())
-        print('RESULT', name, ap, 'ranks', ws, 'bit-identical' if ok else 'MISMATCH max %g' % np.nanmax(np.abs(merged - one)))
+        for which, label in ((0, 'stepped'), (1, 're-initialised + graph replay')):
+            parts = sorted((g[which] for g in gathered), key=lambda t: t[0])
+            merged = np.concatenate([g[1] for g in parts], axis=1)
+            same = bool(np.array_equal(merged[finite], one[finite])) and bool((np.isfinite(merged) == finite).all())
+            print('RESULT', name, ap, 'ranks', ws, label,
+                  'bit-identical' if same else 'MISMATCH max %g' % np.nanmax(np.abs(merged - one)))
+            ok = ok and same
+        print('RESULT', name, ap, 'all', 'bit-identical' if ok else 'MISMATCH')
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -164,7 +164,7 @@ class FakeLib(object):
     def _outer(self, p):
         return p.arr_nz if p.dim == 3 else p.arr_ny
 
-    def _slf_halo_push(self, plan, dist, face, peer_dist, peer_lat_n, peer_arr_n, with_swap, stream):
+    def _slf_halo_push(self, plan, dist, face, peer_dist, peer_lat_n, peer_arr_n, with_swap, signal, stream):
         """sailfish_b200.halo.face_transfer is the host statement of this copy."""
         from sailfish_b200 import halo, lattice
         p = self._p(plan)
@@ -191,8 +191,11 @@ class FakeLib(object):
     def _slf_sem_signal(self, sem, stream):
         pass
 
-    def _slf_sem_wait(self, ready, consumed, stream):
+    def _slf_sem_wait(self, ready_a, ready_b, seq, status, ahead, stream):
         pass
+
+    def _slf_sem_status(self, status, err):
+        err._obj.value = 0
 
     def _slf_pack_field(self, plan, m, field, out, stream):
         p = self._p(plan)

@@ -1,13 +1,13 @@
 """Bit-exact checks of the data-movement kernels against the oracle on random lattices:
 ApplyPeriodicBoundaryConditions[WithSwap], Collect/DistributeContinuousData[WithSwap] and the
-peer-to-peer plane push (vs sailfish_b200.halo.face_transfer)."""
+peer-to-peer plane push (vs the oracle's collect + distribute), and the sparse index transfers."""
 import ctypes
 
 import numpy as np
 import pytest
 
 import util
-from sailfish_b200 import halo, lattice
+from sailfish_b200 import lattice
 
 pytestmark = pytest.mark.gpu
 
@@ -130,26 +130,89 @@ def test_macro_collect_distribute_bit_exact(oracle, case):
 
 @pytest.mark.parametrize('case', ['ldc2d_bgk_AA', 'ldc3d_bgk_AA', 'ldc3d_q27_AA'])
 @pytest.mark.parametrize('swap', [0, 1])
-def test_halo_push_matches_host_statement(case, swap):
-    """slf_halo_push (device statement) == sailfish_b200.halo.face_transfer (host statement)."""
+@pytest.mark.parametrize('signal', [0, 1])
+def test_halo_push_matches_oracle_collect_distribute(oracle, case, swap, signal):
+    """slf_halo_push into a second lattice == the oracle's CollectContinuousData on the sender followed by
+    DistributeContinuousData on the receiver (kernel_utils.mako:526-794 restated in oracle/lbm_oracle.c), over
+    the whole lattice cross-section.  With `signal` the copy kernel's last block must have raised the
+    semaphore word exactly once per launch."""
     c, p, dev = _dev(case)
     rng = np.random.RandomState(13)
     shape = (p.Q,) + c['map'].shape
     src = rng.rand(*shape).astype(np.float32)
-    L = lattice.get(str(c['grid']))
+    lat = [int(x) for x in c['lat']]
+    nx = lat[0]
+    n_other = 1 if p.dim == 2 else lat[1]
     outer = shape[1]
+    L = lattice.get(str(c['grid']))
     peer = dev.be.alloc_buf(size=src.nbytes)
+    sem = dev.be.alloc_buf(size=64)
+    dev.lib.call('slf_memset', int(sem), 0, 64, 0)
+    dev.lib.call('slf_sync')
+    launches = 0
     for side in (0, 1):
         face = 2 * (p.dim - 1) + side
+        ndists = len(L.get_interblock_dists([(1 if side else -1) if a == p.dim - 1 else 0 for a in range(p.dim)]))
         dst0 = rng.rand(*shape).astype(np.float32)
         dev.set_dist(src)
         dev.lib.call('slf_memcpy_h2d', int(peer), dst0.ctypes.data_as(ctypes.c_void_p), dst0.nbytes)
-        dev.lib.call('slf_halo_push', dev.plan, int(dev.d_dist_a), face, int(peer), outer, outer, swap,
-                     dev.stream.handle)
+        for _ in range(3):                       # repeated launches: the block counter must re-arm itself
+            dev.lib.call('slf_halo_push', dev.plan, int(dev.d_dist_a), face, int(peer), lat[p.dim - 1], outer, swap,
+                         int(sem) if signal else 0, dev.stream.handle)
+            launches += 1
         dev.sync()
         got = np.zeros_like(dst0)
         dev.lib.call('slf_memcpy_d2h', got.ctypes.data_as(ctypes.c_void_p), int(peer), got.nbytes)
-        slots, s_layer, d_layer = halo.face_transfer(L, face, bool(swap), outer, outer)
-        want = dst0.copy()
-        halo.insert_planes(want, slots, d_layer, halo.extract_planes(src, slots, s_layer))
-        assert np.array_equal(got, want), (face, swap)
+        buf = np.zeros(ndists * n_other * nx, np.float32)
+        oracle.collect(p, src.reshape(-1), face, 0, 0, nx, n_other, buf, bool(swap))
+        want = dst0.copy().reshape(-1)
+        oracle.distribute(p, want, face, 0, 0, nx, n_other, buf, bool(swap))
+        want = want.reshape(shape)
+        assert np.array_equal(got[..., :nx], want[..., :nx]), (face, swap)
+        # nothing but the target planes changed (x padding of those planes travels too and is never read)
+        changed = np.any((got != dst0)[..., :nx].reshape(p.Q, outer, -1), axis=2)
+        assert changed.sum() == ndists, (face, swap, changed.sum())
+    word = np.zeros(1, np.uint32)
+    dev.lib.call('slf_memcpy_d2h', word.ctypes.data_as(ctypes.c_void_p), int(sem), 4)
+    assert int(word[0]) == (launches if signal else 0)
+
+
+@pytest.mark.parametrize('case', ['ldc2d_bgk_AA', 'ldc3d_bgk_AA', 'ldc3d_q27_AA'])
+def test_sparse_collect_distribute_bit_exact(case):
+    """Collect/DistributeSparseData (kernel_utils.mako:796-836): buffer[k] = dist[idx[k]] and back, for the
+    index sets the reference builds for x faces, edges and corners (global population indices, some
+    repeated, 0xffffffff = padding entry that must be skipped)."""
+    c, p, dev = _dev(case)
+    rng = np.random.RandomState(17)
+    shape = (p.Q,) + c['map'].shape
+    d0 = rng.rand(*shape).astype(np.float32)
+    total = d0.size
+    n = 5000
+    idx = rng.randint(0, total, size=n).astype(np.uint32)
+    idx[rng.rand(n) < 0.05] = 0xffffffff
+    didx = dev.be.alloc_buf(size=idx.nbytes)
+    dbuf = dev.be.alloc_buf(size=n * 4)
+    dev.lib.call('slf_memcpy_h2d', int(didx), idx.ctypes.data_as(ctypes.c_void_p), idx.nbytes)
+    dev.set_dist(d0)
+    sentinel = np.full(n, -7.0, np.float32)
+    dev.lib.call('slf_memcpy_h2d', int(dbuf), sentinel.ctypes.data_as(ctypes.c_void_p), n * 4)
+    dev.lib.call('slf_collect_sparse_data', dev.plan, int(didx), int(dev.d_dist_a), int(dbuf), n, dev.stream.handle)
+    dev.sync()
+    got = np.zeros(n, np.float32)
+    dev.lib.call('slf_memcpy_d2h', got.ctypes.data_as(ctypes.c_void_p), int(dbuf), n * 4)
+    valid = idx != 0xffffffff
+    want = sentinel.copy()
+    want[valid] = d0.reshape(-1)[idx[valid]]
+    assert np.array_equal(got, want)
+    # distribute: unique targets so that the result does not depend on the write order
+    uidx = rng.permutation(total)[:n].astype(np.uint32)
+    uidx[::17] = 0xffffffff
+    src = rng.rand(n).astype(np.float32)
+    dev.lib.call('slf_memcpy_h2d', int(didx), uidx.ctypes.data_as(ctypes.c_void_p), uidx.nbytes)
+    dev.lib.call('slf_memcpy_h2d', int(dbuf), src.ctypes.data_as(ctypes.c_void_p), n * 4)
+    dev.lib.call('slf_distribute_sparse_data', dev.plan, int(didx), int(dev.d_dist_a), int(dbuf), n, dev.stream.handle)
+    g = dev.get_dist()
+    o = d0.copy().reshape(-1)
+    ok = uidx != 0xffffffff
+    o[uidx[ok]] = src[ok]
+    assert np.array_equal(g, o.reshape(shape))

@@ -2,17 +2,16 @@
 do-nothing nodes, obstacles with unused cores, D3Q27 with pressure planes -- node types the BASELINE examples do
 not use.  The oracle is pinned on these cases (tests/test_oracle_golden.py, reference-expression goldens).
 
-Status: written after this round's GPU budget was spent, so these comparisons have not run on a B200 yet.  They
-are marked xfail(strict=False): a pass shows up as XPASS, a failure cannot mask the suite behind `-x`.  Remove the
-marker once they have been seen to pass."""
+
+Status: passed on the driver's B200 at the end of round 1 (22 XPASS in GPUTEST_r01); the provisional xfail
+marker is gone, a regression now fails the suite."""
 import numpy as np
 import pytest
 
 import util
 from test_gpu_parity import _errs, _gpu_run, _oracle_run
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(reason='new this round, not yet run on a B200 (GPU budget spent)', strict=False)]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize('case', util.ZOO_STEP_CASES)
