@@ -54,37 +54,72 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md): NVML in-process (a query takes
+    well under a millisecond, so even a 60 ms region yields several samples under load); nvidia-smi as fallback."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
     def __init__(self, index=0):
         threading.Thread.__init__(self, daemon=True)
         self.index = index
-        self.samples = []
+        self.samples = []            # (sm_mhz, [active reasons])
+        self.max_mhz = None
+        self.source = 'nvml'
         self._stop_evt = threading.Event()
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            # torch / CUDA index the visible devices; NVML indexes the physical ones
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[index]) if vis and all(v.strip().isdigit() for v in vis.split(',')) else index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:            # noqa: BLE001
+            self._h = None
+            self.source = 'nvidia-smi'
+
+    def _sample_nvml(self):
+        nv = self._nv
+        mhz = int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+        except Exception:            # noqa: BLE001
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+        bits = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4}
+        self.samples.append((mhz, [n for n in self.NAMES if mask & bits[n]]))
+
+    def _sample_smi(self):
+        out = subprocess.check_output(
+            ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
+            timeout=5).decode().strip()
+        s = [x.strip() for x in out.split(',')]
+        self.max_mhz = int(float(s[1]))
+        self.samples.append((int(float(s[0])), [n for i, n in enumerate(self.NAMES) if s[2 + i].lower().startswith('active')]))
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.check_output(
-                    ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
-                    timeout=5).decode().strip()
-                self.samples.append([x.strip() for x in out.split(',')])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.1)
+                if self._h is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
+            except Exception:        # noqa: BLE001
+                if self._h is not None:          # NVML query failed: fall back to the command-line tool
+                    self._h, self.source = None, 'nvidia-smi'
+            self._stop_evt.wait(0.004 if self._h is not None else 0.1)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=3)
         if not self.samples:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace('.', '').isdigit())
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples)]
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None,
-                'sm_max_mhz': int(float(self.samples[0][1])), 'reasons': reasons, 'samples': len(self.samples)}
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['clock query unavailable']}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = sorted(set(r for s in self.samples for r in s[1]))
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_min_mhz': sm[0], 'sm_max_mhz': self.max_mhz, 'reasons': reasons,
+                'samples': len(self.samples), 'source': self.source}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -134,10 +169,34 @@ class CpuArm(object):
         from oracle import oracle
         oracle.build()
         self.oracle = oracle
-        ncpu = len(oracle.HOST_CPUS)
-        # set explicitly: torchrun exports OMP_NUM_THREADS=1 and another library may already have
-        # initialised the OpenMP runtime with it
-        self.threads = oracle.omp_config(ncpu, pin=True)
+        cpus = oracle.HOST_CPUS
+        ncpu = len(cpus)
+        # Thread count and placement are chosen by measurement: the "CPUs" of a container may be hyper-threads
+        # or be capped by a CPU quota, and then fewer, well-placed threads stream faster.  Set explicitly in any
+        # case: torchrun exports OMP_NUM_THREADS=1 and another library may already have initialised OpenMP with it.
+        case = build_oracle_case(96)
+        cands = []
+        for t in sorted(set(max(1, ncpu // d) for d in (1, 2, 4, 8)), reverse=True):
+            for pin in (True, False):
+                cands.append((t, pin))
+        best, self.calibration = None, []
+        for t, pin in cands:
+            sub = cpus[::max(1, ncpu // t)][:t] if pin else cpus
+            oracle.omp_config(t, pin=pin, cpus=sub)
+            sim = oracle.Simulation(case[0], case[1], case[2], case[3], dtype=np.float32)    # first touch under this placement
+            sim.step(); sim.step()
+            t0, n = time.time(), 0
+            while time.time() - t0 < 0.6:
+                sim.step(); sim.step()
+                n += 2
+            mlups = case[4] * n / (time.time() - t0) * 1e-6
+            self.calibration.append({'threads': t, 'pinned': pin, 'mlups': round(mlups, 1)})
+            if best is None or mlups > best[0]:
+                best = (mlups, t, pin, sub)
+            del sim
+        _, t, pin, sub = best
+        self.pinned, self.cpus = pin, sub
+        self.threads = oracle.omp_config(t, pin=pin, cpus=sub)
         self.size = cpu_sample_size(ncpu)
         p, node_map, rho, v, fluid = build_oracle_case(self.size)[:5]
         self.fluid = fluid
@@ -158,8 +217,9 @@ class CpuArm(object):
         return self.fluid * n / dt * 1e-6, n, dt
 
     def describe(self, n, dt):
-        return ('ldc_3d D3Q19 BGK AA %d^3, %d steps in %.1f s per sample, oracle fp32, %d OpenMP threads pinned to %d CPUs'
-                % (self.size, n, dt, self.threads, len(self.oracle.HOST_CPUS)))
+        return ('ldc_3d D3Q19 BGK AA %d^3, %d steps in %.1f s per sample, oracle fp32, %d OpenMP threads (%s; best of the '
+                'calibrated thread counts / placements) on a host with %d usable CPUs'
+                % (self.size, n, dt, self.threads, 'pinned 1:1' if self.pinned else 'free to move', len(self.oracle.HOST_CPUS)))
 
 
 def workload_name(size, gpus):
@@ -194,7 +254,7 @@ def run_reference_arm(args):
                    'note': 'reference has no CPU path (backend_dummy is a no-op) and its GPU path needs Mako+pycuda; '
                            'this is the CPU restatement of its kernels (oracle/), all host threads'},
         'cpu_baseline': {'value': value, 'min': float(np.min(vals)), 'max': float(np.max(vals)), 'unit': 'MLUPS',
-                         'cores': arm.threads, 'kind': 'port', 'sample': sample},
+                         'cores': arm.threads, 'kind': 'port', 'sample': sample, 'calibration': arm.calibration},
         'e2e': {'value': value, 'unit': 'MLUPS', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line))

@@ -800,7 +800,7 @@ int orc_sizeof_real(void) { return (int)sizeof(REAL); }
  * orc_set_initial_conditions then places every thread's rows on its own NUMA node). */
 #ifdef _OPENMP
 #include <omp.h>
-int orc_omp_config(int nthreads, const int *cpus, int ncpu) {
+int orc_omp_config(int nthreads, const int *cpus, int ncpu, int pin) {
   if (nthreads > 0) omp_set_num_threads(nthreads);
   int used = 1;
 #pragma omp parallel
@@ -808,16 +808,17 @@ int orc_omp_config(int nthreads, const int *cpus, int ncpu) {
 #pragma omp single
     used = omp_get_num_threads();
     if (cpus && ncpu > 0) {
-      cpu_set_t one;
-      CPU_ZERO(&one);
-      CPU_SET(cpus[omp_get_thread_num() % ncpu], &one);
-      sched_setaffinity(0, sizeof(one), &one);
+      cpu_set_t set;
+      CPU_ZERO(&set);
+      if (pin) CPU_SET(cpus[omp_get_thread_num() % ncpu], &set);        /* thread k on the k-th CPU of the list */
+      else for (int c = 0; c < ncpu; c++) CPU_SET(cpus[c], &set);         /* free to move within the list */
+      sched_setaffinity(0, sizeof(set), &set);
     }
   }
   return used;
 }
 #else
-int orc_omp_config(int nthreads, const int *cpus, int ncpu) { (void)nthreads; (void)cpus; (void)ncpu; return 1; }
+int orc_omp_config(int nthreads, const int *cpus, int ncpu, int pin) { (void)nthreads; (void)cpus; (void)ncpu; (void)pin; return 1; }
 #endif
 
 /* ------------------------------------------------------------------------------------

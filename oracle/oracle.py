@@ -39,11 +39,13 @@ def _lib(dtype):
 HOST_CPUS = sorted(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else list(range(os.cpu_count() or 1))
 
 
-def omp_config(nthreads=0, pin=True, dtype=np.float32):
-    """Sets the OpenMP thread count of the oracle library (0 = leave), pins thread k to the k-th CPU the
-    process may use and returns the number of threads a parallel region really gets."""
-    cpus = (ctypes.c_int * len(HOST_CPUS))(*HOST_CPUS)
-    return int(_lib(dtype).orc_omp_config(int(nthreads), cpus if pin else None, len(HOST_CPUS) if pin else 0))
+def omp_config(nthreads=0, pin=True, dtype=np.float32, cpus=None):
+    """Sets the OpenMP thread count of the oracle library (0 = leave) and the threads' CPU affinity -- pin:
+    thread k on the k-th CPU of `cpus` (default: every CPU the process may use); not pin: free to move within
+    `cpus`.  Returns the number of threads a parallel region really gets."""
+    cpus = list(cpus if cpus is not None else HOST_CPUS)
+    arr = (ctypes.c_int * len(cpus))(*cpus)
+    return int(_lib(dtype).orc_omp_config(int(nthreads), arr, len(cpus), int(bool(pin))))
 
 
 def _p(a):

@@ -183,18 +183,16 @@ __device__ __forceinline__ int edotn(int i, int n0, int n1, int n2) {
 // LISTED = true: `list[k]`, k in [gi0, gi1) are the indices of the nodes to process (built by
 // slf_plan_bind_map: every active node that the masked bulk kernel does not handle, sorted by
 // gi).  LISTED = false: scan the node range [gi0, gi1) and pick the non-fluid nodes.
-template <class L, int MODEL, int MODE, bool SAVE, bool LISTED>
-__global__ void __launch_bounds__(128)
-collide_boundary(const DevParams P, const uint32_t *__restrict__ map, const uint32_t *__restrict__ list,
-                 const float *din, float *dout,
-                 float *__restrict__ orho, float *__restrict__ ovx, float *__restrict__ ovy,
-                 float *__restrict__ ovz, long long gi0, long long gi1) {
-  long long gi = gi0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gi >= gi1) return;
-  if (LISTED) gi = list[gi];
+// One node of the generic path (every node class, run-time normals); `skip_fluid`: the caller scans a node
+// range in which plain fluid nodes belong to the bulk kernel.
+template <class L, int MODEL, int MODE, bool SAVE>
+__device__ __forceinline__ void
+boundary_node(const DevParams &P, const uint32_t *__restrict__ map, const float *din, float *dout,
+              float *__restrict__ orho, float *__restrict__ ovx, float *__restrict__ ovy,
+              float *__restrict__ ovz, const long long gi, const bool skip_fluid) {
   const uint32_t code = map[gi];
   const uint32_t type = code & P.tmask;
-  if (!LISTED && type == P.tid[SLF_NT_FLUID]) return;
+  if (skip_fluid && type == P.tid[SLF_NT_FLUID]) return;
   const int cls = node_class<L>(P, type);
   if (cls < 0 || cls == SLF_NT_GHOST || cls == SLF_NT_UNUSED || cls == SLF_NT_PROPAGATION_ONLY) return;
   const int x = (int)(gi % P.ax);
@@ -349,6 +347,18 @@ collide_boundary(const DevParams P, const uint32_t *__restrict__ map, const uint
       if (ok) dout[gi + noff<L>(P, i) + P.DS * i] = f[i];
     }
   }
+}
+
+template <class L, int MODEL, int MODE, bool SAVE, bool LISTED>
+__global__ void __launch_bounds__(128)
+collide_boundary(const DevParams P, const uint32_t *__restrict__ map, const uint32_t *__restrict__ list,
+                 const float *din, float *dout,
+                 float *__restrict__ orho, float *__restrict__ ovx, float *__restrict__ ovy,
+                 float *__restrict__ ovz, long long gi0, long long gi1) {
+  long long gi = gi0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= gi1) return;
+  if (LISTED) gi = list[gi];
+  boundary_node<L, MODEL, MODE, SAVE>(P, map, din, dout, orho, ovx, ovy, ovz, gi, !LISTED);
 }
 
 // ----------------------------------------------------------------------------------------

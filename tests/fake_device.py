@@ -17,6 +17,8 @@ class FakeLib(object):
         self.links = {}         # plan key -> (low, high)
         self.launches = 0
         self.calls = []
+        self._capture = None
+        self.graphs = []
 
     # -- helpers -------------------------------------------------------------------------------
     def _arr(self, ptr, dtype, count):
@@ -30,7 +32,26 @@ class FakeLib(object):
 
     def call(self, name, *args):
         self.calls.append(name)
+        if self._capture is not None and not name.startswith('slf_graph_'):
+            self._capture.append((name, args))          # recorded, not run (stream capture)
+            return None
         return getattr(self, '_' + name)(*args)
+
+    # -- stream capture: the recorded calls are replayed in order -----------------------------------
+    def _slf_graph_begin_capture(self, stream):
+        self._capture = []
+
+    def _slf_graph_end_capture(self, stream, out):
+        self.graphs.append(self._capture)
+        self._capture = None
+        out._obj.value = len(self.graphs)
+
+    def _slf_graph_launch(self, graph, stream):
+        for name, args in self.graphs[int(graph) - 1]:
+            getattr(self, '_' + name)(*args)
+
+    def _slf_graph_destroy(self, graph):
+        pass
 
     # -- runtime -------------------------------------------------------------------------------
     def _slf_init(self, dev):

@@ -49,35 +49,60 @@ def rel(a, b, scale=None):
     return float(np.max(np.abs(a - b)) / (scale if scale is not None else np.max(np.abs(b))))
 
 
-def check_against_oracle(oracle, cls, geo, args, steps, tol_rho=1e-6, tol_v=1e-5, envelope=False):
-    """envelope: long runs are compared with the fp64 oracle and must stay within twice the fp32 oracle's own
-    round-off (as tests/test_gpu_parity.py does for the golden runs)."""
+def _record(name, data):
+    """Measured deviations travel back to the build container (gpurun_out/ is merged) -> profiles/parity_r02.json."""
+    import json
+    import os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    try:
+        os.makedirs(out, exist_ok=True)
+        path = os.path.join(out, 'parity_r02.json')
+        cur = json.load(open(path)) if os.path.exists(path) else {}
+        cur[name] = data
+        json.dump(cur, open(path, 'w'), indent=1, sort_keys=True)
+    except Exception:                            # noqa: BLE001
+        pass
+
+
+def check_against_oracle(oracle, cls, geo, args, steps, name, v_floor=1e-6):
+    """GPU (public runner) vs the oracle on identical inputs after `steps` steps, relative max norm over wet
+    nodes (v: relative to max |v|).  The reference computes in fp32, so its own arithmetic deviates from exact
+    (fp64) arithmetic; that deviation is measured with the fp32 oracle and recorded beside the GPU's.  Bar
+    (north_star: <= 1e-6 relative fp32): 1e-6, or twice (v: three times) the fp32 restatement's own deviation where that is larger."""
     ctrl = setup(cls, geo, args)
     r = ctrl.runners[0]
     p, node_map, f0, v0 = inputs(r)
     wet = r._subdomain.fluid_map()
     sl = r._spec._nonghost_slice
     got = run_gpu(ctrl, steps)
-    if len(f0) == 2:
-        ref = oracle.ShanChenSimulation(p, node_map, f0[0], f0[1], v0, dtype=np.float32)
-        ref.run(steps)
-        want = [ref.rho, ref.phi] + list(ref.v)
-    else:
-        ref = oracle.Simulation(p, node_map, f0[0], v0, dtype=np.float64 if envelope else np.float32)
-        ref.run(steps)
-        want = [ref.rho] + list(ref.v)
-        if envelope:
-            r32 = oracle.Simulation(p, node_map, f0[0], v0, dtype=np.float32)
-            r32.run(steps)
-            e32 = rel(np.asarray(r32.rho).reshape(node_map.shape)[sl][wet], np.asarray(ref.rho).reshape(node_map.shape)[sl][wet])
-            tol_rho, tol_v = 2 * e32 + 1e-6, 20 * e32 + 1e-5
-    want = [np.asarray(w).reshape(node_map.shape)[sl] for w in want]
     ns = len(f0)
-    for k in range(ns):
-        assert rel(got[k][wet], want[k][wet]) <= tol_rho, (k, rel(got[k][wet], want[k][wet]))
-    vscale = max(float(np.max(np.abs(w[wet]))) for w in want[ns:]) or 1.0
-    for k in range(ns, len(want)):
-        assert rel(got[k][wet], want[k][wet], vscale) <= tol_v, (k, rel(got[k][wet], want[k][wet], vscale))
+    res = {}
+    for key, dt in (('f64', np.float64), ('f32', np.float32)):
+        if ns == 2:
+            ref = oracle.ShanChenSimulation(p, node_map, f0[0], f0[1], v0, dtype=dt)
+            ref.run(steps)
+            want = [ref.rho, ref.phi] + list(ref.v)
+        else:
+            ref = oracle.Simulation(p, node_map, f0[0], v0, dtype=dt)
+            ref.run(steps)
+            want = [ref.rho] + list(ref.v)
+        res[key] = [np.asarray(w, dtype=np.float64).reshape(node_map.shape)[sl][wet] for w in want]
+        del ref, want
+    g = [x[wet].astype(np.float64) for x in got]
+
+    def errs(a, b):
+        e_s = max(rel(a[k], b[k]) for k in range(ns))
+        vscale = max(float(np.max(np.abs(w))) for w in b[ns:]) or 1.0
+        e_v = max(rel(a[k], b[k], vscale) for k in range(ns, len(b)))
+        return e_s, e_v
+    e_gpu, e_f32, e_gg = errs(g, res['f64']), errs(res['f32'], res['f64']), errs(g, res['f32'])
+    rec = {'steps': steps, 'config': ' '.join(args), 'wet_nodes': int(wet.sum()),
+           'gpu_vs_f64': {'rho': e_gpu[0], 'v': e_gpu[1]}, 'f32oracle_vs_f64': {'rho': e_f32[0], 'v': e_f32[1]},
+           'gpu_vs_f32oracle': {'rho': e_gg[0], 'v': e_gg[1]},
+           'v_scale': max(float(np.max(np.abs(w))) for w in res['f64'][ns:])}
+    _record(name, rec)
+    assert e_gpu[0] <= max(1e-6, 2 * e_f32[0]), rec
+    assert e_gpu[1] <= max(v_floor, 3 * e_f32[1]), rec
     return got, wet
 
 
@@ -89,17 +114,18 @@ C5 = ['--lat_nx=256', '--lat_ny=256', '--lat_nz=256', '--seed=1234']
 
 
 def test_c1_ldc2d_256_against_oracle(oracle):
-    check_against_oracle(oracle, ldc_2d.LDCSim, None, C1, 200, envelope=True)
+    check_against_oracle(oracle, ldc_2d.LDCSim, None, C1, 200, 'C1_ldc2d_256_bgk_AA')
 
 
 @pytest.mark.parametrize('model', ['bgk', 'mrt'])
 def test_c2_ldc3d_256_against_oracle(oracle, model):
-    got, wet = check_against_oracle(oracle, ldc_3d.LDCSim, None, C2 + ['--access_pattern=AA', '--model=' + model], 4)
+    got, wet = check_against_oracle(oracle, ldc_3d.LDCSim, None, C2 + ['--access_pattern=AA', '--model=' + model], 100,
+                                    'C2_ldc3d_256_%s_AA' % model)
     # the cavity is mirror-symmetric in y: rho, vx, vz even, vy odd (fp32 summation order differs: tolerance)
     rho, vx, vy, vz = got
     vs = float(np.max(np.abs(vx[wet])))
-    assert rel(rho[:, ::-1, :][wet], rho[wet]) <= 1e-6
-    assert rel(vx[:, ::-1, :][wet], vx[wet], vs) <= 1e-5 and rel(-vy[:, ::-1, :][wet], vy[wet], vs) <= 1e-5
+    assert rel(rho[:, ::-1, :][wet], rho[wet]) <= 2e-6
+    assert rel(vx[:, ::-1, :][wet], vx[wet], vs) <= 2e-5 and rel(-vy[:, ::-1, :][wet], vy[wet], vs) <= 2e-5
 
 
 def test_c2_aa_equals_ab_and_split_equals_single():
@@ -117,23 +143,25 @@ def test_c2_aa_equals_ab_and_split_equals_single():
 
 
 def test_c3_poiseuille_128x128x512_against_oracle(oracle):
-    check_against_oracle(oracle, poiseuille_3d.PoiseuilleSim, EqualSubdomainsGeometry3D, C3, 3, envelope=True)
+    check_against_oracle(oracle, poiseuille_3d.PoiseuilleSim, EqualSubdomainsGeometry3D, C3, 100, 'C3_poiseuille_128x128x512_mrt_AA')
 
 
 def test_c4_ldc3d_512_against_oracle(oracle):
     """BASELINE config 4 / the bench workload: 143.7 M nodes, 2.73e9 population slots (offsets beyond 2^31)."""
     import psutil
-    if psutil.virtual_memory().available < 80 << 30:
-        pytest.skip('needs ~60 GB of host memory for the oracle copy of the lattice')
+    if psutil.virtual_memory().available < 100 << 30:
+        pytest.skip('needs ~70 GB of host memory for the fp64 + fp32 oracle copies of the lattice')
     check_against_oracle(oracle, ldc_3d.LDCSim, None,
-                         ['--lat_nx=512', '--lat_ny=512', '--lat_nz=512', '--visc=0.03175', '--access_pattern=AA'], 2)
+                         ['--lat_nx=512', '--lat_ny=512', '--lat_nz=512', '--visc=0.03175', '--access_pattern=AA'], 20,
+                         'C4_ldc3d_512_bgk_AA')
 
 
 @pytest.mark.parametrize('ap', ['AA', 'AB'])
 def test_c5_shan_chen_256_against_oracle_and_conservation(oracle, ap):
     args = C5 + ['--access_pattern=' + ap]
-    got, wet = check_against_oracle(oracle, sc_separation_3d.SeparationSCSim, EqualSubdomainsGeometry3D, args, 2,
-                                    tol_v=2e-3)      # |v| ~ 1e-5 here: absolute accuracy ~1e-8
+    # |v| ~ 1e-5 lattice units here (an unmixed fluid at rest): 1e-3 of that is an absolute accuracy of 1e-8
+    got, wet = check_against_oracle(oracle, sc_separation_3d.SeparationSCSim, EqualSubdomainsGeometry3D, args,
+                                    100 if ap == 'AA' else 10, 'C5_shan_chen_256_%s' % ap, v_floor=2e-3)
     # periodic box: each component's mass is conserved exactly by collision + streaming
     ctrl = setup(sc_separation_3d.SeparationSCSim, EqualSubdomainsGeometry3D, args)
     r = ctrl.runners[0]
