@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -502,6 +503,32 @@ int slf_run_steps(SlfPlan *pl, uint64_t map, uint64_t dist_a, uint64_t dist_b, u
   if (nsteps <= 0) return 0;
   if (pl->hp.access_pattern == SLF_AB && !dist_b) return fail(SLF_EINVAL, "AB needs two lattices");
   cudaStream_t s = (cudaStream_t)stream;
+  // Small lattices without periodic axes: all steps in one cooperative launch (grid barrier between steps).
+  if (pl->hp.access_pattern == SLF_AA && nsteps >= 2 && s != 0 && !pl->hp.periodic[0] && !pl->hp.periodic[1] &&
+      !pl->hp.periodic[2] && !getenv("SLF_NO_MULTISTEP")) {
+    const uint32_t *m = (const uint32_t *)map;
+    float *d = (float *)dist_a, *r = (float *)rho, *x = (float *)vx, *y = (float *)vy, *z = (float *)vz;
+    int left = nsteps;
+    uint32_t it = iteration;
+    int rc = 1;
+    while (left > 0) {
+      const int chunk = left > 65536 ? 65536 : left;      // the barrier counter is 32 bits wide
+      const int sl = save_last && chunk == left;
+      switch (pl->hp.lattice) {
+        case SLF_D2Q9: rc = slf_multistep_d2q9(pl, pl->hp.model, m, d, r, x, y, z, it, chunk, sl, s); break;
+        case SLF_D3Q19:
+          rc = pl->hp.model == SLF_MRT ? slf_multistep_d3q19_mrt(pl, m, d, r, x, y, z, it, chunk, sl, s)
+                                       : slf_multistep_d3q19_bgk(pl, m, d, r, x, y, z, it, chunk, sl, s);
+          break;
+        default: rc = slf_multistep_d3q27(pl, m, d, r, x, y, z, it, chunk, sl, s); break;
+      }
+      if (rc != 0) break;
+      left -= chunk; it += chunk;
+    }
+    if (left == 0) return 0;
+    if (rc != 1) cudaGetLastError();                      // cooperative launch refused: step kernel by kernel
+    iteration = it; nsteps = left;                        // (chunks already issued stay issued)
+  }
   int done = 0;
   const int plain = nsteps - (save_last ? 1 : 0);       // steps that may be replayed from a graph
   if (plain >= 4 && s != 0) {

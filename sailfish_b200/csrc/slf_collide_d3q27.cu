@@ -3,3 +3,7 @@ int slf_collide_d3q27(SlfPlan *pl, int mode, bool save, const uint32_t *map, con
                       float *rho, float *vx, float *vy, float *vz, int z0, int z1, cudaStream_t s) {
   return dispatch_mode<D3Q27, SLF_BGK>(pl, mode, save, map, din, dout, rho, vx, vy, vz, z0, z1, s);
 }
+int slf_multistep_d3q27(SlfPlan *pl, const uint32_t *map, float *dist, float *rho, float *vx, float *vy, float *vz,
+        uint32_t it0, int nsteps, int save_last, cudaStream_t s) {
+  return launch_multistep<D3Q27, SLF_BGK>(pl, map, dist, rho, vx, vy, vz, it0, nsteps, save_last, s);
+}

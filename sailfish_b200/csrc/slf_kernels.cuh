@@ -135,19 +135,14 @@ template <> struct BulkTuning<D2Q9, SLF_MRT> { static constexpr int MINB = 10; }
 // f_i is loaded from table[i] and stored to table[opp(i)] in both cases.
 template <class L> struct SlotTable { float *p[L::Q]; };
 
-template <class L, int MODEL, bool SAVE>
-__global__ void __launch_bounds__(128, BulkTuning<L, MODEL>::MINB)
-collide_bulk_aa_tab(const DevParams P, const SlotTable<L> T, const uint32_t *__restrict__ fluid_mask,
-                    float *__restrict__ orho, float *__restrict__ ovx, float *__restrict__ ovy,
-                    float *__restrict__ ovz, long long gi0, unsigned n) {
-  const unsigned t = blockIdx.x * 128u + threadIdx.x;
-  if (t >= n) return;
-  const long long gi = gi0 + t;
-  if (!((fluid_mask[gi >> 5] >> (gi & 31)) & 1u)) return;
-
+// one plain fluid node: f_i from T.p[i][t], relax, store to T.p[opp(i)][t]
+template <class L, int MODEL, bool SAVE, int HINT = 0>
+__device__ __forceinline__ void
+bulk_aa_node(const DevParams &P, const SlotTable<L> &T, float *__restrict__ orho, float *__restrict__ ovx,
+             float *__restrict__ ovy, float *__restrict__ ovz, const long long gi, const unsigned t) {
   float f[L::Q];
 #pragma unroll
-  for (int i = 0; i < L::Q; i++) f[i] = T.p[i][t];
+  for (int i = 0; i < L::Q; i++) f[i] = ldp<HINT>(T.p[i] + t);
   float rho, v[3];
   moments<L>(f, rho, v);
   const float inv = 1.0f / rho;
@@ -160,6 +155,18 @@ collide_bulk_aa_tab(const DevParams P, const SlotTable<L> T, const uint32_t *__r
   }
 #pragma unroll
   for (int i = 0; i < L::Q; i++) T.p[L::opp(i)][t] = f[i];
+}
+
+template <class L, int MODEL, bool SAVE>
+__global__ void __launch_bounds__(128, BulkTuning<L, MODEL>::MINB)
+collide_bulk_aa_tab(const DevParams P, const SlotTable<L> T, const uint32_t *__restrict__ fluid_mask,
+                    float *__restrict__ orho, float *__restrict__ ovx, float *__restrict__ ovy,
+                    float *__restrict__ ovz, long long gi0, unsigned n) {
+  const unsigned t = blockIdx.x * 128u + threadIdx.x;
+  if (t >= n) return;
+  const long long gi = gi0 + t;
+  if (!((fluid_mask[gi >> 5] >> (gi & 31)) & 1u)) return;
+  bulk_aa_node<L, MODEL, SAVE>(P, T, orho, ovx, ovy, ovz, gi, t);
 }
 
 template <class L>
@@ -185,7 +192,7 @@ __device__ __forceinline__ int edotn(int i, int n0, int n1, int n2) {
 // gi).  LISTED = false: scan the node range [gi0, gi1) and pick the non-fluid nodes.
 // One node of the generic path (every node class, run-time normals); `skip_fluid`: the caller scans a node
 // range in which plain fluid nodes belong to the bulk kernel.
-template <class L, int MODEL, int MODE, bool SAVE>
+template <class L, int MODEL, int MODE, bool SAVE, int HINT = 0>
 __device__ __forceinline__ void
 boundary_node(const DevParams &P, const uint32_t *__restrict__ map, const float *din, float *dout,
               float *__restrict__ orho, float *__restrict__ ovx, float *__restrict__ ovy,
@@ -204,7 +211,7 @@ boundary_node(const DevParams &P, const uint32_t *__restrict__ map, const float 
   constexpr bool AA = MODE != MODE_AB;
 
   float f[L::Q];
-  load_node<L, MODE>(P, din, gi, f);
+  load_node<L, MODE, HINT>(P, din, gi, f);
 
   // inward normal of the node (primary orientation); zero when unknown
   int n0 = 0, n1 = 0, n2 = 0;
@@ -359,6 +366,73 @@ collide_boundary(const DevParams P, const uint32_t *__restrict__ map, const uint
   if (gi >= gi1) return;
   if (LISTED) gi = list[gi];
   boundary_node<L, MODEL, MODE, SAVE>(P, map, din, dout, orho, ovx, ovy, ovz, gi, !LISTED);
+}
+
+// ----------------------------------------------------------------------------------------
+// Many steps in ONE launch, for lattices that fit a single co-resident grid (ldc_2d 256^2: 74 k nodes,
+// 2.7 MB -- it lives in L2).  At that size a step is a few hundred nanoseconds of memory time and the
+// cost of a time step is the launch: two kernels per step, ~6 us even when replayed from a CUDA graph
+// (profiles/r01_bench_configs.txt).  Here a persistent cooperative grid keeps one node per thread and
+// separates the steps by a grid-wide barrier (one atomic per block + acquire polling in L2) instead of a
+// kernel boundary.  Population loads bypass L1 (ld.global.cg): other blocks rewrite those lines
+// every step and L1 is not coherent.  Boundary-list nodes are taken by the grid's LAST threads (the tail of
+// the index space is padding and ghost nodes), so they run beside the bulk nodes, not after them.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// `bar` counts arrivals cumulatively (zeroed by the host before the launch)
+__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    while (ld_acquire_gpu_u32(bar) < target) { }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <class L, int MODEL>
+__global__ void __launch_bounds__(256)
+collide_multistep(const DevParams P, const SlotTable<L> Te, const SlotTable<L> To,
+                  const uint32_t *__restrict__ fluid_mask, const uint32_t *__restrict__ map,
+                  const uint32_t *__restrict__ list, unsigned nlist, float *dist,
+                  float *__restrict__ orho, float *__restrict__ ovx, float *__restrict__ ovy,
+                  float *__restrict__ ovz, long long gi0, unsigned n, unsigned it0, int nsteps, int save_last,
+                  unsigned int *bar) {
+  const unsigned gsize = gridDim.x * 256u;
+  const unsigned gtid = blockIdx.x * 256u + threadIdx.x;
+  const unsigned rtid = gsize - 1u - gtid;
+  for (int s = 0; s < nsteps; s++) {
+    const bool odd = ((it0 + (unsigned)s) & 1u) != 0;
+    const bool save = save_last && s == nsteps - 1;
+    for (unsigned t = gtid; t < n; t += gsize) {
+      const long long gi = gi0 + t;
+      if (!((fluid_mask[gi >> 5] >> (gi & 31)) & 1u)) continue;
+      if (save) {
+        if (odd) bulk_aa_node<L, MODEL, true, 2>(P, To, orho, ovx, ovy, ovz, gi, t);
+        else bulk_aa_node<L, MODEL, true, 2>(P, Te, orho, ovx, ovy, ovz, gi, t);
+      } else {
+        if (odd) bulk_aa_node<L, MODEL, false, 2>(P, To, orho, ovx, ovy, ovz, gi, t);
+        else bulk_aa_node<L, MODEL, false, 2>(P, Te, orho, ovx, ovy, ovz, gi, t);
+      }
+    }
+    for (unsigned k = rtid; k < nlist; k += gsize) {
+      const long long gi = list[k];
+      if (save) {
+        if (odd) boundary_node<L, MODEL, MODE_AA_ODD, true, 2>(P, map, dist, dist, orho, ovx, ovy, ovz, gi, false);
+        else boundary_node<L, MODEL, MODE_AA_EVEN, true, 2>(P, map, dist, dist, orho, ovx, ovy, ovz, gi, false);
+      } else {
+        if (odd) boundary_node<L, MODEL, MODE_AA_ODD, false, 2>(P, map, dist, dist, orho, ovx, ovy, ovz, gi, false);
+        else boundary_node<L, MODEL, MODE_AA_EVEN, false, 2>(P, map, dist, dist, orho, ovx, ovy, ovz, gi, false);
+      }
+    }
+    if (s + 1 < nsteps) grid_barrier(bar, gridDim.x * (unsigned)(s + 1));
+  }
 }
 
 // ----------------------------------------------------------------------------------------

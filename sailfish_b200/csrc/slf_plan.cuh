@@ -54,6 +54,16 @@ int slf_collide_d3q19_mrt(SlfPlan *pl, int mode, bool save, const uint32_t *map,
 int slf_collide_d3q27(SlfPlan *pl, int mode, bool save, const uint32_t *map, const float *din, float *dout,
                       float *rho, float *vx, float *vy, float *vz, int z0, int z1, cudaStream_t s);
 
+// many steps in one cooperative launch (small lattices); 1 = does not qualify
+int slf_multistep_d2q9(SlfPlan *pl, int model, const uint32_t *map, float *dist, float *rho, float *vx, float *vy,
+                       float *vz, uint32_t it0, int nsteps, int save_last, cudaStream_t s);
+int slf_multistep_d3q19_bgk(SlfPlan *pl, const uint32_t *map, float *dist, float *rho, float *vx, float *vy, float *vz,
+                            uint32_t it0, int nsteps, int save_last, cudaStream_t s);
+int slf_multistep_d3q19_mrt(SlfPlan *pl, const uint32_t *map, float *dist, float *rho, float *vx, float *vy, float *vz,
+                            uint32_t it0, int nsteps, int save_last, cudaStream_t s);
+int slf_multistep_d3q27(SlfPlan *pl, const uint32_t *map, float *dist, float *rho, float *vx, float *vy, float *vz,
+                        uint32_t it0, int nsteps, int save_last, cudaStream_t s);
+
 #define SLF_LATTICE_SWITCH(pl, CALL)            \
   switch ((pl)->hp.lattice) {                    \
     case SLF_D2Q9: { using L = D2Q9; CALL; } break;   \
