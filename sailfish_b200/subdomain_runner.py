@@ -11,6 +11,7 @@ and the same per-step order (boundary slabs -> halo -> bulk -> PBC), but
     device-side semaphores -- the host never touches halo data.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -400,6 +401,22 @@ class SubdomainRunner(object):
                 dev.collide(save_macro=sync_req, stream=cs)
                 dev.apply_pbc(stream=cs)
                 self._push_all(swap, cs, it)
+            elif os.environ.get('SLF_STEP_SCHEME', 'concurrent') == 'serial':
+                # slabs ahead of the interior on the calc stream, only the pushes overlap (A/B switch for measurements)
+                self._wait_incoming(0, it - 1, cs)
+                lo, hi = 1, n - 1
+                if 0 in links:
+                    dev.collide(save_macro=sync_req, z_begin=1, z_end=2, stream=cs)
+                    lo = 2
+                if 1 in links and n - 2 >= lo:
+                    dev.collide(save_macro=sync_req, z_begin=n - 2, z_end=n - 1, stream=cs)
+                    hi = n - 2
+                self._fork_event.record(cs)
+                ds.wait_for_event(self._fork_event)
+                self._push_all(swap, ds, it)
+                if hi > lo:
+                    dev.collide(save_macro=sync_req, z_begin=lo, z_end=hi, stream=cs)
+                cs.wait_for_event(self._push_events[0][it & 1])
             else:
                 self._fork_event.record(cs)
                 ds.wait_for_event(self._fork_event)
@@ -470,7 +487,7 @@ class SubdomainRunner(object):
             return
         plain = n - (1 if save_last else 0)
         done = 0
-        if self._uses_semaphores() and plain >= 4 and not getattr(self.config, 'no_step_graphs', False):
+        if self._uses_semaphores() and plain >= 4 and not getattr(self.config, 'no_step_graphs', False) and not os.environ.get('SLF_NO_STEP_GRAPHS'):
             g = self._step_graph(self._dev.iteration & 1)
             for _ in range(plain // 2):
                 self._lib.call('slf_graph_launch', g, self._calc_stream.handle)
@@ -681,7 +698,7 @@ class NNSubdomainRunner(SubdomainRunner):
         plain = n - (1 if save_last else 0)
         done = 0
         if ((not self._links or self._uses_semaphores()) and plain >= 4
-                and not getattr(self.config, 'no_step_graphs', False)):
+                and not getattr(self.config, 'no_step_graphs', False) and not os.environ.get('SLF_NO_STEP_GRAPHS')):
             g = self._step_graph(self._dev.iteration & 1)
             for _ in range(plain // 2):
                 self._lib.call('slf_graph_launch', g, self._calc_stream.handle)

@@ -24,8 +24,8 @@ CONFIGS = [
     ('C2ab ldc_3d D3Q19 BGK 256^3 AB', ldc_3d.LDCSim, None,
      ['--lat_nx=256', '--lat_ny=256', '--lat_nz=256', '--visc=0.03175', '--access_pattern=AB'], 400, 152),
     ('C3 poiseuille_3d D3Q19 MRT 128x128x512 pressure', poiseuille_3d.PoiseuilleSim, EqualSubdomainsGeometry3D,
-     ['--lat_nx=128', '--lat_ny=128', '--lat_nz=512', '--flow_direction=z', '--drive=pressure', '--stationary',
-      '--model=mrt', '--visc=0.1', '--access_pattern=AA'], 1000, 152),
+     ['--lat_nx=128', '--lat_ny=128', '--lat_nz=512', '--flow_direction=z', '--drive=pressure',
+      '--model=mrt', '--visc=0.1', '--access_pattern=AA'], 1000, 152),      # (no --stationary: see tests/test_gpu_full_size.py)
     ('C3f poiseuille_3d D3Q19 BGK 128x128x512 force+PBC', poiseuille_3d.PoiseuilleSim, EqualSubdomainsGeometry3D,
      ['--lat_nx=128', '--lat_ny=128', '--lat_nz=512', '--flow_direction=z', '--drive=force',
       '--visc=0.1', '--access_pattern=AA'], 1000, 152),
