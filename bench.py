@@ -462,15 +462,17 @@ def main():
         r = ctrl.runners[0]
 
         def barrier():
+            ctrl.sync()                      # own streams idle first, so that every rank leaves the rendezvous together
             if ws > 1 and not ctrl._local:
                 dist.barrier()
             torch.cuda.synchronize()
-            ctrl.sync()
-        ctrl.run_steps(warm)
-        barrier()
         if sampler_box is not None and rank == 0:
+            # started BEFORE the rendezvous: initialising NVML takes milliseconds, and a rank that enters the timed
+            # region late makes its neighbours wait for its ghost layers inside theirs
             sampler_box.append(ClockSampler(local_rank))
             sampler_box[0].start()
+        ctrl.run_steps(warm)
+        barrier()
         l0 = lib.launch_count()
         ev0 = r.backend.make_event(r._calc_stream, timing=True)
         ctrl.run_steps(steps)

@@ -26,7 +26,12 @@ static int launch_collide(SlfPlan *pl, const uint32_t *map, const float *din, fl
         LAUNCH_OK("collide_bulk_aa");
       }
     }
-    if (MODE == MODE_AB || !plain) {
+    if (MODE == MODE_AB && plain) {
+      collide_bulk_ab_tab<L, MODEL, SAVE><<<(unsigned)nb, bs, 0, s>>>(
+          pl->dp, make_ab_table<L>(pl->dp, din, dout, gi0), pl->d_fluid_mask, pl->d_wall_mask, rho, vx, vy, vz, gi0,
+          (unsigned)n);
+      LAUNCH_OK("collide_bulk_ab");
+    } else if (MODE == MODE_AB || !plain) {
       if (bound)
         collide_bulk<L, MODEL, MODE, SAVE, true><<<(unsigned)nb, bs, 0, s>>>(
             pl->dp, map, pl->d_fluid_mask, pl->d_wall_mask, din, dout, rho, vx, vy, vz, gi0, gi1);

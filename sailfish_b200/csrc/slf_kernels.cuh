@@ -169,6 +169,59 @@ collide_bulk_aa_tab(const DevParams P, const SlotTable<L> T, const uint32_t *__r
   bulk_aa_node<L, MODEL, SAVE>(P, T, orho, ovx, ovy, ovz, gi, t);
 }
 
+// AB (two-lattice) counterpart: loads from `din` at the node, stores to `dout` at the downstream neighbours, both
+// through per-slot base pointers.  Measured (tools/exp_ab.cu on B200, profiles/r02_exp_ab.txt): the tables are worth
+// +1 % over 64-bit index arithmetic on this kernel, and a shared-memory x shift that turns every store into whole
+// aligned lines changes nothing (33.6 vs 33.4 GLUPS) -- the AB pattern is bound by its 38 concurrent DRAM streams
+// (19 read in one array, 19 written in the other), not by partially written sectors.  Full-way bounce-back walls are
+// applied here (reflect, then stream), as in collide_bulk.
+template <class L> struct SlotTableAB { const float *ld[L::Q]; float *st[L::Q]; };
+
+template <class L, int MODEL, bool SAVE>
+__global__ void __launch_bounds__(128, BulkTuning<L, MODEL>::MINB)
+collide_bulk_ab_tab(const DevParams P, const SlotTableAB<L> T, const uint32_t *__restrict__ fluid_mask,
+                    const uint32_t *__restrict__ wall_mask, float *__restrict__ orho, float *__restrict__ ovx,
+                    float *__restrict__ ovy, float *__restrict__ ovz, long long gi0, unsigned n) {
+  const unsigned t = blockIdx.x * 128u + threadIdx.x;
+  if (t >= n) return;
+  const long long gi = gi0 + t;
+  const uint32_t bit = 1u << (gi & 31);
+  const bool is_fluid = (fluid_mask[gi >> 5] & bit) != 0;
+  const bool is_wall = (wall_mask[gi >> 5] & bit) != 0;
+  if (!is_fluid && !is_wall) return;
+  float f[L::Q];
+#pragma unroll
+  for (int i = 0; i < L::Q; i++) f[i] = T.ld[i][t];
+  if (is_wall) {
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) T.st[i][t] = f[L::opp(i)];
+    return;
+  }
+  float rho, v[3];
+  moments<L>(f, rho, v);
+  const float inv = 1.0f / rho;
+  v[0] *= inv; v[1] *= inv; v[2] *= inv;
+  if (MODEL == SLF_MRT) collide_mrt<L, false>(P, v, f);
+  else collide_bgk<L>(P, rho, v, f);
+  if (SAVE) {
+    orho[gi] = rho; ovx[gi] = v[0]; ovy[gi] = v[1];
+    if (L::D == 3) ovz[gi] = v[2];
+  }
+#pragma unroll
+  for (int i = 0; i < L::Q; i++) T.st[i][t] = f[i];
+}
+
+template <class L>
+static inline SlotTableAB<L> make_ab_table(const DevParams &P, const float *din, float *dout, long long gi0) {
+  SlotTableAB<L> T;
+  for (int i = 0; i < L::Q; i++) {
+    const long long off = (long long)L::ex(i) + P.sy * L::ey(i) + P.sz * L::ez(i);
+    T.ld[i] = din + P.DS * i + gi0;
+    T.st[i] = dout + P.DS * i + gi0 + off;
+  }
+  return T;
+}
+
 template <class L>
 static inline SlotTable<L> make_aa_table(const DevParams &P, float *dist, long long gi0, bool odd) {
   SlotTable<L> T;

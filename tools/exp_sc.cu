@@ -67,6 +67,79 @@ k_tile(const DevParams P, const ScParams S, const ScTables<L> T, int s) {
   fused_node(P, S, T, (unsigned)(x + P.sy * y + P.sz * z));
 }
 
+// smem-staged psi stencil: the block's (TX+2) x (TY+2) x (TZ+2) halo tile of rho and phi is loaded once
+// (coalesced rows) and the 2 x 18 neighbour values of every node come from shared memory.
+template <int TX, int TY, int TZ, int MINB>
+__global__ void __launch_bounds__(TX * TY * TZ, MINB)
+k_smem(const DevParams P, const ScParams S, const ScTables<L> T, const float *__restrict__ rho,
+       const float *__restrict__ phi, int s) {
+  constexpr int HX = TX + 2, HY = TY + 2, HZ = TZ + 2, NT = TX * TY * TZ;
+  __shared__ float sm[2][HZ][HY][HX];
+  const int tid = threadIdx.x;
+  const int lx = tid % TX, ly = (tid / TX) % TY, lz = tid / (TX * TY);
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, z0 = blockIdx.z * TZ;      // real-node coordinates (0-based)
+  // node (x, y, z) real -> array index (x + 1, y + 1, z + 1); the halo starts one node before the tile
+  for (int idx = tid; idx < HX * HY * HZ; idx += NT) {
+    const int hx = idx % HX, hy = (idx / HX) % HY, hz = idx / (HX * HY);
+    const int ax = x0 + hx, ay = y0 + hy, az = z0 + hz;                              // array coordinates
+    float a = 0.f, b = 0.f;
+    if (ax < P.ax && ay < P.ay && az < P.az) {
+      const long long gi = ax + P.sy * ay + P.sz * az;
+      a = rho[gi]; b = phi[gi];
+    }
+    sm[0][hz][hy][hx] = a; sm[1][hz][hy][hx] = b;
+  }
+  __syncthreads();
+  const int x = x0 + lx, y = y0 + ly, z = z0 + lz;
+  if (x >= s || y >= s || z >= s) return;
+  const unsigned t = (unsigned)(x + P.sy * y + P.sz * z);
+  float f0[L::Q], f1[L::Q];
+#pragma unroll
+  for (int i = 0; i < L::Q; i++) f0[i] = T.ld1[i][t];
+#pragma unroll
+  for (int i = 0; i < L::Q; i++) f1[i] = T.ld2[i][t];
+  const float g0 = sm[0][lz + 1][ly + 1][lx + 1], g1 = sm[1][lz + 1][ly + 1][lx + 1];
+  float grad0[3] = {0.f, 0.f, 0.f}, grad1[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+#pragma unroll
+    for (int i = 1; i < L::Q; i++) {
+      const float psi = sm[k][lz + 1 + L::ez(i)][ly + 1 + L::ey(i)][lx + 1 + L::ex(i)];
+      if (L::ex(i)) fx = fmaf(psi, (float)L::ex(i) * L::w(i), fx);
+      if (L::ey(i)) fy = fmaf(psi, (float)L::ey(i) * L::w(i), fy);
+      if (L::ez(i)) fz = fmaf(psi, (float)L::ez(i) * L::w(i), fz);
+    }
+    if (k == 0) { grad0[0] = fx; grad0[1] = fy; grad0[2] = fz; } else { grad1[0] = fx; grad1[1] = fy; grad1[2] = fz; }
+  }
+  float r0, r1, j0[3], j1[3];
+  moments<L>(f0, r0, j0);
+  moments<L>(f1, r1, j1);
+  const float total = S.tau0_inv * r0 + S.tau1_inv * r1;
+  const float v[3] = {(S.tau0_inv * j0[0] + S.tau1_inv * j1[0]) / total, (S.tau0_inv * j0[1] + S.tau1_inv * j1[1]) / total,
+                      (S.tau0_inv * j0[2] + S.tau1_inv * j1[2]) / total};
+  {
+    float a[3] = {0.f, 0.f, 0.f};
+    if (S.g[0] != 0.0f) sc_add_force(S.potential, g0, S.g[0], grad0, a);
+    if (S.g[1] != 0.0f) sc_add_force(S.potential, g0, S.g[1], grad1, a);
+    const float ig = 1.0f / g0;
+    a[0] *= ig; a[1] *= ig; a[2] *= ig;
+    sc_relax<L>(f0, g0, a, v, S.omega[0], S.tau[0]);
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) T.st1[i][t] = f0[i];
+  }
+  {
+    float a[3] = {0.f, 0.f, 0.f};
+    if (S.g[2] != 0.0f) sc_add_force(S.potential, g1, S.g[2], grad0, a);
+    if (S.g[3] != 0.0f) sc_add_force(S.potential, g1, S.g[3], grad1, a);
+    const float ig = 1.0f / g1;
+    a[0] *= ig; a[1] *= ig; a[2] *= ig;
+    sc_relax<L>(f1, g1, a, v, S.omega[1], S.tau[1]);
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) T.st2[i][t] = f1[i];
+  }
+}
+
 struct Ctx {
   DevParams P;
   ScParams S;
@@ -133,6 +206,11 @@ static void run(const char *name, Ctx &c, K launch, bool is_ref) {
         dim3 grid((c.s + TX - 1) / TX, (c.s + TY - 1) / TY, (c.s + TZ - 1) / TZ);                          \
         k_tile<TX, TY, TZ, MINB><<<grid, TX * TY * TZ>>>(c.P, c.S, tables(c, odd), c.s); }, REF)
 
+#define SVARIANT(TX, TY, TZ, MINB)                                                                        \
+  run("smem " #TX "x" #TY "x" #TZ " minb" #MINB, c, [](Ctx &c, bool odd) {                                \
+        dim3 grid((c.s + TX - 1) / TX, (c.s + TY - 1) / TY, (c.s + TZ - 1) / TZ);                          \
+        k_smem<TX, TY, TZ, MINB><<<grid, TX * TY * TZ>>>(c.P, c.S, tables(c, odd), c.rho, c.phi, c.s); }, false)
+
 int main(int argc, char **argv) {
   Ctx c;
   c.s = argc > 1 ? atoi(argv[1]) : 256;
@@ -173,5 +251,13 @@ int main(int argc, char **argv) {
   VARIANT(32, 4, 2, 2, false);
   VARIANT(64, 2, 1, 5, false);
   VARIANT(64, 2, 2, 2, false);
+  SVARIANT(32, 2, 2, 6);
+  SVARIANT(32, 4, 2, 3);
+  SVARIANT(32, 4, 2, 2);
+  SVARIANT(32, 4, 4, 1);
+  SVARIANT(32, 8, 2, 1);
+  SVARIANT(32, 2, 4, 3);
+  SVARIANT(32, 4, 1, 6);
+  SVARIANT(64, 2, 2, 3);
   return 0;
 }
