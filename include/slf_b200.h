@@ -283,6 +283,15 @@ int  slf_distribute_continuous_macro_data(SlfPlan *plan, uint64_t field, int fac
  */
 int  slf_halo_push(SlfPlan *plan, uint64_t dist, int face, uint64_t peer_dist, int peer_lat_n,
                    int peer_arr_n, int with_swap, uint64_t signal_sem, uint64_t stream);
+/* The same for ANY face of a subdomain that is split along x and / or y as well (block decompositions,
+ * regtest/subdomains/3d_ldc.py).  Replaces, together with a dimension-ordered schedule of the caller (all x faces,
+ * then y, then z; the caller waits for axis k before it pushes axis k + 1), the reference's per-pair face, edge and
+ * corner connections with their sparse index lists (subdomain_connection.py:348-407, Collect/DistributeSparseData,
+ * subdomain_runner.py:624-738): edge and corner data travel in the ghost ring of the face messages and reach their
+ * diagonal destination in two or three hops.  peer_lat / peer_arr: the neighbour's lattice / array extents (x, y, z);
+ * cross-sections must be equal.  The copied windows are disjoint between messages (see csrc/slf_halo.cuh). */
+int  slf_halo_push_face(SlfPlan *plan, uint64_t dist, int face, uint64_t peer_dist, const int *peer_lat,
+                        const int *peer_arr, int with_swap, uint64_t signal_sem, uint64_t stream);
 /* Stream-ordered counting semaphores in device memory for cross-GPU ordering of the pushes
  * (they stand where the reference blocks in zmq recv, connector.py:73-117).  A subdomain owns a
  * zero-initialised block of uint32 words: ready[channel][side] (incremented by the neighbour on

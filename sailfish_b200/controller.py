@@ -72,24 +72,40 @@ class LBSimulationController(object):
 
     # -- set-up --------------------------------------------------------------------------------
     def _make_specs(self):
+        """Subdomain list + face connections (controller.py:155-269 of the reference: _connect_subdomains and local
+        periodicity).  Two subdomains are neighbours across an axis when one ends where the other begins (modulo the
+        global size on a periodic axis) and they share the WHOLE face; edge and corner neighbours need no connection
+        of their own here (dimension-ordered exchange)."""
         cfg = self.config
         self.geo = self._lb_geo(cfg)
         specs = self.geo.subdomains()
-        axis = self.dim - 1
-        per = [bool(getattr(cfg, 'periodic_' + a, False)) for a in 'xyz'[:self.dim]]
-        n = len(specs)
-        for s in specs:
-            for a in range(self.dim):
-                if per[a] and (a != axis or n == 1):
-                    s.enable_local_periodicity(a)     # controller.py:155-269 (local periodicity)
-        lo_face, hi_face = 2 * axis, 2 * axis + 1
-        for i, s in enumerate(specs):
-            if i + 1 < n:
-                s.connect(hi_face, i + 1)
-                specs[i + 1].connect(lo_face, i)
-        if n > 1 and per[axis]:
-            specs[-1].connect(hi_face, 0)
-            specs[0].connect(lo_face, n - 1)
+        gsize = list(self.geo.gsize)
+        dim = self.dim
+        per = [bool(getattr(cfg, 'periodic_' + a, False)) for a in 'xyz'[:dim]]
+        for a in range(dim):
+            spans = set((s.location[a], s.size[a]) for s in specs)
+            whole = all(sz == gsize[a] for _, sz in spans)
+            if per[a] and whole:
+                for s in specs:
+                    s.enable_local_periodicity(a)     # one block along this axis: PBC kernels
+            if whole:
+                continue
+            for s in specs:
+                end = s.location[a] + s.size[a]
+                if end == gsize[a]:
+                    if not per[a]:
+                        continue
+                    end = 0                            # wrap-around neighbour
+                for o in specs:
+                    if o is s or o.location[a] != end:
+                        continue
+                    if all(o.location[b] == s.location[b] and o.size[b] == s.size[b] for b in range(dim) if b != a):
+                        s.connect(2 * a + 1, o.id)
+                        o.connect(2 * a, s.id)
+                    elif all(o.location[b] < s.location[b] + s.size[b] and s.location[b] < o.location[b] + o.size[b]
+                             for b in range(dim) if b != a):
+                        raise NotImplementedError('subdomains %d and %d touch across %s but do not share a whole face'
+                                                  % (s.id, o.id, 'xyz'[a]))
         return specs
 
     def _distributed(self):
@@ -144,38 +160,41 @@ class LBSimulationController(object):
     def _link(self, dist_mode, rank, ws):
         """Exchanges buffer addresses between neighbours: plain pointers inside one process, CUDA
         IPC handles (backend_cuda.py:122-126 wraps them, never uses them) across ranks."""
-        axis = self.dim - 1
         by_id = dict((r._spec.id, r) for r in self.runners)
         remote = {}
+
+        def geometry(r):
+            return dict(lat=list(reversed(r._lat_size)), arr=list(reversed(r._physical_size)))
         if dist_mode:
             import torch.distributed as dist
             if not dist.is_initialized():
                 dist.init_process_group('gloo')
             mine = self.runners[0]
             be = mine.backend
-            payload = dict(id=mine._spec.id, lat_n=mine._lat_size[0], arr_n=mine._physical_size[0],
-                           bufs=dict((k, be.ipc_handle(v) if v else None) for k, v in mine.export_buffers().items()))
+            payload = dict(id=mine._spec.id, bufs=dict((k, be.ipc_handle(v) if v else None)
+                                                       for k, v in mine.export_buffers().items()), **geometry(mine))
             gathered = [None] * ws
             dist.all_gather_object(gathered, payload)
             needed = set(mine._spec._face_conn.values())
             for g in gathered:
                 if g['id'] in needed and g['id'] != mine._spec.id:
-                    remote[g['id']] = dict(lat_n=g['lat_n'], arr_n=g['arr_n'],
+                    remote[g['id']] = dict(lat=g['lat'], arr=g['arr'],
                                            bufs=dict((k, int(be.ipc_handle_wrap(h)) if h else 0)
                                                      for k, h in g['bufs'].items()))
             self._dist = dist
         for r in self.runners:
-            for face, other in r._spec._face_conn.items():
-                if face // 2 != axis:
-                    continue
+            for face, other in sorted(r._spec._face_conn.items()):
+                axis = face // 2
                 if other in by_id:
                     o = by_id[other]
-                    r.add_link(HaloLink(face, o.export_buffers(), o._lat_size[0], o._physical_size[0],
-                                        peer_runner=o))
+                    g = geometry(o)
+                    r.add_link(HaloLink(face, o.export_buffers(), g['lat'][axis], g['arr'][axis], peer_runner=o,
+                                        peer_lat=g['lat'], peer_arr=g['arr']))
                 else:
                     info = remote[other]
-                    r.add_link(HaloLink(face, info['bufs'], info['lat_n'], info['arr_n'],
-                                        peer_sems=info['bufs']['sems'], my_sems=int(r._sems)))
+                    r.add_link(HaloLink(face, info['bufs'], info['lat'][axis], info['arr'][axis],
+                                        peer_sems=info['bufs']['sems'], my_sems=int(r._sems),
+                                        peer_lat=info['lat'], peer_arr=info['arr']))
 
     # -- running -------------------------------------------------------------------------------
     def barrier(self):

@@ -99,6 +99,48 @@ __global__ void sem_wait_kernel(const unsigned int *ready_a, const unsigned int 
   *seq = want + 1u - ahead;
 }
 
+// ---- any face (subdomains split along x and / or y as well: regtest/subdomains/3d_ldc.py block layouts) ------
+// The reference connects every pair of subdomains that share a face, an edge or a corner and ships each
+// population set separately (subdomain_connection.py:348-407, sparse index lists for x faces, edges and
+// corners).  Here the exchange is dimension ordered -- all x faces, then all y faces, then z -- and edge / corner
+// data reach their diagonal destination in two or three hops, riding in the ghost ring of the face messages.
+// Per face and crossing population i the copied window is chosen such that (a) forwarded data are included and
+// (b) no two messages ever write the same location (so no ordering between different senders is needed):
+//   along an EARLIER axis (already exchanged in this step): the whole extent, ghost ring included;
+//   along a LATER axis b: after in-place steps (with_swap) the real nodes 1 .. n_b - 2; after streaming steps the
+//   real nodes shifted by e_i[b] (the entries of the ghost layer that real nodes of this subdomain streamed into).
+struct FaceArgs {
+  const float *src[9];
+  float *dst[9];
+  int lo1[9], n1[9], lo2[9], n2[9];     // window along the two other axes (other1 < other2)
+  long long s1, s2, d1, d2;             // strides of those axes in the source / destination array
+  int n;
+  unsigned int *signal, *done;
+};
+
+__global__ void __launch_bounds__(128) halo_push_face_kernel(const FaceArgs a) {
+  const int k = blockIdx.z;
+  const int i1 = blockIdx.x * blockDim.x + threadIdx.x, i2 = blockIdx.y;
+  if (i1 < a.n1[k] && i2 < a.n2[k]) {
+    const long long so = (long long)(a.lo1[k] + i1) * a.s1 + (long long)(a.lo2[k] + i2) * a.s2;
+    const long long dn = (long long)(a.lo1[k] + i1) * a.d1 + (long long)(a.lo2[k] + i2) * a.d2;
+    a.dst[k][dn] = a.src[k][so];
+  }
+  __threadfence_system();
+  if (a.signal) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+      const unsigned int prev = atomicAdd(a.done, 1u);
+      if (prev == total - 1u) {
+        *a.done = 0u;
+        __threadfence_system();
+        atomicAdd_system(a.signal, 1u);
+      }
+    }
+  }
+}
+
 static unsigned long long sem_timeout_ns() {
   static unsigned long long v = 0;
   if (!v) {
@@ -150,6 +192,62 @@ int slf_halo_push(SlfPlan *pl, uint64_t dist, int face, uint64_t peer_dist, int 
   dim3 grid(bx, a.n);
   halo_push_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   LAUNCH_OK("halo_push");
+  return 0;
+}
+
+int slf_halo_push_face(SlfPlan *pl, uint64_t dist, int face, uint64_t peer_dist, const int *peer_lat, const int *peer_arr,
+                       int with_swap, uint64_t signal_sem, uint64_t stream) {
+  if (!pl) return fail(SLF_EINVAL, "null plan");
+  if (!peer_lat || !peer_arr) return fail(SLF_EINVAL, "null peer geometry");
+  const DevParams &d = pl->dp;
+  const int D = pl->D, axis = face >> 1, hi = face & 1;
+  if (face < 0 || axis >= D) return fail(SLF_EINVAL, "bad face");
+  const int lat[3] = {d.nx, d.ny, d.nz};
+  const long long str[3] = {1, d.sy, d.sz};
+  const long long pstr[3] = {1, (long long)peer_arr[0], (long long)peer_arr[0] * peer_arr[1]};
+  const long long peer_DS = (long long)peer_arr[0] * peer_arr[1] * (D == 3 ? peer_arr[2] : 1);
+  int o1, o2;                                    // the other axes, o1 < o2 (2-D: o2 unused)
+  if (D == 2) { o1 = 1 - axis; o2 = 2; } else { o1 = axis == 0 ? 1 : 0; o2 = axis == 2 ? 1 : 2; }
+  if (lat[o1] != peer_lat[o1] || (D == 3 && lat[o2] != peer_lat[o2]))
+    return fail(SLF_EUNSUPPORTED, "neighbouring subdomains must share the whole face (equal cross-sections)");
+  const int n = lat[axis], pn = peer_lat[axis];
+  const int src_layer = with_swap ? (hi ? n - 2 : 1) : (hi ? n - 1 : 0);
+  const int dst_layer = with_swap ? (hi ? 0 : pn - 1) : (hi ? 1 : pn - 2);
+  FaceArgs a;
+  a.n = 0; a.s1 = str[o1]; a.d1 = pstr[o1];
+  a.s2 = D == 3 ? str[o2] : 0; a.d2 = D == 3 ? pstr[o2] : 0;
+  a.signal = (unsigned int *)signal_sem;
+  a.done = signal_sem ? pl->d_push_done + hi : nullptr;
+  const int sgn = hi ? 1 : -1;
+  int max1 = 0, max2 = 1;
+  for (int i = 0; i < pl->Q; i++) {
+    int e[3], opp;
+    switch (pl->hp.lattice) {
+      case SLF_D2Q9: e[0] = D2Q9::ex(i); e[1] = D2Q9::ey(i); e[2] = 0; opp = D2Q9::opp(i); break;
+      case SLF_D3Q19: e[0] = D3Q19::ex(i); e[1] = D3Q19::ey(i); e[2] = D3Q19::ez(i); opp = D3Q19::opp(i); break;
+      default: e[0] = D3Q27::ex(i); e[1] = D3Q27::ey(i); e[2] = D3Q27::ez(i); opp = D3Q27::opp(i); break;
+    }
+    if (e[axis] * sgn < 1) continue;
+    const int slot = with_swap ? opp : i;
+    const int oth[2] = {o1, o2};
+    int lo[2] = {0, 0}, cnt[2] = {1, 1};
+    for (int b = 0; b < D - 1; b++) {
+      const int ax = oth[b];
+      if (ax < axis) { lo[b] = 0; cnt[b] = lat[ax]; }                          // earlier axis: ghost ring included
+      else if (with_swap) { lo[b] = 1; cnt[b] = lat[ax] - 2; }                 // later axis, un-streamed data: real nodes
+      else { lo[b] = 1 + e[ax]; cnt[b] = lat[ax] - 2; }                        // later axis, streamed data: shifted by e_i
+    }
+    a.src[a.n] = (const float *)dist + d.DS * slot + str[axis] * src_layer;
+    a.dst[a.n] = (float *)peer_dist + peer_DS * slot + pstr[axis] * dst_layer;
+    a.lo1[a.n] = lo[0]; a.n1[a.n] = cnt[0]; a.lo2[a.n] = lo[1]; a.n2[a.n] = cnt[1];
+    if (cnt[0] > max1) max1 = cnt[0];
+    if (cnt[1] > max2) max2 = cnt[1];
+    a.n++;
+  }
+  if (a.n == 0 || max1 <= 0) return 0;
+  dim3 grid((max1 + 127) / 128, max2, a.n);
+  halo_push_face_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  LAUNCH_OK("halo_push_face");
   return 0;
 }
 

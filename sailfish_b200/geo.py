@@ -46,9 +46,9 @@ class LBGeometry3D(LBGeometry):
 
 
 class _EqualMixin(object):
-    """geo.py:69-135: --subdomains N --conn_axis {x,y,z}.  The B200 data plane exchanges
-    ghost layers along the outermost (slowest-varying) axis only, where a face message is a
-    run of contiguous planes: z in 3-D, y in 2-D."""
+    """geo.py:69-135: --subdomains N --conn_axis {x,y,z}.  The default axis is the outermost (slowest-varying)
+    one, where a face message is a run of contiguous planes (z in 3-D, y in 2-D) and the step overlaps the exchange
+    with the interior; other axes use the dimension-ordered face exchange."""
     @classmethod
     def add_options(cls, group):
         super(_EqualMixin, cls).add_options(group)
@@ -58,11 +58,9 @@ class _EqualMixin(object):
 
     def subdomains(self, n=None):
         n = self.config.subdomains if n is None else n
-        axis = self.dim - 1
-        want = {'x': 0, 'y': 1, 'z': 2}.get(self.config.conn_axis, axis)
-        if n > 1 and want != axis:
-            raise ValueError('B200 backend: subdomains are connected along the outermost axis (%s)'
-                             % 'xyz'[axis])
+        axis = {'x': 0, 'y': 1, 'z': 2}.get(self.config.conn_axis, self.dim - 1)
+        if axis >= self.dim:
+            raise ValueError('--conn_axis=%s in a %d-D simulation' % (self.config.conn_axis, self.dim))
         size = self.gsize
         total = size[axis]
         q, r = divmod(total, n)
@@ -75,6 +73,38 @@ class _EqualMixin(object):
             sz[axis] = ext
             specs.append(SubdomainSpec(tuple(loc), tuple(sz), id_=i))
         return specs
+
+
+class _BlockMixin(object):
+    """--blocks=BX,BY[,BZ]: a regular grid of blocks (the layouts of regtest/subdomains/{2d,3d}_ldc.py:
+    2 x 2 and 2 x 2 x 2 blocks; the last block of every axis takes the remainder)."""
+    @classmethod
+    def add_options(cls, group):
+        super(_BlockMixin, cls).add_options(group)
+        group.add_argument('--blocks', type=str, default='', help='blocks per axis, e.g. 2,2,2')
+        group.add_argument('--subdomains', type=int, default=1, help='(ignored when --blocks is given)')
+
+    def subdomains(self, n=None):
+        blocks = [int(b) for b in self.config.blocks.split(',')] if self.config.blocks else [1] * self.dim
+        if len(blocks) != self.dim or min(blocks) < 1:
+            raise ValueError('--blocks needs %d positive integers' % self.dim)
+        size = self.gsize
+        q = [size[a] // blocks[a] for a in range(self.dim)]
+        specs = []
+        import itertools
+        for idx in itertools.product(*[range(b) for b in blocks]):
+            loc = [idx[a] * q[a] for a in range(self.dim)]
+            sz = [q[a] if idx[a] < blocks[a] - 1 else size[a] - q[a] * (blocks[a] - 1) for a in range(self.dim)]
+            specs.append(SubdomainSpec(tuple(loc), tuple(sz), id_=len(specs)))
+        return specs
+
+
+class BlockSubdomainsGeometry2D(_BlockMixin, LBGeometry2D):
+    pass
+
+
+class BlockSubdomainsGeometry3D(_BlockMixin, LBGeometry3D):
+    pass
 
 
 class EqualSubdomainsGeometry2D(_EqualMixin, LBGeometry2D):

@@ -47,28 +47,37 @@ class HaloLink(object):
     mappings and ordering uses the stream-ordered device semaphores slf_sem_signal/slf_sem_wait:
     ``peer_sems`` is the neighbour's semaphore block, ``my_sems`` this runner's."""
 
-    def __init__(self, face, peer_bufs, peer_lat_n, peer_arr_n, peer_sems=0, my_sems=0, peer_runner=None):
+    def __init__(self, face, peer_bufs, peer_lat_n, peer_arr_n, peer_sems=0, my_sems=0, peer_runner=None,
+                 peer_lat=None, peer_arr=None):
         self.face = face
         self.side = face & 1
+        self.axis = face >> 1
         self.peer_bufs = dict((k, int(v) if v else 0) for k, v in peer_bufs.items())
         self.peer_lat_n = int(peer_lat_n)
         self.peer_arr_n = int(peer_arr_n)
+        # the neighbour's lattice / array extents (x, y[, z]): needed for faces other than the outermost axis
+        self.peer_lat = [int(v) for v in peer_lat] if peer_lat is not None else None
+        self.peer_arr = [int(v) for v in peer_arr] if peer_arr is not None else None
         self.peer_sems = int(peer_sems)
         self.my_sems = int(my_sems)
         self.peer_runner = peer_runner
 
     # semaphore block layout (uint32 words, csrc/slf_halo.cuh): channel c in {0: populations, 1: macro fields}
-    #   ready[c][side] at 8*c + side, seq[c] at 8*c + 2; status (error, abort) at 16, 17
+    #   ready[c][face] at 8*c + face, seq[c][axis] at 16 + 4*c + axis; status (error, abort) at 32, 33
     def my_ready(self, channel):
-        return self.my_sems + 4 * (8 * channel + self.side)
+        return self.my_sems + 4 * (8 * channel + self.face)
 
     def peer_ready(self, channel):
-        # the neighbour receives through its opposite side
-        return self.peer_sems + 4 * (8 * channel + (1 - self.side))
+        # the neighbour receives through its opposite face
+        return self.peer_sems + 4 * (8 * channel + (self.face ^ 1))
 
 
 SEM_BYTES = 256
-SEM_STATUS_WORD = 16
+SEM_STATUS_WORD = 32
+
+
+def sem_seq_word(channel, axis):
+    return 16 + 4 * channel + axis
 
 
 class LBOutput(object):
@@ -127,7 +136,9 @@ class SubdomainRunner(object):
         self._quit_event = quit_event
         self._scalar_fields, self._vector_fields = [], []
         self._field_base = {}
-        self._links = {}
+        self._links = {}               # side -> link across the outermost axis
+        self._xlinks = {}              # face -> link (every linked face)
+        self._general = False          # links across x / y faces: dimension-ordered exchange
         self._graphs = {}              # step parity -> captured pair of steps (linked subdomains)
         self._pre_checkpoint = None    # set by the controller: quiesce all subdomains / ranks
         self._lib = bk.lib()
@@ -213,6 +224,8 @@ class SubdomainRunner(object):
         self._lib.call('slf_memset', int(self._sems), 0, SEM_BYTES, 0)
         self._lib.call('slf_sync')
         self._push_events = [[self.backend.make_event(self._data_stream) for _ in range(2)] for _ in range(2)]
+        # block decompositions (links across x / y faces too): one event per axis and step parity
+        self._axis_events = [[self.backend.make_event(self._calc_stream) for _ in range(2)] for _ in range(3)]
         self._fork_event = self.backend.make_event(self._calc_stream)
 
     def initialize(self):
@@ -304,7 +317,16 @@ class SubdomainRunner(object):
         return {'dist0a': int(d.d_dist_a), 'dist0b': int(d.d_dist_b) if d.d_dist_b else 0, 'sems': int(self._sems)}
 
     def add_link(self, link):
-        self._links[link.face & 1] = link
+        outer = self.dim - 1
+        self._xlinks[link.face] = link
+        if link.axis == outer:
+            self._links[link.face & 1] = link
+        else:
+            self._general = True
+        if self._general and any(self._spec._periodicity):
+            raise P.UnsupportedConfiguration('native runner: a locally periodic axis next to subdomain links across x / y '
+                                             'faces is not supported (split the periodic axis too, or split along %s only)'
+                                             % 'xyz'[outer])
         self._drop_graphs()
         self._lib.call('slf_plan_set_links', self._dev.plan, int(0 in self._links), int(1 in self._links))
 
@@ -312,22 +334,30 @@ class SubdomainRunner(object):
         return self._lat_size[0]
 
     def _uses_semaphores(self):
-        return bool(self._links) and all(l.peer_runner is None for l in self._links.values())
+        return bool(self._xlinks) and all(l.peer_runner is None for l in self._xlinks.values())
 
-    def _wait_incoming(self, channel, it_prev, stream):
-        """Everything the neighbours pushed in their previous step has landed (events inside one process,
-        device semaphores across ranks: ONE wait kernel covers both sides)."""
+    def _wait_incoming(self, channel, it_prev, stream, axis=None, ahead=None):
+        """Everything the neighbours across `axis` (default: the outermost) pushed in step `it_prev` has landed
+        (events inside one process, device semaphores across ranks: ONE wait kernel covers both sides)."""
+        axis = self.dim - 1 if axis is None else axis
         ready = [0, 0]
-        for side, link in self._links.items():
+        for side in (0, 1):
+            link = self._xlinks.get(2 * axis + side)
+            if link is None:
+                continue
             if link.peer_runner is not None:
-                stream.wait_for_event(link.peer_runner._push_events[channel][it_prev & 1])
+                ev = (link.peer_runner._push_events[channel][it_prev & 1] if axis == self.dim - 1 and not self._general
+                      else link.peer_runner._axis_events[axis][it_prev & 1])
+                stream.wait_for_event(ev)
             else:
                 ready[side] = link.my_ready(channel)
         if ready[0] or ready[1]:
             sems = int(self._sems)
-            # populations: pushes of the previous steps; fields (channel 1): of this step too
-            self._lib.call('slf_sem_wait', ready[0], ready[1], sems + 4 * (8 * channel + 2),
-                           sems + 4 * SEM_STATUS_WORD, int(channel == 1), stream.handle)
+            # ahead = 0: pushes of the previous steps (populations across the last axis); 1: of this step too (fields,
+            # and the earlier axes of a dimension-ordered exchange)
+            ahead = int(channel == 1) if ahead is None else int(ahead)
+            self._lib.call('slf_sem_wait', ready[0], ready[1], sems + 4 * sem_seq_word(channel, axis),
+                           sems + 4 * SEM_STATUS_WORD, ahead, stream.handle)
 
     def check_peers(self):
         """Raises if a semaphore wait gave up (dead or diverged neighbour) since the last check."""
@@ -368,7 +398,57 @@ class SubdomainRunner(object):
 
     # -- stepping ---------------------------------------------------------------------------------
     def phases(self):
-        return ['step']
+        """What LBSimulationController issues for every local subdomain in turn.  Block decompositions exchange
+        dimension by dimension (csrc/slf_halo.cuh): a process that drives several subdomains must have pushed
+        axis k on all of them before any of them forwards that data along axis k + 1."""
+        if not self._general:
+            return ['step']
+        return ['_gstep_collide'] + ['_gstep_push_%d' % k for k in range(len(self._linked_axes()))] + ['_gstep_end']
+
+    def _linked_axes(self):
+        return sorted(set(f >> 1 for f in self._xlinks))
+
+    def _gstep_collide(self, sync_req):
+        dev = self._dev
+        axes = self._linked_axes()
+        # the planes pushed across the LAST axis in the previous step (the earlier axes were awaited in that step)
+        self._wait_incoming(0, dev.iteration - 1, self._calc_stream, axis=axes[-1], ahead=0)
+        dev.collide(save_macro=sync_req, stream=self._calc_stream)
+
+    def _gstep_push(self, k):
+        dev = self._dev
+        it = dev.iteration
+        cs = self._calc_stream
+        axes = self._linked_axes()
+        axis = axes[k]
+        swap = int(dev.aa and (it & 1) == 0)
+        if k > 0:
+            self._wait_incoming(0, it, cs, axis=axes[k - 1], ahead=1)      # forwarded data must have arrived
+        _, dout = dev.io_dists()
+        D = self.dim
+        for side in (0, 1):
+            link = self._xlinks.get(2 * axis + side)
+            if link is None:
+                continue
+            peer = link.peer_bufs['dist0a'] if (dev.aa or (it & 1)) else link.peer_bufs['dist0b']
+            plat = (ctypes.c_int * 3)(*(link.peer_lat + [1] * (3 - D)))
+            parr = (ctypes.c_int * 3)(*(link.peer_arr + [1] * (3 - D)))
+            self._lib.call('slf_halo_push_face', dev.plan, int(dout), link.face, peer, plat, parr, swap,
+                           0 if link.peer_runner is not None else link.peer_ready(0), cs.handle)
+        self._axis_events[axis][it & 1].record(cs)
+
+    def _gstep_push_0(self, sync_req):
+        self._gstep_push(0)
+
+    def _gstep_push_1(self, sync_req):
+        self._gstep_push(1)
+
+    def _gstep_push_2(self, sync_req):
+        self._gstep_push(2)
+
+    def _gstep_end(self, sync_req):
+        self._dev.iteration += 1
+        self._sim.iteration += 1
 
     def step(self, sync_req):
         """One time step.  Cf. subdomain_runner.py:960-1058 (boundary blocks -> send -> bulk -> receive).
@@ -389,6 +469,10 @@ class SubdomainRunner(object):
         n = self._outer_n()
         links = self._links
         local_pbc = any(self._spec._periodicity)
+        if self._general:
+            for ph in self.phases():
+                getattr(self, ph)(sync_req)
+            return
         if not links:
             dev.collide(save_macro=sync_req)
             dev.apply_pbc()

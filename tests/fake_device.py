@@ -199,6 +199,42 @@ class FakeLib(object):
             peer[s_, dst] = mine[s_, src]
         self.launches += 1
 
+    def _slf_halo_push_face(self, plan, dist, face, peer_dist, peer_lat, peer_arr, with_swap, signal, stream):
+        """Dimension-ordered exchange through any face (csrc/slf_halo.cuh: windows along the other axes)."""
+        from sailfish_b200 import lattice
+        p = self._p(plan)
+        D = p.dim
+        grid = lattice.get({0: 'D2Q9', 1: 'D3Q19', 2: 'D3Q27'}[p.lattice])
+        lat = [p.lat_nx, p.lat_ny, p.lat_nz][:D]
+        arr = [p.arr_nx, p.arr_ny, p.arr_nz][:D]
+        plat = [int(peer_lat[k]) for k in range(D)]
+        parr = [int(peer_arr[k]) for k in range(D)]
+        face, swap = int(face), bool(with_swap)
+        axis, hi = face // 2, face & 1
+        sgn = 1 if hi else -1
+        mine = self._arr(dist, np.float32, p.dist_size * p.Q).reshape([p.Q] + arr[::-1])
+        peer = self._arr(peer_dist, np.float32, int(np.prod(parr)) * p.Q).reshape([p.Q] + parr[::-1])
+        n, pn = lat[axis], plat[axis]
+        src_layer = (n - 2 if hi else 1) if swap else (n - 1 if hi else 0)
+        dst_layer = (0 if hi else pn - 1) if swap else (1 if hi else pn - 2)
+        for i, e in enumerate(grid.basis):
+            e = [int(c) for c in e]
+            if e[axis] * sgn < 1:
+                continue
+            slot = int(grid.opposite[i]) if swap else i
+            idx_s, idx_d = [None] * D, [None] * D
+            for ax in range(D):
+                if ax == axis:
+                    idx_s[ax], idx_d[ax] = src_layer, dst_layer
+                elif ax < axis:
+                    idx_s[ax] = idx_d[ax] = slice(0, lat[ax])
+                elif swap:
+                    idx_s[ax] = idx_d[ax] = slice(1, lat[ax] - 1)
+                else:
+                    idx_s[ax] = idx_d[ax] = slice(1 + e[ax], lat[ax] - 1 + e[ax])
+            peer[(slot,) + tuple(idx_d[::-1])] = mine[(slot,) + tuple(idx_s[::-1])]
+        self.launches += 1
+
     def _slf_halo_push_field(self, plan, field, face, peer_field, peer_lat_n, stream):
         p = self._p(plan)
         plane = p.dist_size // self._outer(p)
