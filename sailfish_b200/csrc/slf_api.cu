@@ -217,6 +217,8 @@ int slf_plan_destroy(SlfPlan *plan) {
   if (plan->d_wall_mask) cudaFree(plan->d_wall_mask);
   if (plan->d_list) cudaFree(plan->d_list);
   if (plan->d_push_done) cudaFree(plan->d_push_done);
+  if (plan->d_other_mask) cudaFree(plan->d_other_mask);
+  if (plan->d_flags) cudaFree(plan->d_flags);
   delete plan;
   return 0;
 }
@@ -237,7 +239,7 @@ int slf_plan_bind_map(SlfPlan *pl, uint64_t map) {
   std::vector<uint32_t> h((size_t)d.DS);
   CUDA_OK(cudaMemcpy(h.data(), (const void *)map, (size_t)d.DS * 4, cudaMemcpyDeviceToHost));
   const long long words = (d.DS + 31) / 32;
-  std::vector<uint32_t> fm((size_t)words, 0u), wm((size_t)words, 0u), list;
+  std::vector<uint32_t> fm((size_t)words, 0u), wm((size_t)words, 0u), om((size_t)words, 0u), list;
   const int outer = pl->D == 3 ? d.nz : d.ny;
   const long long slab = pl->D == 3 ? d.sz : d.sy;
   pl->layer_off.assign(outer + 1, 0);
@@ -255,13 +257,16 @@ int slf_plan_bind_map(SlfPlan *pl, uint64_t map) {
       const bool interior = x > 0 && x < d.nx - 1 && y > 0 && y < d.ny - 1 && (pl->D == 2 || (z > 0 && z < d.nz - 1));
       if (type == t_fluid && interior) fm[gi >> 5] |= 1u << (gi & 31);
       else if (type == t_wall && interior) wm[gi >> 5] |= 1u << (gi & 31);
-      else list.push_back((uint32_t)gi);
+      else { list.push_back((uint32_t)gi); om[gi >> 5] |= 1u << (gi & 31); }
     }
   }
   pl->layer_off[outer] = (long long)list.size();
   if (pl->d_fluid_mask) { cudaFree(pl->d_fluid_mask); pl->d_fluid_mask = nullptr; }
   if (pl->d_wall_mask) { cudaFree(pl->d_wall_mask); pl->d_wall_mask = nullptr; }
   if (pl->d_list) { cudaFree(pl->d_list); pl->d_list = nullptr; }
+  if (pl->d_other_mask) { cudaFree(pl->d_other_mask); pl->d_other_mask = nullptr; }
+  CUDA_OK(cudaMalloc((void **)&pl->d_other_mask, (size_t)words * 4));
+  CUDA_OK(cudaMemcpy(pl->d_other_mask, om.data(), (size_t)words * 4, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMalloc((void **)&pl->d_fluid_mask, (size_t)words * 4));
   CUDA_OK(cudaMalloc((void **)&pl->d_wall_mask, (size_t)words * 4));
   CUDA_OK(cudaMalloc((void **)&pl->d_list, (list.size() + 1) * 4));
@@ -512,7 +517,7 @@ int slf_run_steps(SlfPlan *pl, uint64_t map, uint64_t dist_a, uint64_t dist_b, u
     uint32_t it = iteration;
     int rc = 1;
     while (left > 0) {
-      const int chunk = left > 65536 ? 65536 : left;      // the barrier counter is 32 bits wide
+      const int chunk = left > (1 << 30) ? (1 << 30) : left;
       const int sl = save_last && chunk == left;
       switch (pl->hp.lattice) {
         case SLF_D2Q9: rc = slf_multistep_d2q9(pl, pl->hp.model, m, d, r, x, y, z, it, chunk, sl, s); break;

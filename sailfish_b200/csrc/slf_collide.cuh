@@ -85,33 +85,35 @@ static int dispatch_mode(SlfPlan *pl, int mode, bool save, const uint32_t *map, 
 template <class L, int MODEL>
 static int launch_multistep(SlfPlan *pl, const uint32_t *map, float *dist, float *rho, float *vx, float *vy,
                             float *vz, uint32_t it0, int nsteps, int save_last, cudaStream_t s) {
+  constexpr int B = MultiStepTuning<L, MODEL>::BLOCK;
   const DevParams &d = pl->dp;
-  if (pl->bound_map == 0 || pl->bound_map != (uint64_t)map || !d.relax || !d.prop) return 1;
-  const int outer = pl->D == 3 ? d.nz : d.ny;
-  const long long slab = pl->D == 3 ? d.sz : d.sy;
-  const long long n = slab * outer;
+  if (pl->bound_map == 0 || pl->bound_map != (uint64_t)map || !d.relax || !d.prop || !pl->d_other_mask) return 1;
+  const long long n = d.DS;
   static int per_sm = -1, sms = 0;
   if (per_sm < 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, collide_multistep<L, MODEL>, 256, 0) != cudaSuccess) per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, collide_multistep<L, MODEL>, B, 0) != cudaSuccess) per_sm = 0;
   }
   const long long resident = (long long)per_sm * sms;
-  if (resident <= 0) return 1;
-  long long nb = (n + 255) / 256;
-  if (nb > 4 * resident) return 1;                 // more than a few nodes per thread: kernel-per-step streams better
-  if (nb > resident) nb = resident;
-  unsigned int *bar = pl->d_push_done + 2;
-  CUDA_OK(cudaMemsetAsync(bar, 0, sizeof(unsigned int), s));
+  const long long nb = (n + B - 1) / B;
+  if (resident <= 0 || nb > resident || nb > SLF_MULTISTEP_MAX_BLOCKS) return 1;     // one node per thread, all co-resident
+  // everything a node touches lies within R nodes of it: the blocks within `reach` of its own
+  const long long R = d.sz * (pl->D == 3 ? 1 : 0) + d.sy + 1;
+  const int reach = (int)((R + B - 1) / B);
+  if (2 * reach > 32) return 1;
+  if (!pl->d_flags) CUDA_OK(cudaMalloc((void **)&pl->d_flags, SLF_MULTISTEP_MAX_BLOCKS * sizeof(unsigned int)));
+  CUDA_OK(cudaMemsetAsync(pl->d_flags, 0, (size_t)nb * sizeof(unsigned int), s));
   DevParams P = d;
   SlotTable<L> Te = make_aa_table<L>(d, dist, 0, false), To = make_aa_table<L>(d, dist, 0, true);
-  const uint32_t *fm = pl->d_fluid_mask, *list = pl->d_list;
-  unsigned nlist = (unsigned)pl->layer_off[outer], un = (unsigned)n;
-  long long gi0 = 0;
-  void *args[] = {&P, &Te, &To, &fm, &map, &list, &nlist, &dist, &rho, &vx, &vy, &vz, &gi0, &un, &it0, &nsteps,
-                  &save_last, &bar};
-  CUDA_OK(cudaLaunchCooperativeKernel((void *)collide_multistep<L, MODEL>, dim3((unsigned)nb), dim3(256), args, 0, s));
+  const uint32_t *fm = pl->d_fluid_mask, *om = pl->d_other_mask;
+  unsigned un = (unsigned)n;
+  unsigned int *flags = pl->d_flags;
+  int reach_arg = reach;
+  void *args[] = {&P, &Te, &To, &fm, &om, &map, &dist, &rho, &vx, &vy, &vz, &un, &it0, &nsteps, &save_last, &flags,
+                  &reach_arg};
+  CUDA_OK(cudaLaunchCooperativeKernel((void *)collide_multistep<L, MODEL>, dim3((unsigned)nb), dim3(B), args, 0, s));
   LAUNCH_OK("collide_multistep");
   return 0;
 }

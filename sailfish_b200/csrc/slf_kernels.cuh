@@ -425,47 +425,57 @@ collide_boundary(const DevParams P, const uint32_t *__restrict__ map, const uint
 // Many steps in ONE launch, for lattices that fit a single co-resident grid (ldc_2d 256^2: 74 k nodes,
 // 2.7 MB -- it lives in L2).  At that size a step is a few hundred nanoseconds of memory time and the
 // cost of a time step is the launch: two kernels per step, ~6 us even when replayed from a CUDA graph
-// (profiles/r01_bench_configs.txt).  Here a persistent cooperative grid keeps one node per thread and
-// separates the steps by a grid-wide barrier (one atomic per block + acquire polling in L2) instead of a
-// kernel boundary.  Population loads bypass L1 (ld.global.cg): other blocks rewrite those lines
-// every step and L1 is not coherent.  Boundary-list nodes are taken by the grid's LAST threads (the tail of
-// the index space is padding and ghost nodes), so they run beside the bulk nodes, not after them.
+// (profiles/r01_bench_configs.txt).  Here a persistent cooperative grid keeps ONE node per thread for the
+// whole run and the steps are separated by point-to-point synchronisation instead of kernel boundaries
+// (a grid-wide barrier -- one serialised atomic per block -- measured 3.7 us per step,
+// profiles/r02_bench_configs.txt): a block covers B consecutive nodes, so everything its nodes read or write
+// lies within R = sz + sy + 1 nodes of them, i.e. in the few blocks around it; after step s a block
+// publishes s + 1 (release store) and before step s + 1 it polls the counters of those blocks only (acquire
+// loads, one poller thread per neighbour).  In the AA pattern that is enough in both directions: neighbours
+// are never more than one step apart, and a node's Q addresses of step s + 1 are touched in step s only by
+// its neighbours.  Population loads bypass L1 (ld.global.cg): other blocks rewrite those lines every step and
+// L1 is not coherent.  Boundary nodes (the plan's node list, here as a third 1-bit mask) are handled by the
+// thread that covers them.
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-
-// `bar` counts arrivals cumulatively (zeroed by the host before the launch)
-__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1u);
-    while (ld_acquire_gpu_u32(bar) < target) { }
-    __threadfence();
-  }
-  __syncthreads();
+__device__ __forceinline__ void st_release_gpu_u32(unsigned int *p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
+template <class L, int MODEL> struct MultiStepTuning { static constexpr int BLOCK = 512; };
+template <int MODEL> struct MultiStepTuning<D2Q9, MODEL> { static constexpr int BLOCK = 1024; };
+
 template <class L, int MODEL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(MultiStepTuning<L, MODEL>::BLOCK)
 collide_multistep(const DevParams P, const SlotTable<L> Te, const SlotTable<L> To,
-                  const uint32_t *__restrict__ fluid_mask, const uint32_t *__restrict__ map,
-                  const uint32_t *__restrict__ list, unsigned nlist, float *dist,
+                  const uint32_t *__restrict__ fluid_mask, const uint32_t *__restrict__ other_mask,
+                  const uint32_t *__restrict__ map, float *dist,
                   float *__restrict__ orho, float *__restrict__ ovx, float *__restrict__ ovy,
-                  float *__restrict__ ovz, long long gi0, unsigned n, unsigned it0, int nsteps, int save_last,
-                  unsigned int *bar) {
-  const unsigned gsize = gridDim.x * 256u;
-  const unsigned gtid = blockIdx.x * 256u + threadIdx.x;
-  const unsigned rtid = gsize - 1u - gtid;
+                  float *__restrict__ ovz, unsigned n, unsigned it0, int nsteps, int save_last,
+                  unsigned int *flags, int reach) {
+  constexpr unsigned B = MultiStepTuning<L, MODEL>::BLOCK;
+  const unsigned t = blockIdx.x * B + threadIdx.x;
+  const long long gi = t;
+  bool fluid = false, other = false;
+  if (t < n) {
+    fluid = (fluid_mask[gi >> 5] >> (gi & 31)) & 1u;
+    other = (other_mask[gi >> 5] >> (gi & 31)) & 1u;
+  }
+  // the blocks this one exchanges data with: blockIdx.x - reach .. + reach
+  const int dep = (int)blockIdx.x - reach + (int)threadIdx.x + ((int)threadIdx.x >= reach ? 1 : 0);
+  const bool poller = threadIdx.x < 2u * (unsigned)reach && dep >= 0 && dep < (int)gridDim.x;
   for (int s = 0; s < nsteps; s++) {
+    if (s > 0) {
+      if (poller) while (ld_acquire_gpu_u32(flags + dep) < (unsigned)s) { }
+      __syncthreads();
+    }
     const bool odd = ((it0 + (unsigned)s) & 1u) != 0;
     const bool save = save_last && s == nsteps - 1;
-    for (unsigned t = gtid; t < n; t += gsize) {
-      const long long gi = gi0 + t;
-      if (!((fluid_mask[gi >> 5] >> (gi & 31)) & 1u)) continue;
+    if (fluid) {
       if (save) {
         if (odd) bulk_aa_node<L, MODEL, true, 2>(P, To, orho, ovx, ovy, ovz, gi, t);
         else bulk_aa_node<L, MODEL, true, 2>(P, Te, orho, ovx, ovy, ovz, gi, t);
@@ -473,9 +483,7 @@ collide_multistep(const DevParams P, const SlotTable<L> Te, const SlotTable<L> T
         if (odd) bulk_aa_node<L, MODEL, false, 2>(P, To, orho, ovx, ovy, ovz, gi, t);
         else bulk_aa_node<L, MODEL, false, 2>(P, Te, orho, ovx, ovy, ovz, gi, t);
       }
-    }
-    for (unsigned k = rtid; k < nlist; k += gsize) {
-      const long long gi = list[k];
+    } else if (other) {
       if (save) {
         if (odd) boundary_node<L, MODEL, MODE_AA_ODD, true, 2>(P, map, dist, dist, orho, ovx, ovy, ovz, gi, false);
         else boundary_node<L, MODEL, MODE_AA_EVEN, true, 2>(P, map, dist, dist, orho, ovx, ovy, ovz, gi, false);
@@ -484,7 +492,13 @@ collide_multistep(const DevParams P, const SlotTable<L> Te, const SlotTable<L> T
         else boundary_node<L, MODEL, MODE_AA_EVEN, false, 2>(P, map, dist, dist, orho, ovx, ovy, ovz, gi, false);
       }
     }
-    if (s + 1 < nsteps) grid_barrier(bar, gridDim.x * (unsigned)(s + 1));
+    if (s + 1 < nsteps) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        st_release_gpu_u32(flags + blockIdx.x, (unsigned)(s + 1));
+      }
+    }
   }
 }
 

@@ -29,6 +29,8 @@ void slf_count_launch();
 struct StepGraphKey { uint64_t map, a, b, rho; int parity; };
 struct StepGraph { StepGraphKey key; cudaGraphExec_t exec; uint64_t kernels; };
 
+#define SLF_MULTISTEP_MAX_BLOCKS 4096
+
 struct SlfPlan {
   SlfParams hp;
   DevParams dp;
@@ -37,6 +39,8 @@ struct SlfPlan {
   // derived from a bound node map (slf_plan_bind_map)
   uint64_t bound_map = 0;
   uint32_t *d_fluid_mask = nullptr, *d_wall_mask = nullptr, *d_list = nullptr;
+  uint32_t *d_other_mask = nullptr;    // 1 bit per node: member of d_list (multi-step kernel)
+  unsigned int *d_flags = nullptr;     // per-block step counters of the multi-step kernel
   std::vector<long long> layer_off;    // list offsets per outermost-axis layer (size n + 1)
   int link_lo = 0, link_hi = 0;        // neighbours across the low / high face of the split axis
   std::vector<StepGraph> graphs;

@@ -4,6 +4,8 @@
 #include <cmath>
 #include <string>
 
+#include <cstdlib>
+
 #include "slf_plan.cuh"
 #include "slf_shan_chen.cuh"
 
@@ -141,14 +143,30 @@ int slf_sc_collide_and_propagate_fused(SlfPlan *pl, uint64_t map, uint64_t dist1
   cudaStream_t s = (cudaStream_t)stream;
   // walls: bounce-back copies in AB / with propagation off, nothing to do in the AA pattern
   const int bounce_walls = (mode == MODE_AB || !pl->dp.prop) ? 1 : 0;
+  const DevParams &d = pl->dp;
+  const int outer_n = pl->D == 3 ? d.nz : d.ny;
+  const int zb = z0, ze = z1 < 0 ? outer_n : z1;
+  // tile-shaped blocks for thick 3-D ranges (single boundary layers keep the linear map)
+  const bool tiled = pl->D == 3 && ze - zb >= 2 && !getenv("SLF_SC_LINEAR");
+  const dim3 tgrid((d.ax + 31) / 32, (d.ay + 1) / 2, (ze - zb + 1) / 2);
 #define SC_FUSED(SAVE)                                                                                            \
-  SLF_LATTICE_SWITCH(pl, (sc_collide_fused<L, SAVE><<<nb, bs, 0, s>>>(                                             \
-                             pl->dp, S,                                                                            \
-                             make_sc_tables<L>(pl->dp, mode, (const float *)dist1_in, (float *)dist1_out,          \
-                                               (const float *)dist2_in, (float *)dist2_out, (const float *)rho,    \
-                                               (const float *)phi, gi0),                                           \
-                             (const uint32_t *)map, (float *)vx, (float *)vy, (float *)vz, gi0,                    \
-                             (unsigned)(gi1 - gi0), bounce_walls)))
+  if (tiled) {                                                                                                    \
+    SLF_LATTICE_SWITCH(pl, (sc_collide_fused_tile<L, SAVE><<<tgrid, 128, 0, s>>>(                                  \
+                               pl->dp, S,                                                                          \
+                               make_sc_tables<L>(pl->dp, mode, (const float *)dist1_in, (float *)dist1_out,        \
+                                                 (const float *)dist2_in, (float *)dist2_out, (const float *)rho,  \
+                                                 (const float *)phi, gi0),                                         \
+                               (const uint32_t *)map, (float *)vx, (float *)vy, (float *)vz, gi0, zb, ze,          \
+                               bounce_walls)));                                                                    \
+  } else {                                                                                                        \
+    SLF_LATTICE_SWITCH(pl, (sc_collide_fused<L, SAVE><<<nb, bs, 0, s>>>(                                           \
+                               pl->dp, S,                                                                          \
+                               make_sc_tables<L>(pl->dp, mode, (const float *)dist1_in, (float *)dist1_out,        \
+                                                 (const float *)dist2_in, (float *)dist2_out, (const float *)rho,  \
+                                                 (const float *)phi, gi0),                                         \
+                               (const uint32_t *)map, (float *)vx, (float *)vy, (float *)vz, gi0,                  \
+                               (unsigned)(gi1 - gi0), bounce_walls)));                                             \
+  }
   if (save) { SC_FUSED(true); } else { SC_FUSED(false); }
 #undef SC_FUSED
   LAUNCH_OK("sc_collide_fused");

@@ -198,13 +198,10 @@ __device__ __forceinline__ void sc_psi_gradient_tab(const float *const (&g)[L::Q
 }
 
 template <class L, bool SAVE>
-__global__ void __launch_bounds__(128, SLF_MINB_SC_FUSED)
-sc_collide_fused(const DevParams P, const ScParams S, const ScTables<L> T, const uint32_t *__restrict__ map,
-                 float *__restrict__ ovx, float *__restrict__ ovy, float *__restrict__ ovz, long long gi0,
-                 unsigned n, int bounce_walls) {
-  const unsigned t = blockIdx.x * 128u + threadIdx.x;
-  if (t >= n) return;
-  const long long gi = gi0 + t;
+__device__ __forceinline__ void
+sc_fused_node(const DevParams &P, const ScParams &S, const ScTables<L> &T, const uint32_t *__restrict__ map,
+              float *__restrict__ ovx, float *__restrict__ ovy, float *__restrict__ ovz, const long long gi,
+              const unsigned t, const int bounce_walls) {
   const uint32_t type = map[gi] & P.tmask;
   const bool fluid = type == P.tid[SLF_NT_FLUID];
   const bool wall = type == P.tid[SLF_NT_FULLBB_WALL];
@@ -260,6 +257,37 @@ sc_collide_fused(const DevParams P, const ScParams S, const ScTables<L> T, const
 #pragma unroll
     for (int i = 0; i < L::Q; i++) T.st2[i][t] = f1[i];
   }
+}
+
+template <class L, bool SAVE>
+__global__ void __launch_bounds__(128, SLF_MINB_SC_FUSED)
+sc_collide_fused(const DevParams P, const ScParams S, const ScTables<L> T, const uint32_t *__restrict__ map,
+                 float *__restrict__ ovx, float *__restrict__ ovy, float *__restrict__ ovz, long long gi0,
+                 unsigned n, int bounce_walls) {
+  const unsigned t = blockIdx.x * 128u + threadIdx.x;
+  if (t >= n) return;
+  sc_fused_node<L, SAVE>(P, S, T, map, ovx, ovy, ovz, gi0 + t, t, bounce_walls);
+}
+
+// The same node body on tile-shaped blocks: 32 x 2 x 2 nodes (3-D) keep every population access a full line and
+// cut the rows the two psi stencils touch per block from 9 + 9 per node row to 16 + 16 per four node rows.
+// Measured on B200 (tools/exp_sc.cu, profiles/r02_exp_sc.txt, 256^3): 1.093 ms per launch against 1.207 ms for
+// 128 x 1 x 1 blocks at 5 blocks/SM and 1.146 ms at 6; staging the stencil in shared memory on top of that LOSES
+// (1.216 ms: the gathers already hit L1, what limits the kernel is the latency of its 38 population loads at
+// 35 % occupancy) and so do larger tiles (fewer blocks per SM).
+#ifndef SLF_MINB_SC_TILE
+#define SLF_MINB_SC_TILE 6
+#endif
+template <class L, bool SAVE>
+__global__ void __launch_bounds__(128, SLF_MINB_SC_TILE)
+sc_collide_fused_tile(const DevParams P, const ScParams S, const ScTables<L> T, const uint32_t *__restrict__ map,
+                      float *__restrict__ ovx, float *__restrict__ ovy, float *__restrict__ ovz, long long gi0,
+                      int z0, int z1, int bounce_walls) {
+  const int lx = threadIdx.x & 31, ly = (threadIdx.x >> 5) & 1, lz = threadIdx.x >> 6;
+  const int x = blockIdx.x * 32 + lx, y = blockIdx.y * 2 + ly, z = z0 + blockIdx.z * 2 + lz;
+  if (x >= P.ax || y >= P.ay || z >= z1) return;
+  const long long gi = (long long)x + P.sy * y + P.sz * z;
+  sc_fused_node<L, SAVE>(P, S, T, map, ovx, ovy, ovz, gi, (unsigned)(gi - gi0), bounce_walls);
 }
 
 // mode: MODE_AB / MODE_AA_EVEN / MODE_AA_ODD as seen by load_node / sc_store

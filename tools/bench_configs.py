@@ -52,9 +52,8 @@ def main():
         out = {'config': name, 'fluid_nodes': nodes, 'steps': steps}
         for mode in ('c_graph', 'python'):
             if not hasattr(dev, 'run_python_loop'):
-                if mode == 'c_graph':
-                    continue
-                fn = lambda n, save_last=False: dev.run(n)
+                # binary mixture: graph replay is recorded from the runner's own step()
+                fn = (lambda n, save_last=False: r.run_steps(n)) if mode == 'c_graph' else (lambda n, save_last=False: dev.run(n))
             else:
                 fn = dev.run if mode == 'c_graph' else dev.run_python_loop
             fn(20, save_last=False)
