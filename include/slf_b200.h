@@ -101,7 +101,8 @@ typedef struct SlfParams {
   int32_t  relaxation_enabled;  /* config.relaxation_enabled (regtest/subdomains)     */
   int32_t  propagation_enabled;
   int32_t  force_enabled;       /* LBForcedSim.add_body_force, Guo scheme only          */
-  int32_t  reserved0;
+  int32_t  unused_tag_bits;     /* link-tag bits set in every tagged node: no missing-link code exists for them
+                                 * (geo_encoder.py:283-289, boundary.mako:393-401)                           */
   double   visc;                /* --visc; tau = (6 visc + 1) / 2  (sym.py:847)          */
   double   accel[3];            /* body acceleration (sym_force.py:72-119, accel=True)  */
   int32_t  num_node_params;     /* len(ctx['node_params'])                              */

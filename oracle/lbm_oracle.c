@@ -495,6 +495,7 @@ int orc_collide_and_propagate(const SlfParams *P, const uint32_t *map, const REA
           int name;
           if (P->use_link_tags) {
             if (orient & (1 << (i - 1))) continue;   /* link i points to a fluid node */
+            if (P->unused_tag_bits & (1 << (i - 1))) continue;   /* no code is generated for this bit, boundary.mako:396 */
             name = i; missing = L->opp[i];
           } else {
             if (orient == 0) break;

@@ -178,6 +178,7 @@ int slf_plan_create(const SlfParams *p, SlfPlan **out) {
   d.forced = p->force_enabled ? 1 : 0;
   for (int k = 0; k < 3; k++) d.a[k] = p->force_enabled ? (float)p->accel[k] : 0.f;
   d.relax = p->relaxation_enabled; d.prop = p->propagation_enabled; d.use_tags = p->use_link_tags;
+  d.unused_tags = (unsigned int)p->unused_tag_bits;
   const int np = p->num_node_params > 0 ? p->num_node_params : 0;
   std::vector<float> h(np + 4, 0.f);
   for (int k = 0; k < np; k++) h[k] = (float)p->node_params[k];

@@ -43,6 +43,7 @@ struct DevParams {
   float guo_pref;            // 3 (1 - 1/(2 tau))
   float a[3];                // body acceleration
   int forced, relax, prop, use_tags;
+  unsigned int unused_tags;  // link-tag bits without missing-link code (geo_encoder.py:283-289)
   const float *node_params;
 };
 

@@ -104,11 +104,21 @@ __global__ void sem_wait_kernel(const unsigned int *ready_a, const unsigned int 
 // population set separately (subdomain_connection.py:348-407, sparse index lists for x faces, edges and
 // corners).  Here the exchange is dimension ordered -- all x faces, then all y faces, then z -- and edge / corner
 // data reach their diagonal destination in two or three hops, riding in the ghost ring of the face messages.
-// Per face and crossing population i the copied window is chosen such that (a) forwarded data are included and
-// (b) no two messages ever write the same location (so no ordering between different senders is needed):
-//   along an EARLIER axis (already exchanged in this step): the whole extent, ghost ring included;
-//   along a LATER axis b: after in-place steps (with_swap) the real nodes 1 .. n_b - 2; after streaming steps the
-//   real nodes shifted by e_i[b] (the entries of the ghost layer that real nodes of this subdomain streamed into).
+// Per face and crossing population i the copied window is chosen such that (a) everything a real node of the
+// receiver will read and every entry that must be forwarded further is included, and (b) no two messages -- of this
+// step or of neighbouring steps, from different senders, which nothing orders against each other -- ever write the
+// same location:
+//   after streaming steps (data sit where they were streamed to; the receiver's node reads its own slots):
+//     along an EARLIER axis (already exchanged in this step): the real nodes 1 .. n - 2 (entries forwarded by the
+//       earlier exchange sit in the first / last real column);
+//     along a LATER axis b: the real nodes shifted by e_i[b] (the entries real nodes of this subdomain streamed
+//       into, ghost-row entries -- to be forwarded by the later exchange -- included);
+//   after in-place steps (with_swap: data sit un-streamed at their node; receiver node p reads q = p - e_i):
+//     along an EARLIER axis b: q_b in 1 - e_i[b] .. n - 2 - e_i[b] (what some real node of the receiver reads; the
+//       ghost-column entries delivered by the earlier exchange included);
+//     along a LATER axis: the real nodes 1 .. n - 2 (entries to be forwarded by the later exchange sit in real rows).
+// With the looser "whole extent along earlier axes" a late in-place message of one neighbour could overwrite an early
+// streamed message of another in a ghost row (found on hardware with one rank per block, tools/gpu_round2_f.sh).
 struct FaceArgs {
   const float *src[9];
   float *dst[9];
@@ -233,9 +243,9 @@ int slf_halo_push_face(SlfPlan *pl, uint64_t dist, int face, uint64_t peer_dist,
     int lo[2] = {0, 0}, cnt[2] = {1, 1};
     for (int b = 0; b < D - 1; b++) {
       const int ax = oth[b];
-      if (ax < axis) { lo[b] = 0; cnt[b] = lat[ax]; }                          // earlier axis: ghost ring included
-      else if (with_swap) { lo[b] = 1; cnt[b] = lat[ax] - 2; }                 // later axis, un-streamed data: real nodes
-      else { lo[b] = 1 + e[ax]; cnt[b] = lat[ax] - 2; }                        // later axis, streamed data: shifted by e_i
+      cnt[b] = lat[ax] - 2;
+      if (ax < axis) lo[b] = with_swap ? 1 - e[ax] : 1;                        // earlier axis
+      else lo[b] = with_swap ? 1 : 1 + e[ax];                                  // later axis
     }
     a.src[a.n] = (const float *)dist + d.DS * slot + str[axis] * src_layer;
     a.dst[a.n] = (float *)peer_dist + peer_DS * slot + pstr[axis] * dst_layer;

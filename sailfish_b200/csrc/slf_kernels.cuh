@@ -368,7 +368,7 @@ boundary_node(const DevParams &P, const uint32_t *__restrict__ map, const float 
 #pragma unroll
     for (int i = 1; i < L::Q; i++) {
       bool hit; int missing, name;
-      if (P.use_tags) { hit = (orient & (1 << (i - 1))) == 0; name = i; missing = L::opp(i); }
+      if (P.use_tags) { hit = (orient & (1 << (i - 1))) == 0 && (P.unused_tags & (1u << (i - 1))) == 0; name = i; missing = L::opp(i); }
       else { hit = orient != 0 && edotn<L>(i, n0, n1, n2) > 0; missing = i; name = L::opp(i); }
       if (hit) {
         // `name`/`missing` are compile-time per branch: resolve through a tiny switch

@@ -47,7 +47,7 @@ class SlfParams(ctypes.Structure):
         ('relaxation_enabled', ctypes.c_int32),
         ('propagation_enabled', ctypes.c_int32),
         ('force_enabled', ctypes.c_int32),
-        ('reserved0', ctypes.c_int32),
+        ('unused_tag_bits', ctypes.c_int32),
         ('visc', ctypes.c_double),
         ('accel', ctypes.c_double * 3),
         ('num_node_params', ctypes.c_int32),
@@ -82,7 +82,7 @@ class UnsupportedConfiguration(ValueError):
 
 def make_params(lattice, model, access_pattern, lat_size, arr_size, periodic,
                 bits, type_ids, node_params, visc, accel=None, use_link_tags=True,
-                relaxation_enabled=True, propagation_enabled=True, shan_chen=None):
+                relaxation_enabled=True, propagation_enabled=True, shan_chen=None, unused_tag_bits=0):
     """shan_chen: None (single fluid) or dict(tau_phi=, G11=, G12=, G21=, G22=, potential=)."""
     """lat_size/arr_size are (nx, ny, nz) with nz = 1 in 2-D; type_ids maps node
     class name -> remapped id."""
@@ -107,6 +107,7 @@ def make_params(lattice, model, access_pattern, lat_size, arr_size, periodic,
         raise UnsupportedConfiguration(
             'node types outside the B200 hot path: %s' % ', '.join(sorted(unknown)))
     p.use_link_tags = int(bool(use_link_tags))
+    p.unused_tag_bits = int(unused_tag_bits) & 0x7fffffff
     p.relaxation_enabled = int(bool(relaxation_enabled))
     p.propagation_enabled = int(bool(propagation_enabled))
     p.visc = float(visc)
@@ -195,4 +196,5 @@ def from_context(ctx):
         type_ids, [float(x) for x in ctx['node_params']], ctx['visc'], accel,
         use_link_tags=ctx.get('use_link_tags', True),
         relaxation_enabled=ctx.get('relaxation_enabled', True),
-        propagation_enabled=ctx.get('propagation_enabled', True), shan_chen=shan_chen)
+        propagation_enabled=ctx.get('propagation_enabled', True), shan_chen=shan_chen,
+        unused_tag_bits=ctx.get('unused_tag_bits', 0))

@@ -334,6 +334,12 @@ class Subdomain(object):
         self._encoded = ((misc << np.uint32(bits_type)) | choice[tm]).astype(np.uint32)
         self._type_map_encoded = True
         self.have_link_tags = have_link_tags
+        # geo_encoder.py:283-289: tag bits that are set in every tagged node
+        self.unused_tag_bits = 0
+        if have_link_tags:
+            tags = self._orientation_base[self._orientation_base > 0]
+            if tags.size:
+                self.unused_tag_bits = int(np.bitwise_and.reduce(tags.astype(np.uint32)))
 
     def encoded_map(self):
         return self._encoded

@@ -205,7 +205,8 @@ class SubdomainRunner(object):
             sd.node_params, cfg.visc, self._sim.body_acceleration(),
             use_link_tags=getattr(cfg, 'use_link_tags', True),
             relaxation_enabled=getattr(cfg, 'relaxation_enabled', True),
-            propagation_enabled=getattr(cfg, 'propagation_enabled', True))
+            propagation_enabled=getattr(cfg, 'propagation_enabled', True),
+            unused_tag_bits=getattr(sd, 'unused_tag_bits', 0))
 
     def _init_compute(self):
         from sailfish_b200.runtime import DeviceLattice
@@ -279,7 +280,7 @@ class SubdomainRunner(object):
         # (or rank); it is only awaited at the start of the next step.  Quiesce every subdomain and rank
         # first, otherwise the file may miss one step of boundary data (all subdomains checkpoint at the
         # same iterations, so the rendezvous is collective-safe).
-        if self._links and self._pre_checkpoint is not None:
+        if self._xlinks and self._pre_checkpoint is not None:
             self._pre_checkpoint()
         if getattr(cfg, 'single_checkpoint', False):
             fname = checkpoint_filename(cfg.checkpoint_file, 1, self._spec.id, 0)
@@ -565,7 +566,7 @@ class SubdomainRunner(object):
         has no neighbours, recorded from step() when its neighbours live in other ranks.  (Several
         subdomains driven by one process order their pushes with events of the other runners and are
         stepped one by one: LBSimulationController.run_steps.)"""
-        if not self._links:
+        if not self._xlinks:
             self._dev.run(n, save_last=save_last)
             self._sim.iteration += n
             return
@@ -668,6 +669,12 @@ class NNSubdomainRunner(SubdomainRunner):
     Shan-Chen, BASELINE config 5): mirror of sailfish/subdomain_runner.py:1840-2197.  Per step:
     ShanChenPrepareMacroFields -> macro PBC -> field ghost layers to the neighbours ->
     ShanChenCollideAndPropagate0/1 -> distribution PBC -> population planes to the neighbours."""
+
+    def add_link(self, link):
+        if link.axis != self.dim - 1:
+            raise P.UnsupportedConfiguration('binary Shan-Chen runner: subdomains are connected along the outermost axis (%s)'
+                                             % 'xyz'[self.dim - 1])
+        SubdomainRunner.add_link(self, link)
 
     def _init_fields(self):
         sim = self._sim

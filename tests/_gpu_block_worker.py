@@ -24,6 +24,7 @@ ARGS = ['--lat_nx=40', '--lat_ny=36', '--lat_nz=34', '--visc=0.04']
 
 def main():
     ap = sys.argv[1]
+    blocks = sys.argv[2] if len(sys.argv) > 2 else '2,2,2'
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     ndev = torch.cuda.device_count()
     os.environ['LOCAL_RANK'] = str(local_rank % ndev)
@@ -33,7 +34,7 @@ def main():
     args = ARGS + ['--access_pattern=' + ap, '--quiet']
     steps = 21
     ctrl = LBSimulationController(ldc_3d.LDCSim, BlockSubdomainsGeometry3D)
-    ctrl.setup(args + ['--blocks=2,2,2'])
+    ctrl.setup(args + ['--blocks=' + blocks])
     for k in range(steps):
         ctrl.step_all(k == steps - 1)
     ctrl.sync()
@@ -51,10 +52,10 @@ def main():
         for which, label in ((0, 'stepped'), (1, 're-initialised + graph replay')):
             got = block_util.merge([g[which] for g in gathered], GSIZE)
             same = bool(np.array_equal(got, ref, equal_nan=True))
-            print('RESULT', ap, 'ranks', ws, 'gpus', ndev, label, 'bit-identical' if same else
+            print('RESULT', ap, 'blocks', blocks, 'ranks', ws, 'gpus', ndev, label, 'bit-identical' if same else
                   'MISMATCH max %g' % np.nanmax(np.abs(got - ref)))
             ok = ok and same
-        print('RESULT', ap, 'all bit-identical' if ok else 'MISMATCH')
+        print('RESULT', ap, blocks, 'all bit-identical' if ok else 'MISMATCH')
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

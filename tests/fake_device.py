@@ -226,12 +226,12 @@ class FakeLib(object):
             for ax in range(D):
                 if ax == axis:
                     idx_s[ax], idx_d[ax] = src_layer, dst_layer
-                elif ax < axis:
-                    idx_s[ax] = idx_d[ax] = slice(0, lat[ax])
-                elif swap:
-                    idx_s[ax] = idx_d[ax] = slice(1, lat[ax] - 1)
                 else:
-                    idx_s[ax] = idx_d[ax] = slice(1 + e[ax], lat[ax] - 1 + e[ax])
+                    if ax < axis:
+                        lo = 1 - e[ax] if swap else 1
+                    else:
+                        lo = 1 if swap else 1 + e[ax]
+                    idx_s[ax] = idx_d[ax] = slice(lo, lo + lat[ax] - 2)
             peer[(slot,) + tuple(idx_d[::-1])] = mine[(slot,) + tuple(idx_s[::-1])]
         self.launches += 1
 
