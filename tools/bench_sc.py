@@ -35,12 +35,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         ctrl.sync()
-    for _ in range(10):
-        r.step(False)
+    r.run_steps(10)                 # records the step-pair graph
     barrier()
     e0 = r.backend.make_event(r._calc_stream, timing=True)
-    for _ in range(a.steps):
-        r.step(False)
+    r.run_steps(a.steps)            # CUDA-graph replay of step pairs recorded from NNSubdomainRunner.step
     e1 = r.backend.make_event(r._calc_stream, timing=True)
     barrier()
     ms = e1.time_since(e0)
