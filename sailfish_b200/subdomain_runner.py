@@ -741,32 +741,64 @@ class NNSubdomainRunner(SubdomainRunner):
         self.step_macro(sync_req)
         self.step_collide(sync_req)
 
+    def _ranges(self):
+        """(interior, [slabs]) as layer ranges along the split axis: the slabs are the real layers next to a linked
+        face -- the only nodes whose inputs arrive from a neighbour."""
+        n = self._outer_n()
+        links = self._links
+        lo, hi = (2 if 0 in links else 0), (n - 2 if 1 in links else n)
+        slabs = []
+        if 0 in links:
+            slabs.append((1, 2))
+        if 1 in links and n - 2 >= (2 if 0 in links else 1):
+            slabs.append((n - 2, n - 1))
+        else:
+            hi = n if 1 not in links else max(hi, lo)
+        return (lo, max(lo, hi)), slabs
+
     def step_macro(self, sync_req):
+        """Densities (and velocity on output steps) of this step, then the field ghost layers to the neighbours.
+        The interior goes FIRST: it needs nothing from the neighbours, so their population planes of the previous
+        step -- pushed at the very end of it -- travel while it runs; only the slabs wait for them."""
         dev = self._dev
         it = dev.iteration
         cs = self._calc_stream
         links = self._links
-        if links:
-            self._wait_incoming(0, it - 1, cs)
-        dev.macro(stream=cs, with_v=bool(sync_req))
+        if not links:
+            dev.macro(stream=cs, with_v=bool(sync_req))
+            dev.macro_pbc(stream=cs)
+            return
+        (lo, hi), slabs = self._ranges()
+        if hi > lo:
+            dev.macro(z_begin=lo, z_end=hi, stream=cs, with_v=bool(sync_req))
+        self._wait_incoming(0, it - 1, cs)
+        for z0, z1 in slabs:
+            dev.macro(z_begin=z0, z_end=z1, stream=cs, with_v=bool(sync_req))
         dev.macro_pbc(stream=cs)
-        if links:
-            for side, link in links.items():
-                for name, buf in (('rho', dev.d_rho), ('phi', dev.d_phi)):
-                    self._lib.call('slf_halo_push_field', dev.plan, int(buf), link.face, link.peer_bufs[name],
-                                   link.peer_lat_n, cs.handle)
-                if link.peer_runner is None:
-                    self._lib.call('slf_sem_signal', link.peer_ready(1), cs.handle)
-            self._push_events[1][it & 1].record(cs)
+        for side, link in links.items():
+            for name, buf in (('rho', dev.d_rho), ('phi', dev.d_phi)):
+                self._lib.call('slf_halo_push_field', dev.plan, int(buf), link.face, link.peer_bufs[name],
+                               link.peer_lat_n, cs.handle)
+            if link.peer_runner is None:
+                self._lib.call('slf_sem_signal', link.peer_ready(1), cs.handle)
+        self._push_events[1][it & 1].record(cs)
 
     def step_collide(self, sync_req):
+        """Relaxation + streaming of both components.  Again the interior first (its psi stencil reaches the slabs'
+        densities, which are local, but not the neighbours' ghost layers), then the slabs once those have landed."""
         dev = self._dev
         it = dev.iteration
         cs = self._calc_stream
         links = self._links
         if links:
+            (lo, hi), slabs = self._ranges()
+            if hi > lo:
+                dev.collide(z_begin=lo, z_end=hi, stream=cs)
             self._wait_incoming(1, it, cs)
-        dev.collide(stream=cs)
+            for z0, z1 in slabs:
+                dev.collide(z_begin=z0, z_end=z1, stream=cs)
+        else:
+            dev.collide(stream=cs)
         dev.dist_pbc(stream=cs)
         if links:
             swap = int(dev.aa and (it & 1) == 0)
