@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SLF_ABI_VERSION 4
+#define SLF_ABI_VERSION 5
 
 /* error codes (negative; positive values are cudaError_t) */
 #define SLF_EINVAL      (-1)   /* bad argument / unsupported configuration          */
@@ -68,6 +68,8 @@ enum {
   SLF_NT_REGULARIZED_VELOCITY,  /* :269 NTRegularizedVelocity             */
   SLF_NT_REGULARIZED_DENSITY,   /* :211 NTRegularizedDensity              */
   SLF_NT_DO_NOTHING,            /* :296 NTDoNothing                       */
+  SLF_NT_ZOUHE_VELOCITY,        /* :256 NTZouHeVelocity                   */
+  SLF_NT_ZOUHE_DENSITY,         /* :229 NTZouHeDensity                    */
   SLF_NT_COUNT
 };
 #define SLF_NT_ABSENT 0xfffffffeu   /* geo_encoder.py:44-50 */

@@ -311,6 +311,41 @@ static inline void bgk_relax(const Ctx *C, REAL rho, REAL *f, REAL *v) {
   }
 }
 
+/* zouhe_bb, boundary.mako:347-381 (orientation 1..2D): bounce-back of the non-equilibrium parts of the unknown
+ * populations (sym.py:750-766), then the momentum excess rho v - sum e f along the directions tangential to the wall
+ * is spread evenly over the unknown populations that have a component along them (zouhe_fixup, sym.py:770-815). */
+static inline void zouhe_bb(const Lat *L, int orient, REAL rho, const REAL *v, REAL *f) {
+  const int Q = L->Q, D = L->D;
+  const int *n = L->e[L->dir2vec[orient]];
+  REAL feq[MAXQ];
+  feq_all(L, rho, v, feq);
+  int unknown[MAXQ];
+  for (int i = 0; i < Q; i++) {
+    int sp = 0; for (int d = 0; d < D; d++) sp += L->e[i][d] * n[d];
+    unknown[i] = sp > 0;
+  }
+  for (int i = 0; i < Q; i++)
+    if (unknown[i]) f[i] = f[L->opp[i]] - feq[L->opp[i]] + feq[i];
+  REAL nv[3] = {0, 0, 0};
+  for (int d = 0; d < D; d++) {
+    REAL s = 0; for (int i = 0; i < Q; i++) s += (REAL)L->e[i][d] * f[i];
+    nv[d] = rho * v[d] - s;
+  }
+  const int normal_slot = L->dir2vec[orient];
+  for (int d = 0; d < D; d++) {
+    if (n[d] != 0) { nv[d] = 0; continue; }
+    int cnt = 0;
+    for (int i = 0; i < Q; i++) if (unknown[i] && i != normal_slot && L->e[i][d] != 0) cnt++;
+    nv[d] = cnt ? nv[d] / (REAL)cnt : (REAL)0;
+  }
+  for (int i = 0; i < Q; i++) {
+    if (!unknown[i] || i == normal_slot) continue;
+    REAL val = 0;
+    for (int d = 0; d < D; d++) if (L->e[i][d] != 0 && n[d] == 0) val += nv[d] * (REAL)L->e[i][d];
+    f[i] = f[i] + val;
+  }
+}
+
 static inline int in_bounds_target(const Ctx *C, const int *e, int x, int y, int z) {
   /* prop_bnd, propagation.mako:36-41: positive component needs coord < lim-1, negative coord > 0 */
   const int c[3] = {x, y, z}, lim[3] = {C->nx, C->ny, C->nz};
@@ -420,8 +455,10 @@ int orc_collide_and_propagate(const SlfParams *P, const uint32_t *map, const REA
       /* getMacro */
       const int standard = (cls == SLF_NT_FLUID || cls == SLF_NT_FULLBB_WALL || cls == SLF_NT_HALFBB_WALL ||
                             cls == SLF_NT_DO_NOTHING);
-      const int vel_bc = (cls == SLF_NT_EQUILIBRIUM_VELOCITY || cls == SLF_NT_REGULARIZED_VELOCITY);
-      const int den_bc = (cls == SLF_NT_EQUILIBRIUM_DENSITY || cls == SLF_NT_REGULARIZED_DENSITY);
+      const int vel_bc = (cls == SLF_NT_EQUILIBRIUM_VELOCITY || cls == SLF_NT_REGULARIZED_VELOCITY ||
+                          cls == SLF_NT_ZOUHE_VELOCITY);
+      const int den_bc = (cls == SLF_NT_EQUILIBRIUM_DENSITY || cls == SLF_NT_REGULARIZED_DENSITY ||
+                          cls == SLF_NT_ZOUHE_DENSITY);
       if (standard || orient == 0) {
         rho = 0; for (int i = 0; i < Q; i++) rho += f[i];
         for (int d = 0; d < D; d++) { REAL s = 0; for (int i = 0; i < Q; i++) s += (REAL)L->e[i][d] * f[i]; v[d] = s / rho; }
@@ -440,11 +477,18 @@ int orc_collide_and_propagate(const SlfParams *P, const uint32_t *map, const REA
         const REAL par_rho = (REAL)P->node_params[pidx];
         const int *n = L->e[L->dir2vec[orient]];
         for (int d = 0; d < D; d++) v[d] = (REAL)(-n[d]) * (rho - par_rho) / par_rho;   /* sym.py:666-680 */
+        if (cls == SLF_NT_ZOUHE_DENSITY) {                              /* boundary.mako:487-492 */
+          zouhe_bb(L, orient, par_rho, v, f);
+          REAL r = 0; for (int i = 0; i < Q; i++) r += f[i];
+          for (int d = 0; d < D; d++) { REAL q = 0; for (int i = 0; i < Q; i++) q += (REAL)L->e[i][d] * f[i]; v[d] = q / r; }
+        }
         rho = par_rho;
       }
       /* precollisionBoundaryConditions */
       if (cls == SLF_NT_FULLBB_WALL) {
         bounce_back(L, f);
+      } else if (cls == SLF_NT_ZOUHE_VELOCITY) {                        /* boundary.mako:812-816 */
+        if (orient == 0) bounce_back(L, f); else zouhe_bb(L, orient, rho, v, f);
       } else if (cls == SLF_NT_EQUILIBRIUM_VELOCITY || cls == SLF_NT_EQUILIBRIUM_DENSITY) {
         feq_all(L, rho, v, f);
       } else if (cls == SLF_NT_REGULARIZED_VELOCITY || cls == SLF_NT_REGULARIZED_DENSITY) {
@@ -945,7 +989,8 @@ static inline REAL sc_ppot(int pot, REAL x) {       /* sym.py:896-908 */
 static inline int is_wet(int cls) {
   return cls == SLF_NT_FLUID || cls == SLF_NT_HALFBB_WALL || cls == SLF_NT_EQUILIBRIUM_VELOCITY ||
          cls == SLF_NT_EQUILIBRIUM_DENSITY || cls == SLF_NT_REGULARIZED_VELOCITY ||
-         cls == SLF_NT_REGULARIZED_DENSITY || cls == SLF_NT_DO_NOTHING;
+         cls == SLF_NT_REGULARIZED_DENSITY || cls == SLF_NT_DO_NOTHING || cls == SLF_NT_ZOUHE_VELOCITY ||
+         cls == SLF_NT_ZOUHE_DENSITY;
 }
 
 int orc_sc_set_initial_conditions(const SlfParams *P, const uint32_t *map, REAL *d1, REAL *d2, const REAL *ivx,

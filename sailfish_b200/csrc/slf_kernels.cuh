@@ -243,6 +243,48 @@ __device__ __forceinline__ int edotn(int i, int n0, int n1, int n2) {
 // LISTED = true: `list[k]`, k in [gi0, gi1) are the indices of the nodes to process (built by
 // slf_plan_bind_map: every active node that the masked bulk kernel does not handle, sorted by
 // gi).  LISTED = false: scan the node range [gi0, gi1) and pick the non-fluid nodes.
+// zouhe_bb (boundary.mako:347-381): non-equilibrium bounce-back of the unknown populations (sym.py:750-766), then the
+// momentum excess rho v - sum e f tangential to the wall is spread evenly over the unknown populations that have a
+// component along it (zouhe_fixup, sym.py:770-815).  (n0, n1, n2): inward normal of the node.
+template <class L>
+__device__ __forceinline__ void zouhe_bb(int n0, int n1, int n2, float rho, const float (&v)[3], float (&f)[L::Q]) {
+  float feq[L::Q];
+  equilibrium<L>(rho, v, feq);
+#pragma unroll
+  for (int i = 0; i < L::Q; i++)
+    if (edotn<L>(i, n0, n1, n2) > 0) f[i] = f[L::opp(i)] - feq[L::opp(i)] + feq[i];
+  float j[3], r;
+  moments<L>(f, r, j);
+  const int nn[3] = {n0, n1, n2};
+  float nv[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    nv[d] = 0.f;
+    if (d < L::D && nn[d] == 0) {
+      int cnt = 0;
+#pragma unroll
+      for (int i = 0; i < L::Q; i++) {
+        const int sp = edotn<L>(i, n0, n1, n2);
+        const int e2 = L::ex(i) * L::ex(i) + L::ey(i) * L::ey(i) + L::ez(i) * L::ez(i);
+        const int ed = d == 0 ? L::ex(i) : (d == 1 ? L::ey(i) : L::ez(i));
+        if (sp > 0 && e2 > 1 && ed != 0) cnt++;          // unknown, not the normal direction itself
+      }
+      nv[d] = cnt ? (rho * v[d] - j[d]) / (float)cnt : 0.f;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < L::Q; i++) {
+    const int e2 = L::ex(i) * L::ex(i) + L::ey(i) * L::ey(i) + L::ez(i) * L::ez(i);
+    if (edotn<L>(i, n0, n1, n2) > 0 && e2 > 1) {
+      float val = 0.f;
+      if (L::ex(i) != 0 && n0 == 0) val += nv[0] * (float)L::ex(i);
+      if (L::ey(i) != 0 && n1 == 0) val += nv[1] * (float)L::ey(i);
+      if (L::D == 3 && L::ez(i) != 0 && n2 == 0) val += nv[2] * (float)L::ez(i);
+      f[i] += val;
+    }
+  }
+}
+
 // One node of the generic path (every node class, run-time normals); `skip_fluid`: the caller scans a node
 // range in which plain fluid nodes belong to the bulk kernel.
 template <class L, int MODEL, int MODE, bool SAVE, int HINT = 0>
@@ -274,8 +316,10 @@ boundary_node(const DevParams &P, const uint32_t *__restrict__ map, const float 
     for (int d = 1; d <= 2 * L::D; d++)
       if (orient == d) { n0 = L::ex(L::dir2vec(d)); n1 = L::ey(L::dir2vec(d)); n2 = L::ez(L::dir2vec(d)); }
   }
-  const bool vel_bc = cls == SLF_NT_EQUILIBRIUM_VELOCITY || cls == SLF_NT_REGULARIZED_VELOCITY;
-  const bool den_bc = cls == SLF_NT_EQUILIBRIUM_DENSITY || cls == SLF_NT_REGULARIZED_DENSITY;
+  const bool vel_bc = cls == SLF_NT_EQUILIBRIUM_VELOCITY || cls == SLF_NT_REGULARIZED_VELOCITY ||
+                      cls == SLF_NT_ZOUHE_VELOCITY;
+  const bool den_bc = cls == SLF_NT_EQUILIBRIUM_DENSITY || cls == SLF_NT_REGULARIZED_DENSITY ||
+                      cls == SLF_NT_ZOUHE_DENSITY;
   const bool standard = !(vel_bc || den_bc);
 
   float rho, v[3];
@@ -298,6 +342,12 @@ boundary_node(const DevParams &P, const uint32_t *__restrict__ map, const float 
       const float par_rho = P.node_params[pidx];
       const float s = (rho - par_rho) / par_rho;   // sym.py:666-680
       v[0] = (float)(-n0) * s; v[1] = (float)(-n1) * s; v[2] = (float)(-n2) * s;
+      if (cls == SLF_NT_ZOUHE_DENSITY) {          // boundary.mako:487-492: fix up, recompute the moments, impose rho
+        zouhe_bb<L>(n0, n1, n2, par_rho, v, f);
+        float r2, j2[3];
+        moments<L>(f, r2, j2);
+        v[0] = j2[0] / r2; v[1] = j2[1] / r2; v[2] = j2[2] / r2;
+      }
       rho = par_rho;
     }
   }
@@ -309,6 +359,14 @@ boundary_node(const DevParams &P, const uint32_t *__restrict__ map, const float 
       if (i < L::opp(i)) { const float tmp = f[i]; f[i] = f[L::opp(i)]; f[L::opp(i)] = tmp; }
   } else if (cls == SLF_NT_EQUILIBRIUM_VELOCITY || cls == SLF_NT_EQUILIBRIUM_DENSITY) {
     equilibrium<L>(rho, v, f);
+  } else if (cls == SLF_NT_ZOUHE_VELOCITY) {      // boundary.mako:812-816
+    if (orient == 0) {
+#pragma unroll
+      for (int i = 0; i < L::Q; i++)
+        if (i < L::opp(i)) { const float tmp = f[i]; f[i] = f[L::opp(i)]; f[L::opp(i)] = tmp; }
+    } else {
+      zouhe_bb<L>(n0, n1, n2, rho, v, f);
+    }
   } else if (cls == SLF_NT_REGULARIZED_VELOCITY || cls == SLF_NT_REGULARIZED_DENSITY) {
     if (orient == 0) {
 #pragma unroll
@@ -801,7 +859,8 @@ __device__ __forceinline__ bool is_wet_type(const DevParams &P, uint32_t type) {
   return type == P.tid[SLF_NT_FLUID] || type == P.tid[SLF_NT_HALFBB_WALL] ||
          type == P.tid[SLF_NT_EQUILIBRIUM_VELOCITY] || type == P.tid[SLF_NT_EQUILIBRIUM_DENSITY] ||
          type == P.tid[SLF_NT_REGULARIZED_VELOCITY] || type == P.tid[SLF_NT_REGULARIZED_DENSITY] ||
-         type == P.tid[SLF_NT_DO_NOTHING];
+         type == P.tid[SLF_NT_DO_NOTHING] || type == P.tid[SLF_NT_ZOUHE_VELOCITY] ||
+         type == P.tid[SLF_NT_ZOUHE_DENSITY];
 }
 
 static __global__ void __launch_bounds__(256)

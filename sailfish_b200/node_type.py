@@ -118,10 +118,32 @@ class NTRegularizedVelocity(LBNodeType):
         self.orientation = orientation
 
 
+class NTZouHeDensity(LBNodeType):
+    """node_type.py:229-239: imposed density, bounce-back of the non-equilibrium parts + tangential momentum fix-up."""
+    needs_orientation = True
+    wet_node = True
+    id = 17
+
+    def __init__(self, density, orientation=None):
+        self.params = {'density': density}
+        self.orientation = orientation
+
+
+class NTZouHeVelocity(LBNodeType):
+    """node_type.py:256-266."""
+    needs_orientation = True
+    wet_node = True
+    id = 18
+
+    def __init__(self, velocity, orientation=None):
+        self.params = {'velocity': velocity}
+        self.orientation = orientation
+
+
 _NODE_TYPES = dict((c.id, c) for c in (
     _NTFluid, _NTGhost, _NTPropagationOnly, _NTUnused, NTDoNothing, NTEquilibriumDensity,
     NTEquilibriumVelocity, NTFullBBWall, NTHalfBBWall, NTRegularizedDensity,
-    NTRegularizedVelocity))
+    NTRegularizedVelocity, NTZouHeDensity, NTZouHeVelocity))
 
 
 def get_wet_node_type_ids(allow_unused=None):

@@ -21,7 +21,7 @@ SC_POTENTIAL_IDS = {'linear': 0, 'classic': 1}
 NODE_CLASS_NAMES = (
     '_NTFluid', '_NTGhost', '_NTUnused', '_NTPropagationOnly', 'NTFullBBWall',
     'NTHalfBBWall', 'NTEquilibriumVelocity', 'NTEquilibriumDensity',
-    'NTRegularizedVelocity', 'NTRegularizedDensity', 'NTDoNothing')
+    'NTRegularizedVelocity', 'NTRegularizedDensity', 'NTDoNothing', 'NTZouHeVelocity', 'NTZouHeDensity')
 NT_COUNT = len(NODE_CLASS_NAMES)
 NT_ABSENT = 0xfffffffe
 

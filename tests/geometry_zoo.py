@@ -12,6 +12,7 @@ def make_cases(ns):
     NTEquilibriumVelocity, NTEquilibriumDensity = ns['NTEquilibriumVelocity'], ns['NTEquilibriumDensity']
     NTRegularizedVelocity, NTRegularizedDensity = ns['NTRegularizedVelocity'], ns['NTRegularizedDensity']
     NTDoNothing = ns['NTDoNothing']
+    NTZouHeVelocity, NTZouHeDensity = ns['NTZouHeVelocity'], ns['NTZouHeDensity']
 
     def sim(sub, **defaults):
         class _Sim(Sim):
@@ -82,7 +83,38 @@ def make_cases(ns):
         def initial_conditions(self, sim, hx, hy, hz):
             sim.rho[:] = 1.0
 
+    class ZouHeChannel2D(S2):
+        """Zou-He velocity inlet, Zou-He density outlet, full-way walls with a step."""
+        def boundary_conditions(self, hx, hy):
+            wall = (hy == 0) | (hy == self.gy - 1) | ((hx >= 7) & (hx <= 9) & (hy <= 3))
+            self.set_node(wall, NTFullBBWall)
+            self.set_node((hx == 0) & np.logical_not(wall), NTZouHeVelocity((0.03, 0.0)))
+            self.set_node((hx == self.gx - 1) & np.logical_not(wall), NTZouHeDensity(1.0))
+
+        def initial_conditions(self, sim, hx, hy):
+            sim.rho[:] = 1.0
+            sim.vx[:] = 0.03
+
+    class ZouHeBox3D(S3):
+        """Zou-He density planes at both x ends, Zou-He velocity on the z = top plane, full-way walls elsewhere."""
+        def boundary_conditions(self, hx, hy, hz):
+            wall = (hy == 0) | (hy == self.gy - 1) | (hz == 0)
+            wall |= (hz == self.gz - 1) & ((hx == 0) | (hx == self.gx - 1))
+            lid = (hz == self.gz - 1) & np.logical_not(wall)
+            self.set_node(wall, NTFullBBWall)
+            self.set_node(lid, NTZouHeVelocity((0.0, 0.02, 0.0)))
+            free = np.logical_not(wall | lid)
+            self.set_node((hx == 0) & free, NTZouHeDensity(1.01))
+            self.set_node((hx == self.gx - 1) & free, NTZouHeDensity(0.99))
+
+        def initial_conditions(self, sim, hx, hy, hz):
+            sim.rho[:] = 1.0 + 0.01 * (self.gx / 2.0 - hx) / self.gx
+
     return {
+        'zouhe_channel2d': (sim(ZouHeChannel2D, lat_nx=20, lat_ny=12, grid='D2Q9'), []),
+        'zouhe_box3d': (sim(ZouHeBox3D, lat_nx=12, lat_ny=10, lat_nz=9, grid='D3Q19'), []),
+        'zouhe_box3d_mrt': (sim(ZouHeBox3D, lat_nx=12, lat_ny=10, lat_nz=9, grid='D3Q19'), ['--model=mrt']),
+        'zouhe_box3d_q27': (sim(ZouHeBox3D, lat_nx=12, lat_ny=10, lat_nz=9, grid='D3Q27'), []),
         'solid_box2d': (sim(SolidBox2D, lat_nx=16, lat_ny=14, grid='D2Q9', periodic_x=True, periodic_y=True), []),
         'channel2d': (sim(Channel2D, lat_nx=20, lat_ny=12, grid='D2Q9'), []),
         'duct3d': (sim(Duct3D, lat_nx=9, lat_ny=8, lat_nz=7, grid='D3Q19', periodic_x=True), []),

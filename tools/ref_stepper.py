@@ -82,6 +82,16 @@ class RefStepper(object):
         for o in range(1, 2 * self.D + 1):
             self.noneq[o] = [(self.fs.index(a), _lam(self.fs + [S.rho] + self.vs, val))
                              for a, val in sym.noneq_bb(g, o, eq)]
+        # Zou-He closures (boundary.mako:321-382, sym.py:770-815): momentum fix-up after the non-equilibrium bounce-back
+        nv = [sympy.Symbol(n) for n in ('nvx', 'nvy', 'nvz')]
+        self.zh_fix = {}
+        for o in range(1, 2 * self.D + 1):
+            steps = []
+            for lhs, rhs in sym.zouhe_fixup(g, o):
+                lhs = sympy.Symbol(str(lhs))
+                tgt = ('nv', nv.index(lhs)) if lhs in nv else ('f', self.fs.index(lhs))
+                steps.append((tgt, _lam(self.fs + nv, rhs)))
+            self.zh_fix[o] = steps
         comps = [(a, b) for a in range(self.D) for b in range(a, self.D)]
         self.flux = [_lam(self.fs, sym.ex_flux(g, 'fi', a, b, self.cfg)) for a, b in comps]
         self.eqflux = [_lam([S.rho] + self.vs, sym.ex_eq_flux(g, a, b)) for a, b in comps]
@@ -165,8 +175,9 @@ class RefStepper(object):
 
         def m(c):
             return self.is_cls(c)[idx]
-        vel_bc = m(nt.NTEquilibriumVelocity) | m(nt.NTRegularizedVelocity)
-        den_bc = m(nt.NTEquilibriumDensity) | m(nt.NTRegularizedDensity)
+        zh_v, zh_d = m(nt.NTZouHeVelocity), m(nt.NTZouHeDensity)
+        vel_bc = m(nt.NTEquilibriumVelocity) | m(nt.NTRegularizedVelocity) | zh_v
+        den_bc = m(nt.NTEquilibriumDensity) | m(nt.NTRegularizedDensity) | zh_d
         reg_bc = m(nt.NTRegularizedVelocity) | m(nt.NTRegularizedDensity)
         eq_bc = m(nt.NTEquilibriumVelocity) | m(nt.NTEquilibriumDensity)
         # getMacro (boundary.mako:465-507)
@@ -197,6 +208,15 @@ class RefStepper(object):
                     for d in range(D):
                         v[d, sd] = self.v_dbc[o][d](r0d, pr) * np.ones(pr.shape)
                     rho[sd] = pr
+                # NTZouHeDensity (boundary.mako:487-492): fix the populations up, recompute the moments, impose rho
+                sz = s & zh_d
+                if sz.any():
+                    pz = self.node_params[pid[sz]]
+                    self._zouhe_bb(f, sz, o, pz, v[:, sz])
+                    rz = self.rho_std(*f[:, sz])
+                    for d in range(D):
+                        v[d, sz] = self.mom[d](*f[:, sz]) / rz
+                    rho[sz] = pz
                 del r0
             # precollisionBoundaryConditions (boundary.mako:784-878)
             s = m(nt.NTFullBBWall)
@@ -210,6 +230,18 @@ class RefStepper(object):
             if s.any():
                 for i in range(Q):
                     f[i, s] = self.feq[i](rho[s], *v[:, s])
+            if zh_v.any():                       # boundary.mako:812-816
+                s0 = zh_v & (ori == 0)
+                if s0.any():
+                    for i in sym.bb_swap_pairs(g):
+                        j = g.idx_opposite[i]
+                        t = f[i, s0].copy()
+                        f[i, s0] = f[j, s0]
+                        f[j, s0] = t
+                for o in range(1, 2 * D + 1):
+                    s = zh_v & (ori == o)
+                    if s.any():
+                        self._zouhe_bb(f, s, o, rho[s], v[:, s])
             if reg_bc.any():
                 s0 = reg_bc & (ori == 0)
                 if s0.any():
@@ -285,6 +317,21 @@ class RefStepper(object):
         self.iteration += 1
 
     # ------------------------------------------------------------------------------
+    def _zouhe_bb(self, f, s, o, rho, v):
+        """zouhe_bb (boundary.mako:347-381) on the nodes selected by `s` with orientation o: non-equilibrium
+        bounce-back of the unknown populations, then the tangential momentum excess is spread over them."""
+        D = self.D
+        fin = f[:, s].copy()
+        for i, fn in self.noneq[o]:
+            f[i, s] = fn(*fin, rho, *v)
+        nv = [rho * v[d] - self.mom[d](*f[:, s]) for d in range(D)] + [np.zeros_like(rho)] * (3 - D)
+        for (kind, k), fn in self.zh_fix[o]:
+            val = fn(*f[:, s], *nv) * np.ones_like(rho)
+            if kind == 'nv':
+                nv[k] = val
+            else:
+                f[k, s] = val
+
     def _bgk(self, f, rho, v, s):
         """BGK_relaxate0, relaxation.mako:99-181."""
         D, Q = self.D, self.Q
