@@ -219,6 +219,7 @@ int slf_plan_destroy(SlfPlan *plan) {
   if (plan->d_list) cudaFree(plan->d_list);
   if (plan->d_push_done) cudaFree(plan->d_push_done);
   if (plan->d_other_mask) cudaFree(plan->d_other_mask);
+  if (plan->d_seg) cudaFree(plan->d_seg);
   if (plan->d_flags) cudaFree(plan->d_flags);
   delete plan;
   return 0;
@@ -274,6 +275,25 @@ int slf_plan_bind_map(SlfPlan *pl, uint64_t map) {
   CUDA_OK(cudaMemcpy(pl->d_fluid_mask, fm.data(), (size_t)words * 4, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(pl->d_wall_mask, wm.data(), (size_t)words * 4, cudaMemcpyHostToDevice));
   if (!list.empty()) CUDA_OK(cudaMemcpy(pl->d_list, list.data(), list.size() * 4, cudaMemcpyHostToDevice));
+  // segment list: worth it when a good part of the mask words of the real layers holds no fluid at all
+  if (pl->d_seg) { cudaFree(pl->d_seg); pl->d_seg = nullptr; }
+  pl->seg_off.clear();
+  if (slab % 32 == 0 && d.DS < (1ll << 32) && !getenv("SLF_NO_SEGMENTS")) {
+    std::vector<uint32_t> seg;
+    std::vector<long long> off(outer + 1, 0);
+    const long long wps = slab / 32;
+    for (int o = 0; o < outer; o++) {
+      off[o] = (long long)seg.size();
+      for (long long w = wps * o; w < wps * (o + 1); w++) if (fm[(size_t)w]) seg.push_back((uint32_t)w);
+    }
+    off[outer] = (long long)seg.size();
+    const long long real_words = wps * (outer > 2 ? outer - 2 : outer);
+    if (!seg.empty() && (double)seg.size() < 0.85 * (double)real_words) {
+      CUDA_OK(cudaMalloc((void **)&pl->d_seg, seg.size() * 4));
+      CUDA_OK(cudaMemcpy(pl->d_seg, seg.data(), seg.size() * 4, cudaMemcpyHostToDevice));
+      pl->seg_off = off;
+    }
+  }
   pl->bound_map = map;
   return 0;
 }

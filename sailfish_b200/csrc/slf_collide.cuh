@@ -20,10 +20,20 @@ static int launch_collide(SlfPlan *pl, const uint32_t *map, const float *din, fl
     if constexpr (MODE != MODE_AB) {
       if (plain) {
         float *dist = dout;      // AA: dist_in == dist_out (checked by the caller)
-        collide_bulk_aa_tab<L, MODEL, SAVE><<<(unsigned)nb, bs, 0, s>>>(
-            pl->dp, make_aa_table<L>(pl->dp, dist, gi0, MODE == MODE_AA_ODD), pl->d_fluid_mask, rho, vx, vy, vz,
-            gi0, (unsigned)n);
-        LAUNCH_OK("collide_bulk_aa");
+        if (pl->d_seg) {
+          const long long s0 = pl->seg_off[z0], s1 = pl->seg_off[z1];
+          if (s1 > s0) {
+            collide_bulk_aa_seg<L, MODEL, SAVE><<<(unsigned)((s1 - s0 + 3) / 4), bs, 0, s>>>(
+                pl->dp, make_aa_table<L>(pl->dp, dist, 0, MODE == MODE_AA_ODD), pl->d_fluid_mask, pl->d_seg + s0,
+                (unsigned)(s1 - s0), rho, vx, vy, vz);
+            LAUNCH_OK("collide_bulk_aa_seg");
+          }
+        } else {
+          collide_bulk_aa_tab<L, MODEL, SAVE><<<(unsigned)nb, bs, 0, s>>>(
+              pl->dp, make_aa_table<L>(pl->dp, dist, gi0, MODE == MODE_AA_ODD), pl->d_fluid_mask, rho, vx, vy, vz,
+              gi0, (unsigned)n);
+          LAUNCH_OK("collide_bulk_aa");
+        }
       }
     }
     if (MODE == MODE_AB && plain) {

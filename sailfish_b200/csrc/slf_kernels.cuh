@@ -169,6 +169,24 @@ collide_bulk_aa_tab(const DevParams P, const SlotTable<L> T, const uint32_t *__r
   bulk_aa_node<L, MODEL, SAVE>(P, T, orho, ovx, ovy, ovz, gi, t);
 }
 
+// Sparse geometries (a pipe in a box: BASELINE config 3): the same node body driven by a list of the 32-node
+// segments that contain fluid at all (built by slf_plan_bind_map), one warp per segment.  40 % of the threads of the
+// dense launch are padding or solid there and leave at once; the list removes them (ncu, profiles/r02_c3_ab_kernels.txt:
+// 49 % occupancy, issue-bound).  Segments are aligned mask words, so the accesses stay whole lines.
+template <class L, int MODEL, bool SAVE>
+__global__ void __launch_bounds__(128, BulkTuning<L, MODEL>::MINB)
+collide_bulk_aa_seg(const DevParams P, const SlotTable<L> T, const uint32_t *__restrict__ fluid_mask,
+                    const uint32_t *__restrict__ seg, unsigned nseg, float *__restrict__ orho,
+                    float *__restrict__ ovx, float *__restrict__ ovy, float *__restrict__ ovz) {
+  const unsigned wi = blockIdx.x * 4u + (threadIdx.x >> 5);
+  if (wi >= nseg) return;
+  const unsigned w = seg[wi];
+  const unsigned lane = threadIdx.x & 31u;
+  if (!((fluid_mask[w] >> lane) & 1u)) return;
+  const unsigned t = w * 32u + lane;               // tables are based at node 0
+  bulk_aa_node<L, MODEL, SAVE>(P, T, orho, ovx, ovy, ovz, (long long)t, t);
+}
+
 // AB (two-lattice) counterpart: loads from `din` at the node, stores to `dout` at the downstream neighbours, both
 // through per-slot base pointers.  Measured (tools/exp_ab.cu on B200, profiles/r02_exp_ab.txt): the tables are worth
 // +1 % over 64-bit index arithmetic on this kernel, and a shared-memory x shift that turns every store into whole

@@ -39,6 +39,8 @@ struct SlfPlan {
   // derived from a bound node map (slf_plan_bind_map)
   uint64_t bound_map = 0;
   uint32_t *d_fluid_mask = nullptr, *d_wall_mask = nullptr, *d_list = nullptr;
+  uint32_t *d_seg = nullptr;           // indices of the mask words that contain fluid (sparse geometries), or null
+  std::vector<long long> seg_off;      // segment-list offsets per outermost-axis layer (size n + 1)
   uint32_t *d_other_mask = nullptr;    // 1 bit per node: member of d_list (multi-step kernel)
   unsigned int *d_flags = nullptr;     // per-block step counters of the multi-step kernel
   std::vector<long long> layer_off;    // list offsets per outermost-axis layer (size n + 1)
