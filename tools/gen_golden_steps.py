@@ -323,6 +323,7 @@ def gen_geometry_zoo():
             out[key + '/type_names'] = pk['type_names']
             out[key + '/type_ids'] = pk['type_ids']
             out[key + '/fluid_map'] = r._subdomain.fluid_map()
+            out[key + '/unused_tag_bits'] = np.int64(ctx.get('unused_tag_bits', 0))
             out[key + '/rho0'] = r.field_base(r._sim.rho).astype(np.float32)
             print('%-24s map %s types %s' % (key, out[key + '/map'].shape, dict(zip(pk['type_names'], pk['type_ids']))))
     np.savez_compressed(os.path.join(GOLD, 'geometry_zoo.npz'), **out)
