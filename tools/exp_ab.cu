@@ -61,6 +61,28 @@ k1(const DevParams P, const Tab T, const uint32_t *__restrict__ fmask, long long
   for (int i = 0; i < L::Q; i++) T.st[i][t] = f[i];
 }
 
+// V1 with cache operators: LD = 0 default / 1 ld.cs (evict first) / 2 ld.cg (L2 only); ST = 0 default / 1 st.cs / 2 st.wt
+template <int MINB, int LD, int ST>
+__global__ void __launch_bounds__(128, MINB)
+k1h(const DevParams P, const Tab T, const uint32_t *__restrict__ fmask, long long gi0, unsigned n) {
+  const unsigned t = blockIdx.x * 128u + threadIdx.x;
+  if (t >= n) return;
+  const long long gi = gi0 + t;
+  if (!((fmask[gi >> 5] >> (gi & 31)) & 1u)) return;
+  float f[L::Q];
+#pragma unroll
+  for (int i = 0; i < L::Q; i++) f[i] = LD == 1 ? __ldcs(T.ld[i] + t) : (LD == 2 ? __ldcg(T.ld[i] + t) : T.ld[i][t]);
+  float rho, v[3];
+  moments<L>(f, rho, v);
+  const float inv = 1.0f / rho;
+  v[0] *= inv; v[1] *= inv; v[2] *= inv;
+  collide_bgk<L>(P, rho, v, f);
+#pragma unroll
+  for (int i = 0; i < L::Q; i++) {
+    if (ST == 1) __stcs(T.st[i] + t, f[i]); else if (ST == 2) __stwt(T.st[i] + t, f[i]); else T.st[i][t] = f[i];
+  }
+}
+
 // number of directions with e_x != 0 and their position among them
 __host__ __device__ constexpr int xdir_index(int i) {
   int k = 0;
@@ -198,6 +220,14 @@ int main(int argc, char **argv) {
   run("V0 direct minb10", c, [=](Ctx &c) { k0<10><<<nb, 128>>>(c.P, c.fmask, c.din, c.dout, c.gi0, c.gi1); }, true);
   run("V1 tables minb10", c, [=](Ctx &c) { k1<10><<<nb, 128>>>(c.P, make_tab(c, true), c.fmask, c.gi0, (unsigned)n); }, false);
   run("V2 tables+xshift minb10", c, [=](Ctx &c) { k2<10><<<nb, 128>>>(c.P, make_tab(c, false), c.fmask, c.gi0, (unsigned)n); }, false);
+  run("V1 ld.cs st.cs minb10", c, [=](Ctx &c) { k1h<10, 1, 1><<<nb, 128>>>(c.P, make_tab(c, true), c.fmask, c.gi0, (unsigned)n); }, false);
+  run("V1 ld.cg st.default minb10", c, [=](Ctx &c) { k1h<10, 2, 0><<<nb, 128>>>(c.P, make_tab(c, true), c.fmask, c.gi0, (unsigned)n); }, false);
+  run("V1 ld.default st.cs minb10", c, [=](Ctx &c) { k1h<10, 0, 1><<<nb, 128>>>(c.P, make_tab(c, true), c.fmask, c.gi0, (unsigned)n); }, false);
+  run("V1 ld.cs st.default minb10", c, [=](Ctx &c) { k1h<10, 1, 0><<<nb, 128>>>(c.P, make_tab(c, true), c.fmask, c.gi0, (unsigned)n); }, false);
+  run("V1 ld.cg st.wt minb10", c, [=](Ctx &c) { k1h<10, 2, 2><<<nb, 128>>>(c.P, make_tab(c, true), c.fmask, c.gi0, (unsigned)n); }, false);
+  run("V1 tables minb8", c, [=](Ctx &c) { k1<8><<<nb, 128>>>(c.P, make_tab(c, true), c.fmask, c.gi0, (unsigned)n); }, false);
+  run("V1 tables minb12", c, [=](Ctx &c) { k1<12><<<nb, 128>>>(c.P, make_tab(c, true), c.fmask, c.gi0, (unsigned)n); }, false);
+  run("V1 tables minb6", c, [=](Ctx &c) { k1<6><<<nb, 128>>>(c.P, make_tab(c, true), c.fmask, c.gi0, (unsigned)n); }, false);
   run("V2 tables+xshift minb8", c, [=](Ctx &c) { k2<8><<<nb, 128>>>(c.P, make_tab(c, false), c.fmask, c.gi0, (unsigned)n); }, false);
   return 0;
 }
