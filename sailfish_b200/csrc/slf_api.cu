@@ -617,7 +617,12 @@ int slf_graph_end_capture(uint64_t stream, uint64_t *graph_exec) {
   if (ce != cudaSuccess) { cudaGetLastError(); return fail((int)ce, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce)); }
   SlfGraph *g = new SlfGraph();
   g->kernels = kernels;
-  ce = cudaGraphInstantiate(&g->exec, graph, 0);
+  // The recorded step forks onto a high-priority stream (slabs + pushes) beside the interior kernel.  Without this
+  // flag every node runs at the priority of the stream the graph is launched into, the slab kernels' blocks queue
+  // behind the interior kernel's pending blocks, and the chain wait -> slabs -> pushes is only dispatched at the end
+  // of the step instead of beside it.
+  const unsigned long long flags = getenv("SLF_GRAPH_NO_NODE_PRIORITY") ? 0ull : (unsigned long long)cudaGraphInstantiateFlagUseNodePriority;
+  ce = cudaGraphInstantiateWithFlags(&g->exec, graph, flags);
   cudaGraphDestroy(graph);
   if (ce != cudaSuccess) { delete g; return fail((int)ce, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); }
   *graph_exec = (uint64_t)g;
