@@ -44,7 +44,7 @@ def main():
             reqs.append(dist.isend(t, other, tag=face))
             # the neighbour sends through its opposite face
             oface = face ^ 1
-            from sailfish_b200 import halo
+            import halo_ref as halo
             rslots, _, rdst = halo.face_transfer(mine['grid'], oface, sub.swap, lat_n[other], sub.shape[0])
             buf = torch.empty_like(t)
             reqs.append(dist.irecv(buf, other, tag=oface))

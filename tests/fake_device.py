@@ -186,8 +186,9 @@ class FakeLib(object):
         return p.arr_nz if p.dim == 3 else p.arr_ny
 
     def _slf_halo_push(self, plan, dist, face, peer_dist, peer_lat_n, peer_arr_n, with_swap, signal, stream):
-        """sailfish_b200.halo.face_transfer is the host statement of this copy."""
-        from sailfish_b200 import halo, lattice
+        """tests/halo_ref.face_transfer is the host statement of this copy."""
+        import halo_ref as halo
+        from sailfish_b200 import lattice
         p = self._p(plan)
         plane = p.dist_size // self._outer(p)
         lat_n = p.lat_nz if p.dim == 3 else p.lat_ny

@@ -1,5 +1,6 @@
-"""Which planes cross a face, host-side statement (the device statement is
-sailfish_b200/csrc/slf_halo.cuh; tests check they agree).
+"""TEST INFRASTRUCTURE: which planes cross a face of a z-split, host-side statement used by the CPU stand-in device
+and the oracle-driven multi-subdomain harness (the device statement is sailfish_b200/csrc/slf_halo.cuh, which the
+GPU tests check against the oracle's collect / distribute).
 
 For subdomains split along the outermost axis a face message is, per population that
 crosses the face (sym.get_interblock_dists, sym.py:829-845), one whole plane of the SoA

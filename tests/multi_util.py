@@ -1,9 +1,10 @@
 """Drives several subdomains with the CPU oracle the way the B200 runner drives them on GPUs
 (sailfish_b200/subdomain_runner.py step()): collide, local PBC, then the planes of
-sailfish_b200.halo.face_transfer move into the neighbours' lattices."""
+tests/halo_ref.face_transfer move into the neighbours' lattices."""
 import numpy as np
 
-from sailfish_b200 import halo, params as P
+import halo_ref as halo
+from sailfish_b200 import params as P
 from sailfish_b200.controller import LBSimulationController
 
 
