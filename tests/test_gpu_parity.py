@@ -4,8 +4,8 @@ Metric: ||gpu - ref||_inf / ||ref||_inf over real (non-ghost) nodes; rho and v o
 The reference arithmetic is fp32; its own round-off against exact (fp64) arithmetic is measured
 with the fp32 oracle and is ~1e-6 for rho and up to ~2e-5 for v after 20 steps (v is a small
 difference of O(1) populations).  Bar:
-  * after 4 steps: <= 1e-6 (rho, populations), <= 1e-5 (v) against the fp64 oracle
-    [north_star: 1e-6 fp32], or 1.5x the fp32 oracle's own error where that is larger (MRT);
+  * after 4 steps: <= 1e-6 (rho, populations, v) against the fp64 oracle [north_star: 1e-6 fp32], or 1.5x (v: 2x)
+    the fp32 oracle's own error where that is larger;
   * after the full golden step count: within 2x the fp32 oracle's own error (+1e-6).
 """
 import numpy as np
@@ -55,7 +55,7 @@ def test_short_run_within_1e6(oracle, case):
     # 1e-6 where the reference's own fp32 arithmetic achieves it, else no worse than 1.5x that
     assert e_dist <= max(1e-6, 1.5 * o_dist), (e_dist, o_dist)
     assert e_rho <= max(1e-6, 1.5 * o_rho), (e_rho, o_rho)
-    assert e_v <= max(1e-5, 1.5 * o_v), (e_v, o_v)
+    assert e_v <= max(1e-6, 2.0 * o_v), (e_v, o_v)
     assert e_rho <= 2e-6 and e_dist <= 2e-6
 
 
