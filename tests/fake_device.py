@@ -201,7 +201,8 @@ class FakeLib(object):
         self.launches += 1
 
     def _slf_halo_push_face(self, plan, dist, face, peer_dist, peer_lat, peer_arr, with_swap, signal, stream):
-        """Dimension-ordered exchange through any face (csrc/slf_halo.cuh: windows along the other axes)."""
+        """Dimension-ordered exchange through any face (window rules: tests/halo_ref.face_windows)."""
+        import halo_ref
         from sailfish_b200 import lattice
         p = self._p(plan)
         D = p.dim
@@ -210,30 +211,10 @@ class FakeLib(object):
         arr = [p.arr_nx, p.arr_ny, p.arr_nz][:D]
         plat = [int(peer_lat[k]) for k in range(D)]
         parr = [int(peer_arr[k]) for k in range(D)]
-        face, swap = int(face), bool(with_swap)
-        axis, hi = face // 2, face & 1
-        sgn = 1 if hi else -1
         mine = self._arr(dist, np.float32, p.dist_size * p.Q).reshape([p.Q] + arr[::-1])
         peer = self._arr(peer_dist, np.float32, int(np.prod(parr)) * p.Q).reshape([p.Q] + parr[::-1])
-        n, pn = lat[axis], plat[axis]
-        src_layer = (n - 2 if hi else 1) if swap else (n - 1 if hi else 0)
-        dst_layer = (0 if hi else pn - 1) if swap else (1 if hi else pn - 2)
-        for i, e in enumerate(grid.basis):
-            e = [int(c) for c in e]
-            if e[axis] * sgn < 1:
-                continue
-            slot = int(grid.opposite[i]) if swap else i
-            idx_s, idx_d = [None] * D, [None] * D
-            for ax in range(D):
-                if ax == axis:
-                    idx_s[ax], idx_d[ax] = src_layer, dst_layer
-                else:
-                    if ax < axis:
-                        lo = 1 - e[ax] if swap else 1
-                    else:
-                        lo = 1 if swap else 1 + e[ax]
-                    idx_s[ax] = idx_d[ax] = slice(lo, lo + lat[ax] - 2)
-            peer[(slot,) + tuple(idx_d[::-1])] = mine[(slot,) + tuple(idx_s[::-1])]
+        for slot, src, dst in halo_ref.face_windows(grid, lat, int(face), bool(with_swap), plat):
+            peer[(slot,) + tuple(dst[::-1])] = mine[(slot,) + tuple(src[::-1])]
         self.launches += 1
 
     def _slf_halo_push_field(self, plan, field, face, peer_field, peer_lat_n, stream):

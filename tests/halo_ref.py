@@ -43,3 +43,35 @@ def extract_planes(dist, slots, layer):
 def insert_planes(dist, slots, layer, planes):
     for k, s in enumerate(slots):
         dist[s, layer] = planes[k]
+
+
+def face_windows(grid, lat, face, with_swap, peer_lat):
+    """Dimension-ordered exchange through ANY face (subdomains split along x / y too): for every population that
+    crosses `face`, (slot, source index, destination index) as tuples over the axes (x, y[, z]) -- ints along the
+    face axis, slices along the others.  Host statement of the window rules of csrc/slf_halo.cuh:
+      after streaming steps: earlier axes 1 .. n-2, later axes 1+e .. n-2+e;
+      after in-place steps : earlier axes 1-e .. n-2-e, later axes 1 .. n-2."""
+    D = len(lat)
+    axis, hi = face // 2, face & 1
+    sgn = 1 if hi else -1
+    n, pn = lat[axis], peer_lat[axis]
+    src_layer = (n - 2 if hi else 1) if with_swap else (n - 1 if hi else 0)
+    dst_layer = (0 if hi else pn - 1) if with_swap else (1 if hi else pn - 2)
+    out = []
+    for i, e in enumerate(grid.basis):
+        e = [int(c) for c in e]
+        if e[axis] * sgn < 1:
+            continue
+        slot = int(grid.opposite[i]) if with_swap else i
+        src, dst = [None] * D, [None] * D
+        for ax in range(D):
+            if ax == axis:
+                src[ax], dst[ax] = src_layer, dst_layer
+                continue
+            if ax < axis:
+                lo = 1 - e[ax] if with_swap else 1
+            else:
+                lo = 1 if with_swap else 1 + e[ax]
+            src[ax] = dst[ax] = slice(lo, lo + lat[ax] - 2)
+        out.append((slot, tuple(src), tuple(dst)))
+    return out
