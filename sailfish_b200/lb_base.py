@@ -8,6 +8,9 @@ from sailfish_b200 import lattice
 
 ScalarField = namedtuple('ScalarField', 'name')
 VectorField = namedtuple('VectorField', 'name')
+# What the reference hands to code generation under ctx['forces'] (lb_base.py:316, :363): numeric forces as
+# {grid: {is_acceleration: vector}}, symbolic ones by expression.
+ForcePair = namedtuple('ForcePair', 'numeric symbolic')
 
 
 class LBSim(object):
@@ -49,6 +52,26 @@ class LBSim(object):
     @classmethod
     def fields(cls):
         return []
+
+    def constants(self):
+        """lb_base.py:104-107: named constants of the model (the Shan-Chen couplings)."""
+        return {}
+
+    def update_context(self, ctx):
+        """The model's share of the kernel configuration, under the keys the reference passes to code
+        generation (lb_base.py:120-137).  `params.from_context` turns the finished dict into SlfParams; the
+        same function serves the unmodified reference on --backends=b200, so both ways in configure the
+        kernels through one path."""
+        cfg = self.config
+        ctx['grid'] = self.grid
+        ctx['grids'] = self.grids
+        ctx['constants'] = self.constants()
+        ctx['relaxation_enabled'] = getattr(cfg, 'relaxation_enabled', True)
+        ctx['propagation_enabled'] = getattr(cfg, 'propagation_enabled', True)
+        ctx['access_pattern'] = cfg.access_pattern
+        ctx['node_addressing'] = getattr(cfg, 'node_addressing', 'direct')
+        ctx['propagate_on_read'] = getattr(cfg, 'propagate_on_read', False)
+        ctx['config'] = cfg
 
     def get_state(self):
         """lb_base.py:216-220: what a checkpoint stores besides the populations."""
@@ -97,6 +120,7 @@ class LBForcedSim(LBSim):
     def __init__(self, config):
         super(LBForcedSim, self).__init__(config)
         self._forces = {}
+        self._force_couplings = {}
 
     @classmethod
     def add_options(cls, group, dim):
@@ -111,6 +135,19 @@ class LBForcedSim(LBSim):
             raise ValueError('no lattice %d in this model' % grid)
         cur = self._forces.setdefault(grid, np.zeros(dim, np.float64))
         self._forces[grid] = cur + np.float64(force)
+
+    def update_context(self, ctx):
+        """lb_base.py:361-366."""
+        super(LBForcedSim, self).update_context(ctx)
+        numeric = dict((g, {True: tuple(float(x) for x in a)}) for g, a in self._forces.items())
+        ctx['forces'] = ForcePair(numeric, {})
+        ctx['force_couplings'] = dict(self._force_couplings)
+        ctx['force_implementation'] = getattr(self.config, 'force_implementation', 'guo')
+
+    def add_force_coupling(self, grid_a, grid_b, const_name):
+        """lb_base.py:386-394: Shan-Chen interaction of component grid_a with grid_b, strength
+        constants()[const_name]."""
+        self._force_couplings[(grid_a, grid_b)] = const_name
 
     def body_acceleration(self, grid=0):
         if grid not in self._forces:

@@ -16,13 +16,43 @@ class LBBinaryFluidBase(LBSim):
     def add_options(cls, group, dim):
         group.add_argument('--tau_phi', type=float, default=1.0, help='relaxation time for the phase field')
 
+    def update_context(self, ctx):
+        """lb_binary.py:130-133."""
+        super(LBBinaryFluidBase, self).update_context(ctx)
+        ctx['tau_phi'] = self.config.tau_phi
+        ctx['model'] = 'bgk'
+
 
 class LBBinaryFluidShanChen(LBBinaryFluidBase, LBForcedSim):
     """lb_binary.py:375-420: two BGK lattices coupled by the Shan-Chen force (G11, G12 = G21, G22)."""
 
+    def __init__(self, config):
+        """lb_binary.py:382-387."""
+        super(LBBinaryFluidShanChen, self).__init__(config)
+        self.add_force_coupling(0, 0, 'G11')
+        self.add_force_coupling(0, 1, 'G12')
+        self.add_force_coupling(1, 0, 'G21')
+        self.add_force_coupling(1, 1, 'G22')
+
+    def constants(self):
+        """lb_binary.py:389-395: the cross coupling is symmetric (G21 = G12)."""
+        ret = super(LBBinaryFluidShanChen, self).constants()
+        cfg = self.config
+        ret.update(G11=cfg.G11, G12=cfg.G12, G21=cfg.G12, G22=cfg.G22)
+        return ret
+
     @classmethod
     def fields(cls):
         return [ScalarField('rho'), ScalarField('phi'), VectorField('v')]
+
+    def update_context(self, ctx):
+        """lb_binary.py:416-421."""
+        super(LBBinaryFluidShanChen, self).update_context(ctx)
+        cfg = self.config
+        ctx['simtype'] = 'shan-chen'
+        ctx['sc_potential'] = cfg.sc_potential
+        ctx['tau'] = (6.0 * cfg.visc + 1.0) / 2.0
+        ctx['visc'] = cfg.visc
 
     @classmethod
     def add_options(cls, group, dim):

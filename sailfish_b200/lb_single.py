@@ -13,3 +13,16 @@ class LBFluidSim(LBSim):
     @classmethod
     def fields(cls):
         return [ScalarField('rho'), VectorField('v')]
+
+    def update_context(self, ctx):
+        """lb_single.py:52-70.  tau = (6 visc + 1) / 2 (sym.relaxation_time); the kernels take the viscosity
+        and form the relaxation rates themselves, as the generated code does."""
+        super(LBFluidSim, self).update_context(ctx)
+        cfg = self.config
+        ctx['tau'] = (6.0 * cfg.visc + 1.0) / 2.0
+        ctx['visc'] = cfg.visc
+        ctx['model'] = cfg.model
+        ctx['simtype'] = 'lbm'
+        ctx['subgrid'] = getattr(cfg, 'subgrid', 'none')
+        ctx['regularized'] = getattr(cfg, 'regularized', False)
+        ctx['incompressible'] = getattr(cfg, 'incompressible', False)

@@ -358,6 +358,20 @@ class Subdomain(object):
     def num_fluid_nodes(self):
         return int(np.sum(self.fluid_map()))
 
+    def update_context(self, ctx):
+        """The encoder's share of the kernel configuration (geo_encoder.py:341-363 via subdomain.py:781-793)."""
+        ctx.update({
+            'use_link_tags': getattr(self.config, 'use_link_tags', True),
+            'node_types': self.node_types,
+            'type_id_remap': self.type_id_remap,
+            'nt_misc_shift': self.bits[0],
+            'nt_param_shift': self.bits[1],
+            'nt_scratch_shift': self.bits[2],
+            'node_params': self.node_params,
+            'scratch_space': False,
+            'unused_tag_bits': getattr(self, 'unused_tag_bits', 0),
+        })
+
     def type_ids_by_name(self):
         return dict((c.__name__, int(self.type_id_remap[c.id])) for c in self.node_types)
 

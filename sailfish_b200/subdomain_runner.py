@@ -195,18 +195,27 @@ class SubdomainRunner(object):
             setattr(sim, 'v' + c, sim.v[i])
         self._subdomain.init_fields(sim)
 
-    def make_params(self):
-        sd, cfg, g = self._subdomain, self.config, self._sim.grid
+    def update_context(self, ctx):
+        """subdomain_runner.py:182-248 of the reference: model, encoder, then the array geometry of this
+        subdomain (lattice size with ghosts, padded array size, which axes wrap locally)."""
+        self._sim.update_context(ctx)
+        sd = self._subdomain
+        sd.update_context(ctx)
         lat = list(reversed(sd.lat_shape)) + ([1] if self.dim == 2 else [])
         arr = list(reversed(sd.arr_shape)) + ([1] if self.dim == 2 else [])
-        per = list(self._spec._periodicity) + [False] * (3 - self.dim)
-        return P.make_params(
-            g.name, cfg.model, cfg.access_pattern, lat, arr, per, sd.bits, sd.type_ids_by_name(),
-            sd.node_params, cfg.visc, self._sim.body_acceleration(),
-            use_link_tags=getattr(cfg, 'use_link_tags', True),
-            relaxation_enabled=getattr(cfg, 'relaxation_enabled', True),
-            propagation_enabled=getattr(cfg, 'propagation_enabled', True),
-            unused_tag_bits=getattr(sd, 'unused_tag_bits', 0))
+        for a, n, m in zip('xyz', lat, arr):
+            ctx['lat_n' + a] = n
+            ctx['arr_n' + a] = m
+        ctx['block_periodicity'] = list(self._spec._periodicity) + [False] * (3 - self.dim)
+        ctx['sim'] = self._sim
+        ctx['block'] = self._spec
+
+    def make_params(self):
+        """SlfParams of this subdomain, through the same context -> parameters function that serves the
+        unmodified reference (params.from_context)."""
+        ctx = {}
+        self.update_context(ctx)
+        return P.from_context(ctx)
 
     def _init_compute(self):
         from sailfish_b200.runtime import DeviceLattice
@@ -686,22 +695,12 @@ class NNSubdomainRunner(SubdomainRunner):
         self._subdomain.init_fields(sim)
 
     def make_params(self):
-        sd, cfg, g = self._subdomain, self.config, self._sim.grid
-        lat = list(reversed(sd.lat_shape)) + ([1] if self.dim == 2 else [])
-        arr = list(reversed(sd.arr_shape)) + ([1] if self.dim == 2 else [])
-        per = list(self._spec._periodicity) + [False] * (3 - self.dim)
-        unsupported = set(sd.type_ids_by_name()) - {'_NTFluid', '_NTGhost', '_NTUnused', '_NTPropagationOnly',
-                                                    'NTFullBBWall'}
+        unsupported = set(self._subdomain.type_ids_by_name()) - {'_NTFluid', '_NTGhost', '_NTUnused',
+                                                                 '_NTPropagationOnly', 'NTFullBBWall'}
         if unsupported:
             raise P.UnsupportedConfiguration('Shan-Chen path supports fluid and full-way bounce-back nodes; got %s'
                                              % sorted(unsupported))
-        return P.make_params(
-            g.name, 'bgk', cfg.access_pattern, lat, arr, per, sd.bits, sd.type_ids_by_name(),
-            sd.node_params, cfg.visc, self._sim.body_acceleration(0),
-            use_link_tags=getattr(cfg, 'use_link_tags', True),
-            shan_chen=dict(tau_phi=cfg.tau_phi, G11=cfg.G11, G12=cfg.G12, G21=cfg.G12, G22=cfg.G22,
-                           accel1=self._sim.body_acceleration(1),
-                           potential=cfg.sc_potential))
+        return super(NNSubdomainRunner, self).make_params()
 
     def _init_compute(self):
         from sailfish_b200.runtime import DeviceShanChenLattice

@@ -139,6 +139,24 @@ def test_native_host_stack_equals_reference_host_stack(reference, oracle, monkey
     fake_device.install_fake(monkeypatch)
     script, cls_name, native_mod, geo_name, args = NATIVE[name]
     steps = 10
+    # both stacks hand a context dict under the reference's keys to params.from_context; keep what comes out
+    from sailfish_b200 import params as P
+    made = []
+    real_from_context = P.from_context
+
+    def recording_from_context(ctx):
+        p = real_from_context(ctx)
+        vals = []
+        for fname, ftype in p._fields_:
+            v = getattr(p, fname)
+            if fname == 'node_params':
+                v = [v[i] for i in range(p.num_node_params)]
+            elif hasattr(v, '__len__'):
+                v = list(v)
+            vals.append((fname, v))
+        made.append((vals, set(ctx)))
+        return p
+    monkeypatch.setattr(P, 'from_context', recording_from_context)
     common = args + ['--access_pattern=' + ap, '--max_iters=%d' % steps, '--every=%d' % steps, '--quiet']
     # reference stack
     mod = reference.load_example(script)
@@ -147,6 +165,8 @@ def test_native_host_stack_equals_reference_host_stack(reference, oracle, monkey
     out_ref = str(tmp_path / 'ref')
     monkeypatch.setattr(sys, 'argv', [script] + common + ['--backends=b200', '--debug_single_process', '--output=' + out_ref])
     RefController(getattr(mod, cls_name), getattr(refgeo, geo_name) if geo_name else None).run()
+    n_ref = len(made)
+    assert n_ref >= 1
     # native stack
     from sailfish_b200 import geo as mygeo
     from sailfish_b200.controller import LBSimulationController
@@ -156,6 +176,10 @@ def test_native_host_stack_equals_reference_host_stack(reference, oracle, monkey
     monkeypatch.setattr(sys, 'argv', ['x'] + native_args)
     geo_cls = getattr(mygeo, geo_name, None) if geo_name else None
     LBSimulationController(getattr(nat, cls_name), geo_cls).run()
+    assert len(made) == n_ref + 1
+    # the kernel parameter block is the same, field for field, and the mirror's context uses the reference's keys
+    assert made[-1][0] == made[0][0]
+    assert made[-1][1] <= made[0][1], sorted(made[-1][1] - made[0][1])
     fr = sorted(glob.glob(out_ref + '.0.*%d.npz' % steps))
     fn = sorted(glob.glob(out_nat + '.0.*%d.npz' % steps))
     assert fr and fn
