@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SLF_ABI_VERSION 5
+#define SLF_ABI_VERSION 6
 
 /* error codes (negative; positive values are cudaError_t) */
 #define SLF_EINVAL      (-1)   /* bad argument / unsupported configuration          */
@@ -70,6 +70,8 @@ enum {
   SLF_NT_DO_NOTHING,            /* :296 NTDoNothing                       */
   SLF_NT_ZOUHE_VELOCITY,        /* :256 NTZouHeVelocity                   */
   SLF_NT_ZOUHE_DENSITY,         /* :229 NTZouHeDensity                    */
+  SLF_NT_COPY,                  /* :310 NTCopy (AB access pattern only)   */
+  SLF_NT_YU_OUTFLOW,            /* :336 NTYuOutflow (AB only)             */
   SLF_NT_COUNT
 };
 #define SLF_NT_ABSENT 0xfffffffeu   /* geo_encoder.py:44-50 */

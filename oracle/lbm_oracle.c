@@ -210,6 +210,9 @@ static int ctx_init(Ctx *C, const SlfParams *P) {
   if (P->lattice < 0 || P->lattice > 2) return SLF_EINVAL;
   C->P = P; C->L = &g_lat[P->lattice];
   if (P->model == SLF_MRT && !C->L->has_mrt) return SLF_EUNSUPPORTED;
+  if (P->access_pattern == SLF_AA &&                 /* boundary.mako:626-628 */
+      (P->type_id[SLF_NT_COPY] != SLF_NT_ABSENT || P->type_id[SLF_NT_YU_OUTFLOW] != SLF_NT_ABSENT))
+    return SLF_EUNSUPPORTED;
   C->nx = P->lat_nx; C->ny = P->lat_ny; C->nz = C->L->D == 3 ? P->lat_nz : 1;
   C->ax = P->arr_nx; C->ay = P->arr_ny; C->az = C->L->D == 3 ? P->arr_nz : 1;
   C->DS = (long long)C->ax * C->ay * C->az;
@@ -514,9 +517,21 @@ int orc_collide_and_propagate(const SlfParams *P, const uint32_t *map, const REA
       /* getDist */
       if (!odd) for (int i = 0; i < Q; i++) f[i] = din[gi + DS * i];
       else      for (int i = 0; i < Q; i++) f[i] = din[gi - off[i] + DS * L->opp[i]];
+      /* fixMissingDistributions, boundary.mako:574-605: copy / extrapolation outflow takes the populations that
+       * would arrive from outside from dist_in of the inward neighbour(s); AB pattern only (:626-628) */
+      if ((cls == SLF_NT_COPY || cls == SLF_NT_YU_OUTFLOW) && orient != 0) {
+        const int *n = L->e[L->dir2vec[orient]];
+        const long long noff = n[0] + C->stride[1] * n[1] + C->stride[2] * n[2];
+        for (int i = 0; i < Q; i++) {
+          int sp = 0; for (int d = 0; d < D; d++) sp += L->e[i][d] * n[d];
+          if (sp <= 0) continue;
+          if (cls == SLF_NT_COPY) f[i] = din[gi + noff + DS * i];
+          else f[i] = (REAL)2.0 * din[gi + noff + DS * i] - din[gi + 2 * noff + DS * i];
+        }
+      }
       /* getMacro */
       const int standard = (cls == SLF_NT_FLUID || cls == SLF_NT_FULLBB_WALL || cls == SLF_NT_HALFBB_WALL ||
-                            cls == SLF_NT_DO_NOTHING);
+                            cls == SLF_NT_DO_NOTHING || cls == SLF_NT_COPY || cls == SLF_NT_YU_OUTFLOW);
       const int vel_bc = (cls == SLF_NT_EQUILIBRIUM_VELOCITY || cls == SLF_NT_REGULARIZED_VELOCITY ||
                           cls == SLF_NT_ZOUHE_VELOCITY);
       const int den_bc = (cls == SLF_NT_EQUILIBRIUM_DENSITY || cls == SLF_NT_REGULARIZED_DENSITY ||
@@ -589,7 +604,8 @@ int orc_collide_and_propagate(const SlfParams *P, const uint32_t *map, const REA
         }
       }
       /* relaxate */
-      const int wet = (cls == SLF_NT_FLUID || cls == SLF_NT_HALFBB_WALL || vel_bc || den_bc || cls == SLF_NT_DO_NOTHING);
+      const int wet = (cls == SLF_NT_FLUID || cls == SLF_NT_HALFBB_WALL || vel_bc || den_bc || cls == SLF_NT_DO_NOTHING ||
+                       cls == SLF_NT_COPY || cls == SLF_NT_YU_OUTFLOW);
       if (wet && P->relaxation_enabled) {
         if (P->model == SLF_MRT) mrt_relax(C, cls, f, v);
         else bgk_relax(C, rho, f, v);
@@ -1052,7 +1068,7 @@ static inline int is_wet(int cls) {
   return cls == SLF_NT_FLUID || cls == SLF_NT_HALFBB_WALL || cls == SLF_NT_EQUILIBRIUM_VELOCITY ||
          cls == SLF_NT_EQUILIBRIUM_DENSITY || cls == SLF_NT_REGULARIZED_VELOCITY ||
          cls == SLF_NT_REGULARIZED_DENSITY || cls == SLF_NT_DO_NOTHING || cls == SLF_NT_ZOUHE_VELOCITY ||
-         cls == SLF_NT_ZOUHE_DENSITY;
+         cls == SLF_NT_ZOUHE_DENSITY || cls == SLF_NT_COPY || cls == SLF_NT_YU_OUTFLOW;
 }
 
 int orc_sc_set_initial_conditions(const SlfParams *P, const uint32_t *map, REAL *d1, REAL *d2, const REAL *ivx,

@@ -117,7 +117,7 @@ class Lib(object):
             fn = getattr(self.cdll, name)
             fn.argtypes = argtypes
             fn.restype = restype
-        if self.cdll.slf_abi_version() != 5:
+        if self.cdll.slf_abi_version() != 6:
             raise B200Error('ABI version mismatch')
 
     def call(self, name, *args):

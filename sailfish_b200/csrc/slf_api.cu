@@ -145,6 +145,9 @@ int slf_plan_create(const SlfParams *p, SlfPlan **out) {
   if (p->model == SLF_MRT && p->lattice == SLF_D3Q27)
     return fail(SLF_EUNSUPPORTED, "D3Q27 has no MRT basis in the reference (sym.py:409-428)");
   if (p->access_pattern != SLF_AB && p->access_pattern != SLF_AA) return fail(SLF_EINVAL, "unknown access pattern");
+  if (p->access_pattern == SLF_AA &&
+      (p->type_id[SLF_NT_COPY] != SLF_NT_ABSENT || p->type_id[SLF_NT_YU_OUTFLOW] != SLF_NT_ABSENT))
+    return fail(SLF_EUNSUPPORTED, "NTCopy / NTYuOutflow nodes need the AB access pattern (boundary.mako:626-628)");
   if (p->lat_nx < 3 || p->lat_ny < 3 || p->arr_nx < p->lat_nx || p->arr_ny < p->lat_ny)
     return fail(SLF_EINVAL, "bad lattice/array size");
   if (p->bits_type < 1 || p->bits_type + p->bits_param + p->bits_scratch > 31)

@@ -334,6 +334,19 @@ boundary_node(const DevParams &P, const uint32_t *__restrict__ map, const float 
     for (int d = 1; d <= 2 * L::D; d++)
       if (orient == d) { n0 = L::ex(L::dir2vec(d)); n1 = L::ey(L::dir2vec(d)); n2 = L::ez(L::dir2vec(d)); }
   }
+  // fixMissingDistributions (boundary.mako:574-605): copy / extrapolation outflow nodes take the populations that
+  // would arrive from outside from dist_in of their inward neighbour(s).  AB only (boundary.mako:626-628; plan
+  // creation refuses these classes with the AA pattern).
+  if (!AA && (cls == SLF_NT_COPY || cls == SLF_NT_YU_OUTFLOW) && (n0 | n1 | n2) != 0) {
+    const long long nb = (long long)n0 + (long long)P.ax * n1 + (long long)P.ax * P.ay * n2;
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) {
+      if (edotn<L>(i, n0, n1, n2) > 0) {
+        const float a = din[gi + nb + P.DS * i];
+        f[i] = cls == SLF_NT_COPY ? a : 2.0f * a - din[gi + 2 * nb + P.DS * i];
+      }
+    }
+  }
   const bool vel_bc = cls == SLF_NT_EQUILIBRIUM_VELOCITY || cls == SLF_NT_REGULARIZED_VELOCITY ||
                       cls == SLF_NT_ZOUHE_VELOCITY;
   const bool den_bc = cls == SLF_NT_EQUILIBRIUM_DENSITY || cls == SLF_NT_REGULARIZED_DENSITY ||
@@ -430,7 +443,8 @@ boundary_node(const DevParams &P, const uint32_t *__restrict__ map, const float 
     }
   }
 
-  const bool wet = cls == SLF_NT_FLUID || cls == SLF_NT_HALFBB_WALL || vel_bc || den_bc || cls == SLF_NT_DO_NOTHING;
+  const bool wet = cls == SLF_NT_FLUID || cls == SLF_NT_HALFBB_WALL || vel_bc || den_bc || cls == SLF_NT_DO_NOTHING ||
+                   cls == SLF_NT_COPY || cls == SLF_NT_YU_OUTFLOW;
   if (wet && P.relax) {
     if (MODEL == SLF_MRT) {
       if (cls == SLF_NT_EQUILIBRIUM_VELOCITY || cls == SLF_NT_EQUILIBRIUM_DENSITY) collide_mrt<L, true>(P, v, f);
@@ -878,7 +892,7 @@ __device__ __forceinline__ bool is_wet_type(const DevParams &P, uint32_t type) {
          type == P.tid[SLF_NT_EQUILIBRIUM_VELOCITY] || type == P.tid[SLF_NT_EQUILIBRIUM_DENSITY] ||
          type == P.tid[SLF_NT_REGULARIZED_VELOCITY] || type == P.tid[SLF_NT_REGULARIZED_DENSITY] ||
          type == P.tid[SLF_NT_DO_NOTHING] || type == P.tid[SLF_NT_ZOUHE_VELOCITY] ||
-         type == P.tid[SLF_NT_ZOUHE_DENSITY];
+         type == P.tid[SLF_NT_ZOUHE_DENSITY] || type == P.tid[SLF_NT_COPY] || type == P.tid[SLF_NT_YU_OUTFLOW];
 }
 
 static __global__ void __launch_bounds__(256)

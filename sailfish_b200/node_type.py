@@ -47,6 +47,15 @@ class _NTUnused(LBNodeType):
     id = 22
 
 
+class NTCopy(LBNodeType):
+    """node_type.py:310-317: the populations that would arrive from outside are copied from the inward neighbour (a
+    crude vanishing-gradient outflow); AB access pattern only, as in the reference."""
+    wet_node = True
+    standard_macro = True
+    needs_orientation = True
+    id = 1
+
+
 class NTDoNothing(LBNodeType):
     """node_type.py:296-307."""
     wet_node = True
@@ -118,6 +127,15 @@ class NTRegularizedVelocity(LBNodeType):
         self.orientation = orientation
 
 
+class NTYuOutflow(LBNodeType):
+    """node_type.py:336-350: open boundary of Yu, Mei and Shyy, f_i(x) = 2 f_i(x - n) - f_i(x - 2n) for the
+    populations that would arrive from outside; AB access pattern only."""
+    wet_node = True
+    standard_macro = True
+    needs_orientation = True
+    id = 16
+
+
 class NTZouHeDensity(LBNodeType):
     """node_type.py:229-239: imposed density, bounce-back of the non-equilibrium parts + tangential momentum fix-up."""
     needs_orientation = True
@@ -141,7 +159,7 @@ class NTZouHeVelocity(LBNodeType):
 
 
 _NODE_TYPES = dict((c.id, c) for c in (
-    _NTFluid, _NTGhost, _NTPropagationOnly, _NTUnused, NTDoNothing, NTEquilibriumDensity,
+    _NTFluid, _NTGhost, _NTPropagationOnly, _NTUnused, NTCopy, NTYuOutflow, NTDoNothing, NTEquilibriumDensity,
     NTEquilibriumVelocity, NTFullBBWall, NTHalfBBWall, NTRegularizedDensity,
     NTRegularizedVelocity, NTZouHeDensity, NTZouHeVelocity))
 

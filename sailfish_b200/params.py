@@ -21,7 +21,8 @@ SC_POTENTIAL_IDS = {'linear': 0, 'classic': 1}
 NODE_CLASS_NAMES = (
     '_NTFluid', '_NTGhost', '_NTUnused', '_NTPropagationOnly', 'NTFullBBWall',
     'NTHalfBBWall', 'NTEquilibriumVelocity', 'NTEquilibriumDensity',
-    'NTRegularizedVelocity', 'NTRegularizedDensity', 'NTDoNothing', 'NTZouHeVelocity', 'NTZouHeDensity')
+    'NTRegularizedVelocity', 'NTRegularizedDensity', 'NTDoNothing', 'NTZouHeVelocity', 'NTZouHeDensity',
+    'NTCopy', 'NTYuOutflow')
 NT_COUNT = len(NODE_CLASS_NAMES)
 NT_ABSENT = 0xfffffffe
 
@@ -106,6 +107,9 @@ def make_params(lattice, model, access_pattern, lat_size, arr_size, periodic,
     if unknown:
         raise UnsupportedConfiguration(
             'node types outside the B200 hot path: %s' % ', '.join(sorted(unknown)))
+    if access_pattern == 'AA' and ('NTCopy' in type_ids or 'NTYuOutflow' in type_ids):
+        # the reference generates '#error ... not supported with the AA access_pattern' (boundary.mako:626-628)
+        raise UnsupportedConfiguration('NTCopy / NTYuOutflow nodes need --access_pattern=AB')
     p.use_link_tags = int(bool(use_link_tags))
     p.unused_tag_bits = int(unused_tag_bits) & 0x7fffffff
     p.relaxation_enabled = int(bool(relaxation_enabled))

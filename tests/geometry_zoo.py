@@ -4,6 +4,9 @@ Subdomain.reset() + encoding.  The scenarios follow the reference's tests/subdom
 duct, channels with periodic directions, link tagging) and add the node types the examples do not use."""
 import numpy as np
 
+# set-ups whose node types the reference only generates code for in the AB access pattern (boundary.mako:626-628)
+AB_ONLY = ('copy_channel2d', 'yu_channel2d', 'copy_duct3d', 'yu_duct3d_mrt', 'copy_duct3d_q27')
+
 
 def make_cases(ns):
     """ns: namespace with Subdomain2D, Subdomain3D, LBFluidSim, LBForcedSim and the NT* node types."""
@@ -13,6 +16,7 @@ def make_cases(ns):
     NTRegularizedVelocity, NTRegularizedDensity = ns['NTRegularizedVelocity'], ns['NTRegularizedDensity']
     NTDoNothing = ns['NTDoNothing']
     NTZouHeVelocity, NTZouHeDensity = ns['NTZouHeVelocity'], ns['NTZouHeDensity']
+    NTCopy, NTYuOutflow = ns['NTCopy'], ns['NTYuOutflow']
 
     def sim(sub, **defaults):
         class _Sim(Sim):
@@ -110,7 +114,47 @@ def make_cases(ns):
         def initial_conditions(self, sim, hx, hy, hz):
             sim.rho[:] = 1.0 + 0.01 * (self.gx / 2.0 - hx) / self.gx
 
+    def outflow_channel2d(outlet):
+        class OutflowChannel2D(S2):
+            """Equilibrium-velocity inlet, copy / extrapolation outlet (AB pattern only), full-way walls, a step."""
+            def boundary_conditions(self, hx, hy):
+                wall = (hy == 0) | (hy == self.gy - 1) | ((hx >= 6) & (hx <= 8) & (hy <= 3))
+                self.set_node(wall, NTFullBBWall)
+                self.set_node((hx == 0) & np.logical_not(wall), NTEquilibriumVelocity((0.03, 0.0)))
+                self.set_node((hx == self.gx - 1) & np.logical_not(wall), outlet)
+
+            def initial_conditions(self, sim, hx, hy):
+                sim.rho[:] = 1.0 + 0.002 * np.cos(0.5 * hx)
+                sim.vx[:] = 0.03 * np.sin(np.pi * hy / (self.gy - 1))
+        return OutflowChannel2D
+
+    def outflow_duct3d(outlet):
+        class OutflowDuct3D(S3):
+            """Regularised-velocity inlet at x = 0, copy / extrapolation outlet at the far x end and on the z = top
+            plane (two outlet orientations), full-way walls elsewhere."""
+            def boundary_conditions(self, hx, hy, hz):
+                wall = (hy == 0) | (hy == self.gy - 1) | (hz == 0)
+                wall |= (hz == self.gz - 1) & ((hx == 0) | (hx == self.gx - 1))
+                top = (hz == self.gz - 1) & np.logical_not(wall)
+                self.set_node(wall, NTFullBBWall)
+                self.set_node(top, outlet)
+                free = np.logical_not(wall | top)
+                self.set_node((hx == 0) & free, NTRegularizedVelocity((0.02, 0.0, 0.0)))
+                self.set_node((hx == self.gx - 1) & free, outlet)
+
+            def initial_conditions(self, sim, hx, hy, hz):
+                sim.rho[:] = 1.0 + 0.003 * np.sin(0.6 * hx) * np.cos(0.4 * hy)
+                sim.vx[:] = 0.02
+                sim.vz[:] = 0.004 * np.sin(0.5 * hx)
+        return OutflowDuct3D
+
     return {
+        'copy_channel2d': (sim(outflow_channel2d(NTCopy), lat_nx=18, lat_ny=11, grid='D2Q9'), []),
+        'yu_channel2d': (sim(outflow_channel2d(NTYuOutflow), lat_nx=18, lat_ny=11, grid='D2Q9'), []),
+        'copy_duct3d': (sim(outflow_duct3d(NTCopy), lat_nx=12, lat_ny=9, lat_nz=8, grid='D3Q19'), []),
+        'yu_duct3d_mrt': (sim(outflow_duct3d(NTYuOutflow), lat_nx=12, lat_ny=9, lat_nz=8, grid='D3Q19'),
+                          ['--model=mrt']),
+        'copy_duct3d_q27': (sim(outflow_duct3d(NTCopy), lat_nx=12, lat_ny=9, lat_nz=8, grid='D3Q27'), []),
         'zouhe_channel2d': (sim(ZouHeChannel2D, lat_nx=20, lat_ny=12, grid='D2Q9'), []),
         'zouhe_box3d': (sim(ZouHeBox3D, lat_nx=12, lat_ny=10, lat_nz=9, grid='D3Q19'), []),
         'zouhe_box3d_mrt': (sim(ZouHeBox3D, lat_nx=12, lat_ny=10, lat_nz=9, grid='D3Q19'), ['--model=mrt']),

@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol(library):
 
 
 def test_abi_version_and_struct_size(library):
-    assert library.slf_abi_version() == 5
+    assert library.slf_abi_version() == 6
     # sizeof(SlfParams) as the C compiler sees it
     prog = '#include <stdio.h>\n#include "%s"\nint main(){printf("%%zu", sizeof(SlfParams));return 0;}' % HEADER
     exe = os.path.join(util.ROOT, 'tests', '.sizeof_params')

@@ -354,6 +354,8 @@ def gen_zoo_steps():
             # them only the AB run is used as a pin
             if name == 'duct3d_notags' or (name == 'duct3d' and ap == 'AA'):
                 continue
+            if ap == 'AA' and name in geometry_zoo.AB_ONLY:
+                continue
             cases.append(('zoo_%s_%s' % (name, ap), cls, geo, args + ['--access_pattern=' + ap, '--visc=0.06'], 10))
     main(['steps'], cases)
 
@@ -368,6 +370,8 @@ if __name__ == '__main__':
         gen_shan_chen()
     if 'zoo' in what:
         gen_geometry_zoo()
+        gen_zoo_steps()
+    if 'zoo_steps' in what:
         gen_zoo_steps()
     if 'sc_gravity' in what:
         gen_shan_chen(only='gravity')

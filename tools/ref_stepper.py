@@ -175,6 +175,22 @@ class RefStepper(object):
 
         def m(c):
             return self.is_cls(c)[idx]
+        # fixMissingDistributions (boundary.mako:509-630): copy / extrapolation outflow nodes take the populations
+        # that would come from outside from their inward neighbours' dist_in (AB only, :626-628)
+        for c, two in ((nt.NTCopy, False), (nt.NTYuOutflow, True)):
+            if c not in self.ctx['node_types']:
+                continue
+            assert not self.aa, 'NTCopy / NTYuOutflow are not supported with the AA access pattern'
+            sc = m(c)
+            for o in range(1, 2 * D + 1):
+                s = sc & (ori == o)
+                if not s.any():
+                    continue
+                nvec = [int(x) for x in g.dir_to_vec(o)]
+                nb1 = tuple(idx[k][s] + nvec[D - 1 - k] for k in range(D))
+                nb2 = tuple(idx[k][s] + 2 * nvec[D - 1 - k] for k in range(D))
+                for i in self.missing[o]:
+                    f[i, s] = 2.0 * din[i][nb1] - din[i][nb2] if two else din[i][nb1]
         zh_v, zh_d = m(nt.NTZouHeVelocity), m(nt.NTZouHeDensity)
         vel_bc = m(nt.NTEquilibriumVelocity) | m(nt.NTRegularizedVelocity) | zh_v
         den_bc = m(nt.NTEquilibriumDensity) | m(nt.NTRegularizedDensity) | zh_d
