@@ -72,6 +72,7 @@ enum {
   SLF_NT_ZOUHE_DENSITY,         /* :229 NTZouHeDensity                    */
   SLF_NT_COPY,                  /* :310 NTCopy (AB access pattern only)   */
   SLF_NT_YU_OUTFLOW,            /* :336 NTYuOutflow (AB only)             */
+  SLF_NT_WALL_TMS,              /* :171 NTWallTMS                         */
   SLF_NT_COUNT
 };
 #define SLF_NT_ABSENT 0xfffffffeu   /* geo_encoder.py:44-50 */

@@ -258,6 +258,24 @@ static inline void fill_missing_with_opposite(const Lat *L, int orient, REAL *f)
   }
 }
 
+/* for_orientation_dist(link_tags=True), boundary.mako:391-416, for link i = 1..Q-1 of a node with orientation /
+ * tag word `orient`: is a population of this link undefined, and which (missing) is replaced from which (name)? */
+static inline int missing_link(const Ctx *C, int orient, int i, int *missing, int *name) {
+  const Lat *L = C->L; const SlfParams *P = C->P;
+  if (P->use_link_tags) {
+    if (orient & (1 << (i - 1))) return 0;               /* link i points to a fluid node */
+    if (P->unused_tag_bits & (1 << (i - 1))) return 0;   /* no code is generated for this bit, boundary.mako:396 */
+    *name = i; *missing = L->opp[i];
+    return 1;
+  }
+  if (orient == 0) return 0;
+  const int *n = L->e[L->dir2vec[orient]];
+  int sp = 0; for (int d = 0; d < L->D; d++) sp += L->e[i][d] * n[d];
+  if (sp <= 0) return 0;
+  *missing = i; *name = L->opp[i];
+  return 1;
+}
+
 static inline void bounce_back(const Lat *L, REAL *f) {   /* boundary.mako:255-264 */
   for (int i = 0; i < L->Q; i++) { int j = L->opp[i]; if (i < j) { REAL t = f[i]; f[i] = f[j]; f[j] = t; } }
 }
@@ -529,9 +547,24 @@ int orc_collide_and_propagate(const SlfParams *P, const uint32_t *map, const REA
           else f[i] = (REAL)2.0 * din[gi + noff + DS * i] - din[gi + 2 * noff + DS * i];
         }
       }
+      /* NTWallTMS, boundary.mako:631-648: target moments from the populations as loaded (the slots of the links into
+       * the wall hold the values bounced back at the end of the previous step); those populations are then replaced
+       * by the equilibrium at the target moments */
+      REAL tg_rho = 0, tg_v[3] = {0, 0, 0};
+      if (cls == SLF_NT_WALL_TMS) {
+        for (int i = 0; i < Q; i++) tg_rho += f[i];
+        for (int d = 0; d < D; d++) { REAL s = 0; for (int i = 0; i < Q; i++) s += (REAL)L->e[i][d] * f[i]; tg_v[d] = s / tg_rho; }
+        REAL feq[MAXQ]; feq_all(L, tg_rho, tg_v, feq);
+        for (int i = 1; i < Q; i++) {
+          int missing, name;
+          if (!missing_link(C, orient, i, &missing, &name)) continue;
+          f[missing] = feq[missing];
+        }
+      }
       /* getMacro */
       const int standard = (cls == SLF_NT_FLUID || cls == SLF_NT_FULLBB_WALL || cls == SLF_NT_HALFBB_WALL ||
-                            cls == SLF_NT_DO_NOTHING || cls == SLF_NT_COPY || cls == SLF_NT_YU_OUTFLOW);
+                            cls == SLF_NT_DO_NOTHING || cls == SLF_NT_COPY || cls == SLF_NT_YU_OUTFLOW ||
+                            cls == SLF_NT_WALL_TMS);
       const int vel_bc = (cls == SLF_NT_EQUILIBRIUM_VELOCITY || cls == SLF_NT_REGULARIZED_VELOCITY ||
                           cls == SLF_NT_ZOUHE_VELOCITY);
       const int den_bc = (cls == SLF_NT_EQUILIBRIUM_DENSITY || cls == SLF_NT_REGULARIZED_DENSITY ||
@@ -605,27 +638,26 @@ int orc_collide_and_propagate(const SlfParams *P, const uint32_t *map, const REA
       }
       /* relaxate */
       const int wet = (cls == SLF_NT_FLUID || cls == SLF_NT_HALFBB_WALL || vel_bc || den_bc || cls == SLF_NT_DO_NOTHING ||
-                       cls == SLF_NT_COPY || cls == SLF_NT_YU_OUTFLOW);
+                       cls == SLF_NT_COPY || cls == SLF_NT_YU_OUTFLOW || cls == SLF_NT_WALL_TMS);
       if (wet && P->relaxation_enabled) {
         if (P->model == SLF_MRT) mrt_relax(C, cls, f, v);
         else bgk_relax(C, rho, f, v);
       }
-      /* postcollisionBoundaryConditions: half-way bounce-back, boundary.mako:653-683 */
-      if (cls == SLF_NT_HALFBB_WALL) {
+      /* postcollisionBoundaryConditions: TMS adds f^eq(target) - f^eq(instantaneous), boundary.mako:696-722 */
+      if (cls == SLF_NT_WALL_TMS) {
+        REAL feq[MAXQ];
+        feq_all(L, tg_rho, tg_v, feq);
+        for (int i = 0; i < Q; i++) f[i] += feq[i];
+        feq_all(L, rho, v, feq);
+        for (int i = 0; i < Q; i++) f[i] -= feq[i];
+      }
+      /* half-way bounce-back and TMS: the populations of the links into the wall are stored where the next step
+       * reads the ones coming out of it, boundary.mako:653-668 */
+      if (cls == SLF_NT_HALFBB_WALL || cls == SLF_NT_WALL_TMS) {
         for (int i = 1; i < Q; i++) {
           int missing;   /* slot whose data is undefined; f[name] is written into it */
           int name;
-          if (P->use_link_tags) {
-            if (orient & (1 << (i - 1))) continue;   /* link i points to a fluid node */
-            if (P->unused_tag_bits & (1 << (i - 1))) continue;   /* no code is generated for this bit, boundary.mako:396 */
-            name = i; missing = L->opp[i];
-          } else {
-            if (orient == 0) break;
-            const int *n = L->e[L->dir2vec[orient]];
-            int sp = 0; for (int d = 0; d < D; d++) sp += L->e[i][d] * n[d];
-            if (sp <= 0) continue;
-            missing = i; name = L->opp[i];
-          }
+          if (!missing_link(C, orient, i, &missing, &name)) continue;
           if (!aa || odd) dout[gi + DS * missing] = f[name];
           else dout[gi + off[L->opp[missing]] + DS * L->opp[missing]] = f[name];
         }
@@ -1068,7 +1100,7 @@ static inline int is_wet(int cls) {
   return cls == SLF_NT_FLUID || cls == SLF_NT_HALFBB_WALL || cls == SLF_NT_EQUILIBRIUM_VELOCITY ||
          cls == SLF_NT_EQUILIBRIUM_DENSITY || cls == SLF_NT_REGULARIZED_VELOCITY ||
          cls == SLF_NT_REGULARIZED_DENSITY || cls == SLF_NT_DO_NOTHING || cls == SLF_NT_ZOUHE_VELOCITY ||
-         cls == SLF_NT_ZOUHE_DENSITY || cls == SLF_NT_COPY || cls == SLF_NT_YU_OUTFLOW;
+         cls == SLF_NT_ZOUHE_DENSITY || cls == SLF_NT_COPY || cls == SLF_NT_YU_OUTFLOW || cls == SLF_NT_WALL_TMS;
 }
 
 int orc_sc_set_initial_conditions(const SlfParams *P, const uint32_t *map, REAL *d1, REAL *d2, const REAL *ivx,

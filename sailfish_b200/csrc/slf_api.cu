@@ -534,7 +534,7 @@ int slf_run_steps(SlfPlan *pl, uint64_t map, uint64_t dist_a, uint64_t dist_b, u
   cudaStream_t s = (cudaStream_t)stream;
   // Small lattices without periodic axes: all steps in one cooperative launch (grid barrier between steps).
   if (pl->hp.access_pattern == SLF_AA && nsteps >= 2 && s != 0 && !pl->hp.periodic[0] && !pl->hp.periodic[1] &&
-      !pl->hp.periodic[2] && !getenv("SLF_NO_MULTISTEP")) {
+      !pl->hp.periodic[2] && pl->hp.type_id[SLF_NT_WALL_TMS] == SLF_NT_ABSENT && !getenv("SLF_NO_MULTISTEP")) {
     const uint32_t *m = (const uint32_t *)map;
     float *d = (float *)dist_a, *r = (float *)rho, *x = (float *)vx, *y = (float *)vy, *z = (float *)vz;
     int left = nsteps;

@@ -305,7 +305,9 @@ __device__ __forceinline__ void zouhe_bb(int n0, int n1, int n2, float rho, cons
 
 // One node of the generic path (every node class, run-time normals); `skip_fluid`: the caller scans a node
 // range in which plain fluid nodes belong to the bulk kernel.
-template <class L, int MODEL, int MODE, bool SAVE, int HINT = 0>
+// WITH_TMS = false compiles the NTWallTMS branches out (the multi-step kernel, whose launch is refused for lattices
+// with such nodes, stays within its register budget).
+template <class L, int MODEL, int MODE, bool SAVE, int HINT = 0, bool WITH_TMS = true>
 __device__ __forceinline__ void
 boundary_node(const DevParams &P, const uint32_t *__restrict__ map, const float *din, float *dout,
               float *__restrict__ orho, float *__restrict__ ovx, float *__restrict__ ovy,
@@ -328,7 +330,9 @@ boundary_node(const DevParams &P, const uint32_t *__restrict__ map, const float 
 
   // inward normal of the node (primary orientation); zero when unknown
   int n0 = 0, n1 = 0, n2 = 0;
-  const bool tagged = (cls == SLF_NT_HALFBB_WALL) && P.use_tags;
+  const bool is_tms = WITH_TMS && cls == SLF_NT_WALL_TMS;
+  const bool link_bounce = cls == SLF_NT_HALFBB_WALL || is_tms;      // boundary.mako:653-668
+  const bool tagged = link_bounce && P.use_tags;
   if (orient > 0 && orient <= 2 * L::D && !tagged) {
 #pragma unroll
     for (int d = 1; d <= 2 * L::D; d++)
@@ -344,6 +348,25 @@ boundary_node(const DevParams &P, const uint32_t *__restrict__ map, const float 
       if (edotn<L>(i, n0, n1, n2) > 0) {
         const float a = din[gi + nb + P.DS * i];
         f[i] = cls == SLF_NT_COPY ? a : 2.0f * a - din[gi + 2 * nb + P.DS * i];
+      }
+    }
+  }
+  // NTWallTMS (boundary.mako:631-648): target moments from the populations as loaded -- the slots of the links into
+  // the wall hold what was bounced back at the end of the previous step -- then those populations are replaced by
+  // the equilibrium at the target moments.
+  float tg_rho = 0.f, tg_v[3] = {0.f, 0.f, 0.f};
+  if (is_tms) {
+    moments<L>(f, tg_rho, tg_v);
+    tg_v[0] /= tg_rho; tg_v[1] /= tg_rho; tg_v[2] /= tg_rho;
+    float feq[L::Q];
+    equilibrium<L>(tg_rho, tg_v, feq);
+#pragma unroll
+    for (int i = 1; i < L::Q; i++) {
+      // link i -> (missing, name) as in the store loop below; only `missing` matters here
+      if (P.use_tags) {
+        if ((orient & (1 << (i - 1))) == 0 && (P.unused_tags & (1u << (i - 1))) == 0) f[L::opp(i)] = feq[L::opp(i)];
+      } else if (orient != 0 && edotn<L>(i, n0, n1, n2) > 0) {
+        f[i] = feq[i];
       }
     }
   }
@@ -443,7 +466,7 @@ boundary_node(const DevParams &P, const uint32_t *__restrict__ map, const float 
     }
   }
 
-  const bool wet = cls == SLF_NT_FLUID || cls == SLF_NT_HALFBB_WALL || vel_bc || den_bc || cls == SLF_NT_DO_NOTHING ||
+  const bool wet = cls == SLF_NT_FLUID || link_bounce || vel_bc || den_bc || cls == SLF_NT_DO_NOTHING ||
                    cls == SLF_NT_COPY || cls == SLF_NT_YU_OUTFLOW;
   if (wet && P.relax) {
     if (MODEL == SLF_MRT) {
@@ -454,7 +477,17 @@ boundary_node(const DevParams &P, const uint32_t *__restrict__ map, const float 
     }
   }
 
-  if (cls == SLF_NT_HALFBB_WALL) {            // boundary.mako:653-683
+  if (is_tms) {                               // boundary.mako:696-722: + f^eq(target) - f^eq(instantaneous)
+    float feq[L::Q];
+    equilibrium<L>(tg_rho, tg_v, feq);
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) f[i] += feq[i];
+    equilibrium<L>(rho, v, feq);
+#pragma unroll
+    for (int i = 0; i < L::Q; i++) f[i] -= feq[i];
+  }
+
+  if (link_bounce) {                          // boundary.mako:653-683
 #pragma unroll
     for (int i = 1; i < L::Q; i++) {
       bool hit; int missing, name;
@@ -575,11 +608,11 @@ collide_multistep(const DevParams P, const SlotTable<L> Te, const SlotTable<L> T
       }
     } else if (other) {
       if (save) {
-        if (odd) boundary_node<L, MODEL, MODE_AA_ODD, true, 2>(P, map, dist, dist, orho, ovx, ovy, ovz, gi, false);
-        else boundary_node<L, MODEL, MODE_AA_EVEN, true, 2>(P, map, dist, dist, orho, ovx, ovy, ovz, gi, false);
+        if (odd) boundary_node<L, MODEL, MODE_AA_ODD, true, 2, false>(P, map, dist, dist, orho, ovx, ovy, ovz, gi, false);
+        else boundary_node<L, MODEL, MODE_AA_EVEN, true, 2, false>(P, map, dist, dist, orho, ovx, ovy, ovz, gi, false);
       } else {
-        if (odd) boundary_node<L, MODEL, MODE_AA_ODD, false, 2>(P, map, dist, dist, orho, ovx, ovy, ovz, gi, false);
-        else boundary_node<L, MODEL, MODE_AA_EVEN, false, 2>(P, map, dist, dist, orho, ovx, ovy, ovz, gi, false);
+        if (odd) boundary_node<L, MODEL, MODE_AA_ODD, false, 2, false>(P, map, dist, dist, orho, ovx, ovy, ovz, gi, false);
+        else boundary_node<L, MODEL, MODE_AA_EVEN, false, 2, false>(P, map, dist, dist, orho, ovx, ovy, ovz, gi, false);
       }
     }
     if (s + 1 < nsteps) {
@@ -892,7 +925,8 @@ __device__ __forceinline__ bool is_wet_type(const DevParams &P, uint32_t type) {
          type == P.tid[SLF_NT_EQUILIBRIUM_VELOCITY] || type == P.tid[SLF_NT_EQUILIBRIUM_DENSITY] ||
          type == P.tid[SLF_NT_REGULARIZED_VELOCITY] || type == P.tid[SLF_NT_REGULARIZED_DENSITY] ||
          type == P.tid[SLF_NT_DO_NOTHING] || type == P.tid[SLF_NT_ZOUHE_VELOCITY] ||
-         type == P.tid[SLF_NT_ZOUHE_DENSITY] || type == P.tid[SLF_NT_COPY] || type == P.tid[SLF_NT_YU_OUTFLOW];
+         type == P.tid[SLF_NT_ZOUHE_DENSITY] || type == P.tid[SLF_NT_COPY] || type == P.tid[SLF_NT_YU_OUTFLOW] ||
+         type == P.tid[SLF_NT_WALL_TMS];
 }
 
 static __global__ void __launch_bounds__(256)

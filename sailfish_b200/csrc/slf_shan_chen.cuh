@@ -328,7 +328,8 @@ sc_set_initial_conditions(const DevParams P, const uint32_t *__restrict__ map, f
   const bool wet = cls == SLF_NT_FLUID || cls == SLF_NT_HALFBB_WALL || cls == SLF_NT_EQUILIBRIUM_VELOCITY ||
                    cls == SLF_NT_EQUILIBRIUM_DENSITY || cls == SLF_NT_REGULARIZED_VELOCITY ||
                    cls == SLF_NT_REGULARIZED_DENSITY || cls == SLF_NT_DO_NOTHING || cls == SLF_NT_ZOUHE_VELOCITY ||
-                   cls == SLF_NT_ZOUHE_DENSITY || cls == SLF_NT_COPY || cls == SLF_NT_YU_OUTFLOW;
+                   cls == SLF_NT_ZOUHE_DENSITY || cls == SLF_NT_COPY || cls == SLF_NT_YU_OUTFLOW ||
+                   cls == SLF_NT_WALL_TMS;
   if (!wet && cls != SLF_NT_FULLBB_WALL) {
 #pragma unroll
     for (int i = 0; i < L::Q; i++) { d1[gi + P.DS * i] = INFINITY; d2[gi + P.DS * i] = INFINITY; }

@@ -127,6 +127,19 @@ class NTRegularizedVelocity(LBNodeType):
         self.orientation = orientation
 
 
+class NTWallTMS(LBNodeType):
+    """node_type.py:171-192: wall for turbulent flows after Chikatamarla and Karlin (Tamm-Mott-Smith approximation):
+    the populations coming out of the wall are the equilibrium at target moments (those of the bounced-back state),
+    and f^eq(target) - f^eq(instantaneous) is added after the collision."""
+    wet_node = True
+    needs_orientation = True
+    link_tags = True
+    location = 0.5
+    allow_unused = True
+    standard_macro = True
+    id = 15
+
+
 class NTYuOutflow(LBNodeType):
     """node_type.py:336-350: open boundary of Yu, Mei and Shyy, f_i(x) = 2 f_i(x - n) - f_i(x - 2n) for the
     populations that would arrive from outside; AB access pattern only."""
@@ -159,7 +172,7 @@ class NTZouHeVelocity(LBNodeType):
 
 
 _NODE_TYPES = dict((c.id, c) for c in (
-    _NTFluid, _NTGhost, _NTPropagationOnly, _NTUnused, NTCopy, NTYuOutflow, NTDoNothing, NTEquilibriumDensity,
+    _NTFluid, _NTGhost, _NTPropagationOnly, _NTUnused, NTCopy, NTYuOutflow, NTWallTMS, NTDoNothing, NTEquilibriumDensity,
     NTEquilibriumVelocity, NTFullBBWall, NTHalfBBWall, NTRegularizedDensity,
     NTRegularizedVelocity, NTZouHeDensity, NTZouHeVelocity))
 

@@ -245,7 +245,7 @@ class FakeLib(object):
         types = (self._arr(m, np.uint32, p.dist_size).reshape(shape)[real]) & ((1 << p.bits_type) - 1)
         wet_ids = [p.type_id[P.NODE_CLASS_NAMES.index(n)] for n in (
             '_NTFluid', 'NTHalfBBWall', 'NTEquilibriumVelocity', 'NTEquilibriumDensity', 'NTRegularizedVelocity',
-            'NTRegularizedDensity', 'NTDoNothing', 'NTZouHeVelocity', 'NTZouHeDensity', 'NTCopy', 'NTYuOutflow')]
+            'NTRegularizedDensity', 'NTDoNothing', 'NTZouHeVelocity', 'NTZouHeDensity', 'NTCopy', 'NTYuOutflow', 'NTWallTMS')]
         dense = np.where(np.isin(types, wet_ids), f, np.float32(np.nan)).astype(np.float32)
         self._arr(out, np.float32, dense.size)[:] = dense.reshape(-1)
         self.launches += 1

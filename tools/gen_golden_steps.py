@@ -352,9 +352,11 @@ def gen_zoo_steps():
             # half-way walls on the outermost layer (no unused layer behind them) are the configuration the
             # reference warns about; without link tags even its AA == AB invariant does not hold there, and with
             # them only the AB run is used as a pin
-            if name == 'duct3d_notags' or (name == 'duct3d' and ap == 'AA'):
+            # without link tags a wall node's bounced populations and its wall neighbours' propagated ones target the
+            # same slots (a write race in the reference's kernel): geometry goldens only
+            if name in ('duct3d_notags', 'tms_channel2d_notags'):
                 continue
-            if ap == 'AA' and name in geometry_zoo.AB_ONLY:
+            if ap == 'AA' and (name in geometry_zoo.AB_ONLY or name in geometry_zoo.AB_PINNED_ONLY):
                 continue
             cases.append(('zoo_%s_%s' % (name, ap), cls, geo, args + ['--access_pattern=' + ap, '--visc=0.06'], 10))
     main(['steps'], cases)

@@ -191,6 +191,20 @@ class RefStepper(object):
                 nb2 = tuple(idx[k][s] + 2 * nvec[D - 1 - k] for k in range(D))
                 for i in self.missing[o]:
                     f[i, s] = 2.0 * din[i][nb1] - din[i][nb2] if two else din[i][nb1]
+        # NTWallTMS (boundary.mako:631-648): target moments from the populations as loaded (the slots of the links
+        # that point into the wall hold the bounced-back values written at the end of the previous step), then
+        # those populations are replaced by the equilibrium at the target moments
+        tms = m(nt.NTWallTMS)
+        tg_rho = tg_v = None
+        if tms.any():
+            with np.errstate(all='ignore'):
+                tg_rho = np.zeros(N)
+                tg_v = np.zeros((D, N))
+                tg_rho[tms] = self.rho_std(*f[:, tms])
+                for d in range(D):
+                    tg_v[d, tms] = self.mom[d](*f[:, tms]) / tg_rho[tms]
+                for sel, missing, _ in self._missing_links(ori, tms):
+                    f[missing, sel] = self.feq[missing](tg_rho[sel], *tg_v[:, sel])
         zh_v, zh_d = m(nt.NTZouHeVelocity), m(nt.NTZouHeDensity)
         vel_bc = m(nt.NTEquilibriumVelocity) | m(nt.NTRegularizedVelocity) | zh_v
         den_bc = m(nt.NTEquilibriumDensity) | m(nt.NTRegularizedDensity) | zh_d
@@ -303,6 +317,13 @@ class RefStepper(object):
             # postcollision: half-way bounce-back (boundary.mako:653-683)
             if nt.NTHalfBBWall in self.ctx['node_types']:
                 self._halfbb(f, dout, idx, ori, m(nt.NTHalfBBWall), odd)
+            if tms.any():
+                # boundary.mako:696-722: add f^eq(target) - f^eq(instantaneous), then store like half-way bounce-back
+                for i in range(Q):
+                    f[i, tms] += self.feq[i](tg_rho[tms], *tg_v[:, tms])
+                for i in range(Q):
+                    f[i, tms] -= self.feq[i](rho[tms], *v[:, tms])
+                self._halfbb(f, dout, idx, ori, tms, odd)
         # save_macro_fields (kernel_common.mako:213-240)
         if save_macro:
             sub = tuple(a[wet] for a in idx)
@@ -388,26 +409,31 @@ class RefStepper(object):
         if self.accel is not None:
             v[:, s] += 0.5 * self.accel[:, None]
 
-    def _halfbb(self, f, dout, idx, ori, s, odd):
+    def _missing_links(self, ori, s):
+        """for_orientation_dist(link_tags=True), boundary.mako:391-416: yields (node selection, missing_idx,
+        opposite idx) over the nodes selected by `s`."""
         g, D = self.grid, self.D
+        if self.ctx.get('use_link_tags', True):
+            unused = int(self.ctx.get('unused_tag_bits', 0))
+            for k in range(1, self.Q):
+                if unused & (1 << (k - 1)):
+                    continue
+                sel = s & ((ori & (1 << (k - 1))) == 0)
+                if sel.any():
+                    yield sel, g.idx_opposite[k], k
+        else:
+            for on in range(1, 2 * D + 1):
+                sel = s & (ori == on)
+                if sel.any():
+                    for k in self.missing[on]:
+                        yield sel, k, g.idx_opposite[k]
+
+    def _halfbb(self, f, dout, idx, ori, s, odd):
+        """_global_mem_fill_missing_dists_with_opposites, boundary.mako:653-668."""
         if not s.any():
             return
-        sub = tuple(a[s] for a in idx)
-        o = ori[s]
-        for k in range(1, self.Q):
-            if self.ctx.get('use_link_tags', True):
-                sel = (o & (1 << (k - 1))) == 0
-                name, missing = k, g.idx_opposite[k]
-                if not sel.any():
-                    continue
-                self._hbb_write(f[name, s][sel], dout, tuple(a[sel] for a in sub), missing, odd)
-            else:
-                for on in range(1, 2 * D + 1):
-                    if k in self.missing[on]:
-                        sel = (o == on)
-                        if sel.any():
-                            self._hbb_write(f[g.idx_opposite[k], s][sel], dout,
-                                            tuple(a[sel] for a in sub), k, odd)
+        for sel, missing, name in self._missing_links(ori, s):
+            self._hbb_write(f[name, sel], dout, tuple(a[sel] for a in idx), missing, odd)
 
     def _hbb_write(self, vals, dout, sub, missing, odd):
         g, D = self.grid, self.D
