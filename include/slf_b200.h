@@ -73,6 +73,7 @@ enum {
   SLF_NT_COPY,                  /* :310 NTCopy (AB access pattern only)   */
   SLF_NT_YU_OUTFLOW,            /* :336 NTYuOutflow (AB only)             */
   SLF_NT_WALL_TMS,              /* :171 NTWallTMS                         */
+  SLF_NT_SLIP,                  /* :402 NTSlip (orientation from the user) */
   SLF_NT_COUNT
 };
 #define SLF_NT_ABSENT 0xfffffffeu   /* geo_encoder.py:44-50 */

@@ -564,7 +564,7 @@ int orc_collide_and_propagate(const SlfParams *P, const uint32_t *map, const REA
       /* getMacro */
       const int standard = (cls == SLF_NT_FLUID || cls == SLF_NT_FULLBB_WALL || cls == SLF_NT_HALFBB_WALL ||
                             cls == SLF_NT_DO_NOTHING || cls == SLF_NT_COPY || cls == SLF_NT_YU_OUTFLOW ||
-                            cls == SLF_NT_WALL_TMS);
+                            cls == SLF_NT_WALL_TMS || cls == SLF_NT_SLIP);
       const int vel_bc = (cls == SLF_NT_EQUILIBRIUM_VELOCITY || cls == SLF_NT_REGULARIZED_VELOCITY ||
                           cls == SLF_NT_ZOUHE_VELOCITY);
       const int den_bc = (cls == SLF_NT_EQUILIBRIUM_DENSITY || cls == SLF_NT_REGULARIZED_DENSITY ||
@@ -597,6 +597,21 @@ int orc_collide_and_propagate(const SlfParams *P, const uint32_t *map, const REA
       /* precollisionBoundaryConditions */
       if (cls == SLF_NT_FULLBB_WALL) {
         bounce_back(L, f);
+      } else if (cls == SLF_NT_SLIP) {                                  /* boundary.mako:837-856, sym.py:481-497 */
+        if (orient != 0) {
+          const int *n = L->e[L->dir2vec[orient]];
+          for (int i = 0; i < Q; i++) {
+            int sp = 0; for (int d = 0; d < D; d++) sp += L->e[i][d] * n[d];
+            if (sp <= 0) continue;
+            int r[3] = {0, 0, 0};                                       /* e_i with its normal components reversed */
+            for (int d = 0; d < D; d++) r[d] = n[d] != 0 ? -L->e[i][d] : L->e[i][d];
+            for (int j = 0; j < Q; j++)
+              if (L->e[j][0] == r[0] && L->e[j][1] == r[1] && L->e[j][2] == r[2]) {
+                REAL t = f[i]; f[i] = f[j]; f[j] = t;
+                break;
+              }
+          }
+        }
       } else if (cls == SLF_NT_ZOUHE_VELOCITY) {                        /* boundary.mako:812-816 */
         if (orient == 0) bounce_back(L, f); else zouhe_bb(L, orient, rho, v, f);
       } else if (cls == SLF_NT_EQUILIBRIUM_VELOCITY || cls == SLF_NT_EQUILIBRIUM_DENSITY) {

@@ -254,6 +254,9 @@ static inline SlotTable<L> make_aa_table(const DevParams &P, float *dist, long l
 // Boundary kernel: all active non-fluid nodes.
 // ----------------------------------------------------------------------------------------
 template <class L>
+SLF_HD constexpr int axis_comp(int i, int a) { return a == 0 ? L::ex(i) : (a == 1 ? L::ey(i) : L::ez(i)); }
+
+template <class L>
 __device__ __forceinline__ int edotn(int i, int n0, int n1, int n2) {
   return L::ex(i) * n0 + L::ey(i) * n1 + L::ez(i) * n2;
 }
@@ -411,6 +414,20 @@ boundary_node(const DevParams &P, const uint32_t *__restrict__ map, const float 
 #pragma unroll
     for (int i = 0; i < L::Q; i++)
       if (i < L::opp(i)) { const float tmp = f[i]; f[i] = f[L::opp(i)]; f[L::opp(i)] = tmp; }
+  } else if (cls == SLF_NT_SLIP) {                // boundary.mako:837-856: specular reflection (sym.py:481-497)
+#pragma unroll
+    for (int a = 0; a < L::D; a++) {
+      const int na = a == 0 ? n0 : (a == 1 ? n1 : n2);
+      if (na != 0) {
+#pragma unroll
+        for (int i = 0; i < L::Q; i++) {
+          // populations that point into the fluid change places with their mirror images in the wall plane
+          if (axis_comp<L>(i, a) != 0 && axis_comp<L>(i, a) * na > 0) {
+            const float tmp = f[i]; f[i] = f[L::mirror(a, i)]; f[L::mirror(a, i)] = tmp;
+          }
+        }
+      }
+    }
   } else if (cls == SLF_NT_EQUILIBRIUM_VELOCITY || cls == SLF_NT_EQUILIBRIUM_DENSITY) {
     equilibrium<L>(rho, v, f);
   } else if (cls == SLF_NT_ZOUHE_VELOCITY) {      // boundary.mako:812-816

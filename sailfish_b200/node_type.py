@@ -127,6 +127,13 @@ class NTRegularizedVelocity(LBNodeType):
         self.orientation = orientation
 
 
+class NTSlip(LBNodeType):
+    """node_type.py:402-404: full-slip (specular reflection) node; not a wet node, and -- as in the reference -- its
+    orientation is not detected: pass NTSlip(orientation=grid.vec_to_dir(inward normal))."""
+    standard_macro = True
+    id = 14
+
+
 class NTWallTMS(LBNodeType):
     """node_type.py:171-192: wall for turbulent flows after Chikatamarla and Karlin (Tamm-Mott-Smith approximation):
     the populations coming out of the wall are the equilibrium at target moments (those of the bounced-back state),
@@ -172,7 +179,7 @@ class NTZouHeVelocity(LBNodeType):
 
 
 _NODE_TYPES = dict((c.id, c) for c in (
-    _NTFluid, _NTGhost, _NTPropagationOnly, _NTUnused, NTCopy, NTYuOutflow, NTWallTMS, NTDoNothing, NTEquilibriumDensity,
+    _NTFluid, _NTGhost, _NTPropagationOnly, _NTUnused, NTCopy, NTYuOutflow, NTWallTMS, NTSlip, NTDoNothing, NTEquilibriumDensity,
     NTEquilibriumVelocity, NTFullBBWall, NTHalfBBWall, NTRegularizedDensity,
     NTRegularizedVelocity, NTZouHeDensity, NTZouHeVelocity))
 

@@ -22,7 +22,7 @@ NODE_CLASS_NAMES = (
     '_NTFluid', '_NTGhost', '_NTUnused', '_NTPropagationOnly', 'NTFullBBWall',
     'NTHalfBBWall', 'NTEquilibriumVelocity', 'NTEquilibriumDensity',
     'NTRegularizedVelocity', 'NTRegularizedDensity', 'NTDoNothing', 'NTZouHeVelocity', 'NTZouHeDensity',
-    'NTCopy', 'NTYuOutflow', 'NTWallTMS')
+    'NTCopy', 'NTYuOutflow', 'NTWallTMS', 'NTSlip')
 NT_COUNT = len(NODE_CLASS_NAMES)
 NT_ABSENT = 0xfffffffe
 

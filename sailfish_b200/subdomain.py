@@ -119,6 +119,10 @@ class Subdomain(object):
         # per-axis index arrays on a 10^8-node map)
         base = self._type_map_base
         where_idx = np.flatnonzero(np.broadcast_to(np.asarray(where, dtype=bool), base.shape))
+        # the reference's base arrays have no x padding (subdomain.py:887-905): a condition on y / z alone must not
+        # select padding columns here either
+        if base.shape[-1] != self.lat_shape[-1]:
+            where_idx = where_idx[(where_idx % base.shape[-1]) < self.lat_shape[-1]]
         if inspect.isclass(node_type):
             assert issubclass(node_type, nt.LBNodeType)
             node_type = node_type()

@@ -23,6 +23,7 @@ def make_cases(ns):
     NTZouHeVelocity, NTZouHeDensity = ns['NTZouHeVelocity'], ns['NTZouHeDensity']
     NTCopy, NTYuOutflow = ns['NTCopy'], ns['NTYuOutflow']
     NTWallTMS = ns['NTWallTMS']
+    NTSlip = ns['NTSlip']
     Forced = ns['LBForcedSim']
 
     def sim(sub, **defaults):
@@ -85,6 +86,35 @@ def make_cases(ns):
             sim.vx[:] = 0.04 * np.sin(2 * np.pi * hy / self.gy)
             sim.vy[:] = 0.01 * np.cos(2 * np.pi * hz / self.gz)
             sim.vz[:] = 0.005 * np.sin(2 * np.pi * hx / self.gx)
+
+    class SlipChannel2D(S2):
+        """Full-slip walls at both y ends (the node type takes its orientation from the user), periodic along x."""
+        def boundary_conditions(self, hx, hy):
+            self.set_node(hy == 0, NTSlip(orientation=self.grid.vec_to_dir([0, 1])))
+            self.set_node(hy == self.gy - 1, NTSlip(orientation=self.grid.vec_to_dir([0, -1])))
+
+        def initial_conditions(self, sim, hx, hy):
+            sim.rho[:] = 1.0 + 0.004 * np.cos(2 * np.pi * hx / self.gx)
+            sim.vx[:] = 0.04
+            sim.vy[:] = 0.02 * np.sin(2 * np.pi * hx / self.gx) * np.sin(np.pi * hy / (self.gy - 1))
+
+    class SlipBox3D(S3):
+        """Full-slip planes at both z ends and at y = 0, full-way walls on the other faces and along the edges where
+        two planes meet; a jet towards the z = top plane."""
+        def boundary_conditions(self, hx, hy, hz):
+            wall = (hx == 0) | (hx == self.gx - 1) | (hy == self.gy - 1)
+            wall |= (hy == 0) & ((hz == 0) | (hz == self.gz - 1))
+            self.set_node(wall, NTFullBBWall)
+            free = np.logical_not(wall)
+            self.set_node((hz == 0) & free, NTSlip(orientation=self.grid.vec_to_dir([0, 0, 1])))
+            self.set_node((hz == self.gz - 1) & free, NTSlip(orientation=self.grid.vec_to_dir([0, 0, -1])))
+            self.set_node((hy == 0) & free, NTSlip(orientation=self.grid.vec_to_dir([0, 1, 0])))
+
+        def initial_conditions(self, sim, hx, hy, hz):
+            sim.rho[:] = 1.0 + 0.003 * np.cos(0.5 * hx) * np.sin(0.4 * hy)
+            sim.vx[:] = 0.02 * np.sin(np.pi * hz / (self.gz - 1))
+            sim.vz[:] = 0.03 * np.sin(np.pi * hx / (self.gx - 1)) * np.sin(np.pi * hy / (self.gy - 1))
+            sim.vy[:] = -0.015 * np.sin(np.pi * hx / (self.gx - 1))
 
     class SolidBox2D(S2):
         """A half-way bounce-back block inside a periodic box: shell stays, inside becomes propagation-only /
@@ -208,6 +238,10 @@ def make_cases(ns):
         return OutflowDuct3D
 
     return {
+        'slip_channel2d': (sim(SlipChannel2D, lat_nx=16, lat_ny=11, grid='D2Q9', periodic_x=True), []),
+        'slip_box3d': (sim(SlipBox3D, lat_nx=11, lat_ny=10, lat_nz=9, grid='D3Q19'), []),
+        'slip_box3d_mrt': (sim(SlipBox3D, lat_nx=11, lat_ny=10, lat_nz=9, grid='D3Q19'), ['--model=mrt']),
+        'slip_box3d_q27': (sim(SlipBox3D, lat_nx=11, lat_ny=10, lat_nz=9, grid='D3Q27'), []),
         # walls along a periodic axis: pinned in the AB pattern only (see AB_PINNED_ONLY)
         'tms_channel2d': (sim(TMSChannel2D, lat_nx=16, lat_ny=14, grid='D2Q9', periodic_x=True), []),
         'tms_channel2d_notags': (sim(TMSChannel2D, lat_nx=16, lat_ny=14, grid='D2Q9', periodic_x=True),

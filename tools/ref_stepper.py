@@ -256,6 +256,15 @@ class RefStepper(object):
                     t = f[i, s].copy()
                     f[i, s] = f[j, s]
                     f[j, s] = t
+            if nt.NTSlip in self.ctx['node_types']:          # boundary.mako:837-856: specular reflection
+                ssl = m(nt.NTSlip)
+                for o in range(1, 2 * D + 1):
+                    s = ssl & (ori == o)
+                    if s.any():
+                        for j, k in sym.slip_bb_swap_pairs(g, o):
+                            t = f[j, s].copy()
+                            f[j, s] = f[k, s]
+                            f[k, s] = t
             s = eq_bc
             if s.any():
                 for i in range(Q):
