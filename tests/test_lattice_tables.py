@@ -81,3 +81,22 @@ def test_oracle_tables_match_reference(oracle, lid, name):
     assert np.allclose(info['w'], w, rtol=0, atol=1e-16)
     if name != 'D3Q27':
         assert (info['M'] == G[name + '_mrt_matrix']).all()
+
+
+@pytest.mark.parametrize('name', lattice.KNOWN)
+def test_generated_mirror_tables_match_reference_slip_pairs(name):
+    """L::mirror(axis, i) of csrc/lattice_tables.cuh (tools/gen_lattice_header.py) against the reference's
+    sym.slip_bb_swap_pairs (tests/golden/slip_pairs.npz <- tools/gen_golden_steps.py slip_pairs)."""
+    import re
+    gold = np.load(os.path.join(util.GOLD, 'slip_pairs.npz'))
+    src = open(os.path.join(util.ROOT, 'sailfish_b200', 'csrc', 'lattice_tables.cuh')).read()
+    body = src[src.index('struct %s {' % name):]
+    m = re.search(r'mirror\(int a, int i\) \{ constexpr int t\[(\d+)\] = \{([^}]*)\}', body)
+    L = lattice.get(name)
+    table = np.array([int(x) for x in m.group(2).split(',')]).reshape(3, L.Q)
+    assert int(m.group(1)) == 3 * L.Q
+    for o in range(1, 2 * L.dim + 1):
+        n = gold['%s_%d_normal' % (name, o)]
+        (axis,) = np.nonzero(n)[0]
+        pairs = sorted((i, int(table[axis, i])) for i in range(L.Q) if int(L.basis[i][axis]) * int(n[axis]) > 0)
+        assert pairs == [tuple(p) for p in gold['%s_%d' % (name, o)].tolist()]

@@ -362,6 +362,19 @@ def gen_zoo_steps():
     main(['steps'], cases)
 
 
+def gen_slip_pairs():
+    """sym.slip_bb_swap_pairs (sym.py:481-497) per lattice and orientation: pins the generated mirror tables of
+    sailfish_b200/csrc/lattice_tables.cuh (tests/test_lattice_tables.py)."""
+    from sailfish import sym
+    out = {}
+    for name in ('D2Q9', 'D3Q19', 'D3Q27'):
+        g = getattr(sym, name)
+        for o in range(1, 2 * g.dim + 1):
+            out['%s_%d' % (name, o)] = np.array(sorted(sym.slip_bb_swap_pairs(g, o)), dtype=np.int64)
+            out['%s_%d_normal' % (name, o)] = np.array([int(c) for c in g.dir_to_vec(o)], dtype=np.int64)
+    np.savez_compressed(os.path.join(GOLD, 'slip_pairs.npz'), **out)
+
+
 if __name__ == '__main__':
     what = sys.argv[1:] or ['geometry', 'steps', 'split', 'sc']
     if 'geometry' in what or 'steps' in what:
@@ -375,5 +388,7 @@ if __name__ == '__main__':
         gen_zoo_steps()
     if 'zoo_steps' in what:
         gen_zoo_steps()
+    if 'slip_pairs' in what:
+        gen_slip_pairs()
     if 'sc_gravity' in what:
         gen_shan_chen(only='gravity')
