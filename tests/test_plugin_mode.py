@@ -187,3 +187,53 @@ def test_native_host_stack_equals_reference_host_stack(reference, oracle, monkey
     assert sorted(a.files) == sorted(b.files)
     for k in a.files:
         np.testing.assert_array_equal(a[k], b[k])
+
+
+def _zoo_reference_namespace():
+    from sailfish import node_type as rnt
+    from sailfish.subdomain import Subdomain2D, Subdomain3D
+    from sailfish.lb_single import LBFluidSim
+    from sailfish.lb_base import LBForcedSim
+    ns = dict(Subdomain2D=Subdomain2D, Subdomain3D=Subdomain3D, LBFluidSim=LBFluidSim, LBForcedSim=LBForcedSim)
+    for n in dir(rnt):
+        if n.startswith('NT'):
+            ns[n] = getattr(rnt, n)
+    return ns
+
+
+@pytest.mark.parametrize('case', util.ZOO_STEP_CASES)
+def test_reference_runs_geometry_zoo_on_b200_backend(reference, oracle, monkeypatch, tmp_path, case):
+    """tests/geometry_zoo.py written against the REFERENCE's classes (its Subdomain, node types, LBFluidSim,
+    controller, runner) on --backends=b200: every node class the plan accepts -- half-way bounce-back, TMS, slip,
+    equilibrium / regularised / Zou-He planes, do-nothing, copy and Yu outflow -- reaches the C entry points through the
+    reference's own context (from_context) and reproduces the step goldens."""
+    import fake_device
+    import geometry_zoo
+    fake = fake_device.install_fake(monkeypatch)
+    name, ap = case[len('zoo_'):-3], case[-2:]
+    cls, args = geometry_zoo.make_cases(_zoo_reference_namespace())[name]
+    d = {}
+    cls.update_defaults(d)
+    from sailfish.controller import LBSimulationController
+    from sailfish.geo import LBGeometry2D, LBGeometry3D
+    c = util.load_case(case)
+    steps = int(c['steps'])
+    out = str(tmp_path / 'out')
+    argv = ['zoo'] + args + ['--access_pattern=' + ap, '--visc=0.06', '--backends=b200', '--debug_single_process',
+                            '--max_iters=%d' % steps, '--every=%d' % steps, '--output=' + out, '--quiet']
+    monkeypatch.setattr(sys, 'argv', argv)
+    LBSimulationController(cls, LBGeometry2D if d['grid'] == 'D2Q9' else LBGeometry3D).run()
+    assert 'slf_collide_and_propagate' in fake.calls
+    files = sorted(glob.glob(out + '.0.*%d.npz' % steps))
+    assert files, glob.glob(out + '*')
+    res = np.load(files[-1])
+    m = util.real_mask(c)
+    wet = c['fluid_map']
+    rho = c['rho'][m].reshape(res['rho'].shape)
+    assert np.isnan(res['rho'][~wet]).all()
+    err = np.abs(res['rho'][wet] - rho[wet]).max() / np.abs(rho[wet]).max()
+    assert err < 5e-6, err
+    vscale = max(np.abs(c['v'][k][m].reshape(rho.shape)[wet]).max() for k in range(res['v'].shape[0]))
+    for k in range(res['v'].shape[0]):
+        v = c['v'][k][m].reshape(rho.shape)
+        assert np.abs(res['v'][k][wet] - v[wet]).max() / vscale < 1e-4
