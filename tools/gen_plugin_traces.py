@@ -35,6 +35,10 @@ CASES = {
                          ['--lat_nx=16', '--lat_ny=14', '--lat_nz=12', '--visc=0.04', '--access_pattern=AA'], 8, 4),
     'ldc3d_8blocks_AB': ('examples/ldc_3d.py', 'LDCSim', '2x2x2',
                          ['--lat_nx=16', '--lat_ny=14', '--lat_nz=12', '--visc=0.04', '--access_pattern=AB'], 6, 3),
+    # tests/geometry_zoo.py with the reference's classes: node classes the examples do not use
+    'zoo_tms_block3d_AA': ('zoo:tms_block3d', None, None, ['--visc=0.06', '--access_pattern=AA'], 8, 4),
+    'zoo_copy_duct3d_AB': ('zoo:copy_duct3d', None, None, ['--visc=0.06', '--access_pattern=AB'], 8, 4),
+    'zoo_slip_box3d_mrt_AA': ('zoo:slip_box3d_mrt', None, None, ['--visc=0.06', '--access_pattern=AA'], 8, 4),
 }
 
 
@@ -50,9 +54,25 @@ def child(case, out_dir):
     abi_trace.Recorder(fake, out_dir)
     import ref_harness
     script, cls_name, geo_name, args, steps, every = CASES[case]
-    mod = ref_harness.load_example(script)
     from sailfish.controller import LBSimulationController
     from sailfish import geo
+    if script.startswith('zoo:'):
+        import geometry_zoo
+        from sailfish import node_type as rnt
+        from sailfish.subdomain import Subdomain2D, Subdomain3D
+        from sailfish.lb_single import LBFluidSim
+        from sailfish.lb_base import LBForcedSim
+        ns = dict(Subdomain2D=Subdomain2D, Subdomain3D=Subdomain3D, LBFluidSim=LBFluidSim, LBForcedSim=LBForcedSim)
+        ns.update((n, getattr(rnt, n)) for n in dir(rnt) if n.startswith('NT'))
+        sim_cls, zoo_args = geometry_zoo.make_cases(ns)[script[len('zoo:'):]]
+        d = {}
+        sim_cls.update_defaults(d)
+        out = os.path.join(out_dir, 'out')
+        sys.argv = [script] + zoo_args + args + ['--debug_single_process', '--backends=b200', '--max_iters=%d' % steps,
+                                                 '--every=%d' % every, '--output=' + out, '--quiet']
+        LBSimulationController(sim_cls, geo.LBGeometry2D if d['grid'] == 'D2Q9' else geo.LBGeometry3D).run()
+        return
+    mod = ref_harness.load_example(script)
     if geo_name == '2x2x2':
         from sailfish.subdomain import SubdomainSpec3D
 
