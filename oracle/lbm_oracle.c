@@ -748,16 +748,21 @@ static inline long long gidx(const Ctx *C, const int *c) { return c[0] + C->stri
 
 /* make_cond(i), kernel_utils.mako:120-171 */
 static int pbc_make_cond(const Ctx *C, int axis, int opposite, const int *e, const int *oth, int nother,
-                         const int *idx, const int *maxd) {
+                         const int *idx, const int *maxd, int link_lo, int link_hi) {
   const int *per = C->P->periodic;
   if (opposite) {
     for (int k = 0; k < nother; k++) if (!(idx[k] >= 1 && idx[k] <= maxd[k])) return 0;
     return 1;
   }
   if (C->L->D == 2) {
+    /* The reference's 2-D rule stops at the last real row.  With a neighbour across a y face (native plane push,
+     * axis == 0 only) the ghost row on that side holds this subdomain's outgoing populations, and the ones that also
+     * crossed the periodic x face must be wrapped inside it before the row leaves -- what the 3-D rule (no bound on a
+     * non-periodic other axis) does for z-splits. */
     int c = e[1 - axis];
-    if (c == 1) return idx[0] > 1 && idx[0] <= maxd[0];
-    if (c == -1) return idx[0] < maxd[0] && idx[0] >= 1;
+    const int split_other = axis == 0;
+    if (c == 1) return idx[0] > 1 && (idx[0] <= maxd[0] || (split_other && link_hi && idx[0] == maxd[0] + 1));
+    if (c == -1) return idx[0] < maxd[0] && (idx[0] >= 1 || (split_other && link_lo && idx[0] == 0));
     return 1;
   }
   for (int k = 0; k < 2; k++) {
@@ -840,7 +845,7 @@ int orc_apply_periodic_boundary_conditions_linked(const SlfParams *P, REAL *dist
       const int n2e = L->e[i][0]*L->e[i][0] + L->e[i][1]*L->e[i][1] + L->e[i][2]*L->e[i][2];
       if (!isfinite(fv)) continue;
       if (n2e > 1) {
-        int main_ok = pbc_make_cond(C, axis, with_swap, L->e[i], oth, nother, idx, maxd);
+        int main_ok = pbc_make_cond(C, axis, with_swap, L->e[i], oth, nother, idx, maxd, link_lo, link_hi);
         if (main_ok) dist[gi_high + C->DS * j] = fv;
         if (with_swap || !main_ok) {
           int tgt[3];
@@ -859,7 +864,7 @@ int orc_apply_periodic_boundary_conditions_linked(const SlfParams *P, REAL *dist
       const int n2e = L->e[i][0]*L->e[i][0] + L->e[i][1]*L->e[i][1] + L->e[i][2]*L->e[i][2];
       if (!isfinite(fv)) continue;
       if (n2e > 1) {
-        int main_ok = pbc_make_cond(C, axis, with_swap, L->e[i], oth, nother, idx, maxd);
+        int main_ok = pbc_make_cond(C, axis, with_swap, L->e[i], oth, nother, idx, maxd, link_lo, link_hi);
         if (main_ok) dist[gi_low + offset + C->DS * j] = fv;
         if (with_swap || !main_ok) {
           int tgt[3];

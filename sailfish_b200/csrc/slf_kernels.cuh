@@ -693,7 +693,7 @@ __device__ __forceinline__ long long gidx3(const DevParams &P, int c0, int c1, i
 
 template <class L, bool SWAP>
 __device__ __forceinline__ bool pbc_main_cond(int axis, int i, const int (&per)[3], const int (&oth)[2],
-                                              const int (&idx)[2], const int (&maxd)[2]) {
+                                              const int (&idx)[2], const int (&maxd)[2], int link_lo, int link_hi) {
   const int e[3] = {L::ex(i), L::ey(i), L::ez(i)};
   if (SWAP) {
     bool ok = idx[0] >= 1 && idx[0] <= maxd[0];
@@ -701,9 +701,13 @@ __device__ __forceinline__ bool pbc_main_cond(int axis, int i, const int (&per)[
     return ok;
   }
   if (L::D == 2) {
+    // The reference's 2-D rule stops at the last real row.  With a neighbour across a y face (plane push, axis == 0
+    // only) the ghost row on that side holds this subdomain's outgoing populations; the ones that also crossed the
+    // periodic x face are wrapped inside it before the row leaves, as the 3-D rule does for z-splits.
     const int c = e[1 - axis];
-    if (c == 1) return idx[0] > 1 && idx[0] <= maxd[0];
-    if (c == -1) return idx[0] < maxd[0] && idx[0] >= 1;
+    const bool split_other = axis == 0;
+    if (c == 1) return idx[0] > 1 && (idx[0] <= maxd[0] || (split_other && link_hi && idx[0] == maxd[0] + 1));
+    if (c == -1) return idx[0] < maxd[0] && (idx[0] >= 1 || (split_other && link_lo && idx[0] == 0));
     return true;
   }
   bool ok = true;
@@ -807,7 +811,7 @@ apply_pbc(const DevParams P, float *dist, int axis, int per0, int per1, int per2
     if (!isfinite(fv)) continue;
     const int n2e = L::ex(i) * L::ex(i) + L::ey(i) * L::ey(i) + L::ez(i) * L::ez(i);
     if (n2e > 1) {
-      const bool main_ok = pbc_main_cond<L, SWAP>(axis, i, per, oth, idx, maxd);
+      const bool main_ok = pbc_main_cond<L, SWAP>(axis, i, per, oth, idx, maxd, link_lo, link_hi);
       if (main_ok) dist[gi_high + P.DS * j] = fv;
       if (SWAP || !main_ok) {
         int tgt[3];
@@ -834,7 +838,7 @@ apply_pbc(const DevParams P, float *dist, int axis, int per0, int per1, int per2
     if (!isfinite(fv)) continue;
     const int n2e = L::ex(i) * L::ex(i) + L::ey(i) * L::ey(i) + L::ez(i) * L::ez(i);
     if (n2e > 1) {
-      const bool main_ok = pbc_main_cond<L, SWAP>(axis, i, per, oth, idx, maxd);
+      const bool main_ok = pbc_main_cond<L, SWAP>(axis, i, per, oth, idx, maxd, link_lo, link_hi);
       if (main_ok) dist[gi_low + offset + P.DS * j] = fv;
       if (SWAP || !main_ok) {
         int tgt[3];

@@ -70,3 +70,20 @@ def test_gpu_n_subdomains_equal_one(oracle, name, ap):
         err = np.abs(b[wet] - c[wet]).max() / scale
         env = np.abs(c32[wet] - c[wet]).max() / scale
         assert err <= 2.0 * env + 1e-6, (k, err, env)
+
+
+@pytest.mark.parametrize('ap', ['AB', 'AA'])
+@pytest.mark.parametrize('name,n', [('tms_channel2d', 2), ('slip_channel2d', 3)])
+def test_gpu_2d_channel_periodic_in_x_split_in_y(name, n, ap):
+    """2-D, x periodic inside every subdomain, neighbours across the y faces: the linked variant of the periodic
+    kernel wraps the outgoing ghost row before it is pushed (tests/test_block_decomposition_fake.py has the same
+    set-ups on the CPU stand-in device).  Split == single, bit for bit; the single run itself is covered by
+    tests/test_gpu_zoo_node_types.py."""
+    import geometry_zoo
+    from test_host_geometry import _zoo_namespace
+    cls, zargs = geometry_zoo.make_cases(_zoo_namespace())[name]
+    args = zargs + ['--access_pattern=' + ap, '--visc=0.06']
+    one = gpu_run(cls, EqualSubdomainsGeometry2D, args + ['--subdomains=1'], 9)
+    many = gpu_run(cls, EqualSubdomainsGeometry2D, args + ['--subdomains=%d' % n], 9)
+    for a, b in zip(one, many):
+        np.testing.assert_array_equal(a, b)
