@@ -1,10 +1,10 @@
-"""GPU parity on tests/geometry_zoo.py: half-way bounce-back, equilibrium-velocity, regularised-density and
-do-nothing nodes, obstacles with unused cores, D3Q27 with pressure planes -- node types the BASELINE examples do
-not use.  The oracle is pinned on these cases (tests/test_oracle_golden.py, reference-expression goldens).
+"""GPU parity on tests/geometry_zoo.py: node classes the BASELINE examples do not use -- half-way bounce-back,
+equilibrium-velocity, regularised-density, Zou-He, do-nothing, copy and Yu outflow, TMS and full-slip walls, obstacles
+with unused cores, D3Q27 with pressure planes.  The oracle is pinned on these cases (tests/test_oracle_golden.py,
+reference-expression goldens from tools/gen_golden_steps.py zoo).
 
-
-Status: passed on the driver's B200 at the end of round 1 (22 XPASS in GPUTEST_r01); the provisional xfail
-marker is gone, a regression now fails the suite."""
+Status: all cases passed on a B200 in round 2 (profiles/r02_gpu_tests_new_node_types.txt,
+profiles/r02_gpu_tests_slip.txt)."""
 import numpy as np
 import pytest
 
