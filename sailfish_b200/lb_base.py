@@ -63,15 +63,11 @@ class LBSim(object):
         same function serves the unmodified reference on --backends=b200, so both ways in configure the
         kernels through one path."""
         cfg = self.config
-        ctx['grid'] = self.grid
-        ctx['grids'] = self.grids
-        ctx['constants'] = self.constants()
-        ctx['relaxation_enabled'] = getattr(cfg, 'relaxation_enabled', True)
-        ctx['propagation_enabled'] = getattr(cfg, 'propagation_enabled', True)
-        ctx['access_pattern'] = cfg.access_pattern
-        ctx['node_addressing'] = getattr(cfg, 'node_addressing', 'direct')
-        ctx['propagate_on_read'] = getattr(cfg, 'propagate_on_read', False)
-        ctx['config'] = cfg
+        ctx.update(grid=self.grid, grids=self.grids, constants=self.constants(), config=cfg,
+                   access_pattern=cfg.access_pattern)
+        for key, default in (('relaxation_enabled', True), ('propagation_enabled', True),
+                             ('node_addressing', 'direct'), ('propagate_on_read', False)):
+            ctx[key] = getattr(cfg, key, default)
 
     def get_state(self):
         """lb_base.py:216-220: what a checkpoint stores besides the populations."""
@@ -140,9 +136,8 @@ class LBForcedSim(LBSim):
         """lb_base.py:361-366."""
         super(LBForcedSim, self).update_context(ctx)
         numeric = dict((g, {True: tuple(float(x) for x in a)}) for g, a in self._forces.items())
-        ctx['forces'] = ForcePair(numeric, {})
-        ctx['force_couplings'] = dict(self._force_couplings)
-        ctx['force_implementation'] = getattr(self.config, 'force_implementation', 'guo')
+        ctx.update(forces=ForcePair(numeric, {}), force_couplings=dict(self._force_couplings),
+                   force_implementation=getattr(self.config, 'force_implementation', 'guo'))
 
     def add_force_coupling(self, grid_a, grid_b, const_name):
         """lb_base.py:386-394: Shan-Chen interaction of component grid_a with grid_b, strength

@@ -19,8 +19,7 @@ class LBBinaryFluidBase(LBSim):
     def update_context(self, ctx):
         """lb_binary.py:130-133."""
         super(LBBinaryFluidBase, self).update_context(ctx)
-        ctx['tau_phi'] = self.config.tau_phi
-        ctx['model'] = 'bgk'
+        ctx.update(tau_phi=self.config.tau_phi, model='bgk')
 
 
 class LBBinaryFluidShanChen(LBBinaryFluidBase, LBForcedSim):
@@ -29,10 +28,9 @@ class LBBinaryFluidShanChen(LBBinaryFluidBase, LBForcedSim):
     def __init__(self, config):
         """lb_binary.py:382-387."""
         super(LBBinaryFluidShanChen, self).__init__(config)
-        self.add_force_coupling(0, 0, 'G11')
-        self.add_force_coupling(0, 1, 'G12')
-        self.add_force_coupling(1, 0, 'G21')
-        self.add_force_coupling(1, 1, 'G22')
+        for a in (0, 1):
+            for b in (0, 1):
+                self.add_force_coupling(a, b, 'G%d%d' % (a + 1, b + 1))
 
     def constants(self):
         """lb_binary.py:389-395: the cross coupling is symmetric (G21 = G12)."""
@@ -49,10 +47,8 @@ class LBBinaryFluidShanChen(LBBinaryFluidBase, LBForcedSim):
         """lb_binary.py:416-421."""
         super(LBBinaryFluidShanChen, self).update_context(ctx)
         cfg = self.config
-        ctx['simtype'] = 'shan-chen'
-        ctx['sc_potential'] = cfg.sc_potential
-        ctx['tau'] = (6.0 * cfg.visc + 1.0) / 2.0
-        ctx['visc'] = cfg.visc
+        ctx.update(simtype='shan-chen', sc_potential=cfg.sc_potential, visc=cfg.visc,
+                   tau=(6.0 * cfg.visc + 1.0) / 2.0)
 
     @classmethod
     def add_options(cls, group, dim):

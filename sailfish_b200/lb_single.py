@@ -19,10 +19,6 @@ class LBFluidSim(LBSim):
         and form the relaxation rates themselves, as the generated code does."""
         super(LBFluidSim, self).update_context(ctx)
         cfg = self.config
-        ctx['tau'] = (6.0 * cfg.visc + 1.0) / 2.0
-        ctx['visc'] = cfg.visc
-        ctx['model'] = cfg.model
-        ctx['simtype'] = 'lbm'
-        ctx['subgrid'] = getattr(cfg, 'subgrid', 'none')
-        ctx['regularized'] = getattr(cfg, 'regularized', False)
-        ctx['incompressible'] = getattr(cfg, 'incompressible', False)
+        ctx.update(simtype='lbm', model=cfg.model, visc=cfg.visc, tau=(6.0 * cfg.visc + 1.0) / 2.0)
+        for key, default in (('subgrid', 'none'), ('regularized', False), ('incompressible', False)):
+            ctx[key] = getattr(cfg, key, default)
