@@ -808,6 +808,14 @@ static int pbc_corner_target(const Ctx *C, int axis, int opposite, const int *e,
   return 0;
 }
 
+/* The reference's edge entries for vectors with three non-zero components (handle_corners, kernel_utils.mako:84-118)
+ * wrap along the second other axis whether or not that axis is periodic.  In a single subdomain the stray copy lands
+ * in a ghost layer nobody reads; with a neighbour across that face the ghost layer is, after in-place steps, where the
+ * neighbour's planes land -- it is left alone like the rest of that layer. */
+static inline int pbc_target_is_landing_zone(int with_swap, int t_split, int n_split, int link_lo, int link_hi) {
+  return with_swap && ((link_lo && t_split == 0) || (link_hi && t_split == n_split - 1));
+}
+
 /* link_lo / link_hi: this subdomain has a neighbour across the low / high face of the outermost (split) axis
  * that delivers whole, PBC-completed planes (slf_halo_push): after in-place steps (with_swap) into the ghost
  * layer, after streaming steps into the crossing slots of the first / last real layer.  Those cells belong to
@@ -849,7 +857,8 @@ int orc_apply_periodic_boundary_conditions_linked(const SlfParams *P, REAL *dist
         if (main_ok) dist[gi_high + C->DS * j] = fv;
         if (with_swap || !main_ok) {
           int tgt[3];
-          if (pbc_corner_target(C, axis, with_swap, L->e[i], oth, nother, idx, with_swap ? lim[axis] - 1 : lim[axis] - 2, tgt))
+          if (pbc_corner_target(C, axis, with_swap, L->e[i], oth, nother, idx, with_swap ? lim[axis] - 1 : lim[axis] - 2, tgt) &&
+              !pbc_target_is_landing_zone(with_swap, tgt[so], no, link_lo, link_hi))
             dist[gidx(C, tgt) + C->DS * j] = fv;
         }
       } else {
@@ -868,7 +877,8 @@ int orc_apply_periodic_boundary_conditions_linked(const SlfParams *P, REAL *dist
         if (main_ok) dist[gi_low + offset + C->DS * j] = fv;
         if (with_swap || !main_ok) {
           int tgt[3];
-          if (pbc_corner_target(C, axis, with_swap, L->e[i], oth, nother, idx, with_swap ? 0 : 1, tgt))
+          if (pbc_corner_target(C, axis, with_swap, L->e[i], oth, nother, idx, with_swap ? 0 : 1, tgt) &&
+              !pbc_target_is_landing_zone(with_swap, tgt[so], no, link_lo, link_hi))
             dist[gidx(C, tgt) + C->DS * j] = fv;
         }
       } else {

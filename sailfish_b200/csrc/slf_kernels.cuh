@@ -756,6 +756,14 @@ __device__ __forceinline__ bool pbc_corner(int axis, int i, const int (&per)[3],
   return false;
 }
 
+// The reference's edge entries for vectors with three non-zero components wrap along the second other axis whether or
+// not it is periodic (kernel_utils.mako:84-118).  Alone, the stray copy lands in a ghost layer nobody reads; with a
+// neighbour across that face the layer is, after in-place steps, the neighbour's landing zone and is left alone.
+template <bool SWAP>
+__device__ __forceinline__ bool pbc_landing_zone(int t_split, int n_split, int link_lo, int link_hi) {
+  return SWAP && ((link_lo && t_split == 0) || (link_hi && t_split == n_split - 1));
+}
+
 __device__ __forceinline__ void set3(int a, int v, int &x, int &y, int &z) {
   if (a == 0) x = v; else if (a == 1) y = v; else z = v;
 }
@@ -815,7 +823,8 @@ apply_pbc(const DevParams P, float *dist, int axis, int per0, int per1, int per2
       if (main_ok) dist[gi_high + P.DS * j] = fv;
       if (SWAP || !main_ok) {
         int tgt[3];
-        if (pbc_corner<L, SWAP>(axis, i, per, lim, oth, idx, SWAP ? lim[axis] - 1 : lim[axis] - 2, tgt))
+        if (pbc_corner<L, SWAP>(axis, i, per, lim, oth, idx, SWAP ? lim[axis] - 1 : lim[axis] - 2, tgt) &&
+            !pbc_landing_zone<SWAP>(tgt[so], no, link_lo, link_hi))
           dist[gidx3<L>(P, tgt[0], tgt[1], tgt[2]) + P.DS * j] = fv;
       }
     } else {
@@ -842,7 +851,8 @@ apply_pbc(const DevParams P, float *dist, int axis, int per0, int per1, int per2
       if (main_ok) dist[gi_low + offset + P.DS * j] = fv;
       if (SWAP || !main_ok) {
         int tgt[3];
-        if (pbc_corner<L, SWAP>(axis, i, per, lim, oth, idx, SWAP ? 0 : 1, tgt))
+        if (pbc_corner<L, SWAP>(axis, i, per, lim, oth, idx, SWAP ? 0 : 1, tgt) &&
+            !pbc_landing_zone<SWAP>(tgt[so], no, link_lo, link_hi))
           dist[gidx3<L>(P, tgt[0], tgt[1], tgt[2]) + P.DS * j] = fv;
       }
     } else {

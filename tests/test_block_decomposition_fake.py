@@ -109,3 +109,51 @@ def test_2d_channel_periodic_in_x_split_in_y(fake, name, gsize, n, ap):
     _, many = block_util.run_blocks(cls, EqualSubdomainsGeometry2D, args + ['--subdomains=%d' % n], 9)
     np.testing.assert_array_equal(block_util.merge(one, gsize), block_util.merge(many, gsize))
     assert len(many) == n and 'slf_halo_push' in fake.calls and 'slf_apply_periodic_boundary_conditions' in fake.calls
+
+
+def _periodic_box3d(per, walls, grid):
+    from sailfish_b200 import node_type as nt
+    from sailfish_b200.lb_single import LBFluidSim
+    from sailfish_b200.subdomain import Subdomain3D
+
+    class Sub(Subdomain3D):
+        def boundary_conditions(self, hx, hy, hz):
+            w = np.zeros(np.broadcast(hx, hy, hz).shape, bool)
+            if 'x' in walls:
+                w |= (hx == 0) | (hx == self.gx - 1)
+            if 'y' in walls:
+                w |= (hy == 0) | (hy == self.gy - 1)
+            if 'z' in walls:
+                w |= (hz == 0) | (hz == self.gz - 1)
+            if w.any():
+                self.set_node(w, nt.NTFullBBWall)
+
+        def initial_conditions(self, sim, hx, hy, hz):
+            sim.rho[:] = 1.0 + 1e-3 * np.sin(2 * np.pi * hx / self.gx) * np.cos(2 * np.pi * hz / self.gz)
+            sim.vx[:] = 0.05 * np.sin(2 * np.pi * hy / self.gy)
+            sim.vy[:] = 0.03 * np.cos(2 * np.pi * hz / self.gz)
+            sim.vz[:] = 0.02 * np.sin(2 * np.pi * (hx + hy) / self.gx)
+
+    class Sim(LBFluidSim):
+        subdomain = Sub
+
+        @classmethod
+        def update_defaults(cls, d):
+            d.update(lat_nx=10, lat_ny=9, lat_nz=12, grid=grid, **dict(('periodic_' + a, True) for a in per))
+    return Sim
+
+
+@pytest.mark.parametrize('ap', ['AA', 'AB'])
+@pytest.mark.parametrize('grid', ['D3Q19', 'D3Q27'])
+@pytest.mark.parametrize('per,walls', [('xyz', ''), ('xy', 'z'), ('x', 'yz'), ('y', 'xz'), ('xz', 'y')])
+def test_locally_periodic_axes_inside_a_z_split(fake, per, walls, grid, ap):
+    """Every combination of locally periodic x / y (periodic kernels) with neighbours across z (plane push; a periodic z
+    is closed by a wrap-around link), D3Q19 and D3Q27.  D3Q27 in the AA pattern is the case that needs
+    pbc_landing_zone: the reference's edge entries for (±1, ±1, ±1) wrap along z whether or not z is periodic, and
+    after in-place steps that stray copy would land in the ghost layer the neighbour delivers into."""
+    sim = _periodic_box3d(per, walls, grid)
+    args = ['--access_pattern=' + ap, '--visc=0.05']
+    _, one = block_util.run_blocks(sim, EqualSubdomainsGeometry3D, args + ['--subdomains=1'], 8)
+    _, many = block_util.run_blocks(sim, EqualSubdomainsGeometry3D, args + ['--subdomains=3'], 8)
+    np.testing.assert_array_equal(block_util.merge(one, (10, 9, 12)), block_util.merge(many, (10, 9, 12)))
+    assert 'slf_halo_push' in fake.calls
