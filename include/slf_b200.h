@@ -299,6 +299,15 @@ int  slf_halo_push(SlfPlan *plan, uint64_t dist, int face, uint64_t peer_dist, i
  * cross-sections must be equal.  The copied windows are disjoint between messages (see csrc/slf_halo.cuh). */
 int  slf_halo_push_face(SlfPlan *plan, uint64_t dist, int face, uint64_t peer_dist, const int *peer_lat,
                         const int *peer_arr, int with_swap, uint64_t signal_sem, uint64_t stream);
+/* Which faces of this subdomain have a neighbour (bit 2 * axis + side; default: all).  Across a face WITHOUT one -- the
+ * domain boundary -- nothing was delivered into the ghost layer, so slf_halo_push_face leaves the positions that
+ * would forward such data out of its windows.  The reference gets the same effect from the partial maps of its
+ * connections (subdomain_connection.py:96-180: populations whose source lies outside the domain are not sent); it
+ * matters to nodes that keep what they find in the slots nobody streams into (do-nothing outflow, link bounce-back). */
+int  slf_plan_set_face_links(SlfPlan *plan, int links);
+/* The windows slf_halo_push_face uses, as a pure host function (tests): returns 1 if population i of `lattice` crosses
+ * `face`, and then lo[0..1] / cnt[0..1] = first position and count along the other axes (ascending axis order). */
+int  slf_halo_face_window(int lattice, const int *lat, int face, int with_swap, int links, int i, int *lo, int *cnt);
 /* Stream-ordered counting semaphores in device memory for cross-GPU ordering of the pushes
  * (they stand where the reference blocks in zmq recv, connector.py:73-117).  A subdomain owns a
  * zero-initialised block of uint32 words: ready[channel][side] (incremented by the neighbour on

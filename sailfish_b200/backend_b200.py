@@ -74,6 +74,8 @@ _PROTOTYPES = {
     'slf_distribute_sparse_data': [_vp, _u64, _u64, _u64, _i, _u64],
     'slf_halo_push': [_vp, _u64, _i, _u64, _i, _i, _i, _u64, _u64],
     'slf_halo_push_face': [_vp, _u64, _i, _u64, ctypes.POINTER(_i), ctypes.POINTER(_i), _i, _u64, _u64],
+    'slf_plan_set_face_links': [_vp, _i],
+    'slf_halo_face_window': [_i, ctypes.POINTER(_i), _i, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i)],
     'slf_sem_signal': [_u64, _u64],
     'slf_sem_wait': [_u64, _u64, _u64, _u64, _i, _u64],
     'slf_sem_status': [_u64, ctypes.POINTER(_u32)],

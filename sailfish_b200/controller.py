@@ -165,6 +165,11 @@ class LBSimulationController(object):
 
         def geometry(r):
             return dict(lat=list(reversed(r._lat_size)), arr=list(reversed(r._physical_size)))
+        # subdomains with do-nothing or link-bounce nodes exchange through the windowed face push (all of them, or the
+        # step phases of neighbours would not match); with a locally periodic axis the plane push stays (the windowed
+        # exchange has no periodic kernels beside it)
+        windowed = any(r.has_boundary_sensitive_nodes() for r in self.runners if hasattr(r, 'has_boundary_sensitive_nodes'))
+        periodic = any(any(r._spec._periodicity) for r in self.runners)
         if dist_mode:
             import torch.distributed as dist
             if not dist.is_initialized():
@@ -172,9 +177,12 @@ class LBSimulationController(object):
             mine = self.runners[0]
             be = mine.backend
             payload = dict(id=mine._spec.id, bufs=dict((k, be.ipc_handle(v) if v else None)
-                                                       for k, v in mine.export_buffers().items()), **geometry(mine))
+                                                       for k, v in mine.export_buffers().items()),
+                           windowed=windowed, periodic=periodic, **geometry(mine))
             gathered = [None] * ws
             dist.all_gather_object(gathered, payload)
+            windowed = any(g['windowed'] for g in gathered)
+            periodic = any(g['periodic'] for g in gathered)
             needed = set(mine._spec._face_conn.values())
             for g in gathered:
                 if g['id'] in needed and g['id'] != mine._spec.id:
@@ -182,6 +190,8 @@ class LBSimulationController(object):
                                            bufs=dict((k, int(be.ipc_handle_wrap(h)) if h else 0)
                                                      for k, h in g['bufs'].items()))
             self._dist = dist
+        for r in self.runners:
+            r._windowed_exchange = windowed and not periodic and hasattr(r, 'has_boundary_sensitive_nodes')
         for r in self.runners:
             for face, other in sorted(r._spec._face_conn.items()):
                 axis = face // 2

@@ -205,6 +205,59 @@ int slf_halo_push(SlfPlan *pl, uint64_t dist, int face, uint64_t peer_dist, int 
   return 0;
 }
 
+// Window of the positions along the other axes that population e carries across a face of `axis` (dimension-ordered
+// exchange: the axes before `axis` have been exchanged in this step, the ones after it have not):
+//   after streaming steps: earlier axes 1 .. n-2,        later axes 1+e .. n-2+e;
+//   after in-place steps : earlier axes 1-e .. n-2-e,    later axes 1 .. n-2.
+// Along an EARLIER axis the end of the window on the side the population comes from holds data only if a neighbour
+// delivered it there; on a side without a neighbour (domain boundary; bit 2*ax+side of `links` clear) that position is
+// dropped -- its content never left a node (streaming) or belongs to the receiving subdomain's own boundary nodes
+// (in-place: do-nothing and link-bounce nodes store into their ghost neighbours).
+static inline void face_window(int D, const int *lat, const int *e, int axis, int with_swap, int links, int *lo, int *cnt) {
+  int b = 0;
+  for (int ax = 0; ax < D; ax++) {
+    if (ax == axis) continue;
+    int l, c = lat[ax] - 2;
+    if (ax < axis) {
+      l = with_swap ? 1 - e[ax] : 1;
+      const int from_side = e[ax] > 0 ? 0 : 1;               // the side of `ax` the population entered through
+      if (e[ax] != 0 && !((links >> (2 * ax + from_side)) & 1)) {
+        c -= 1;
+        if (with_swap) { if (e[ax] > 0) l = 1; else l = 2; }
+        else if (e[ax] > 0) l = 2;
+      }
+    } else {
+      l = with_swap ? 1 : 1 + e[ax];
+    }
+    lo[b] = l; cnt[b] = c < 0 ? 0 : c;
+    b++;
+  }
+}
+
+// The same windows for the tests (pure host code, no device needed): 1 if population i of the lattice crosses `face`.
+int slf_halo_face_window(int lattice, const int *lat, int face, int with_swap, int links, int i, int *lo, int *cnt) {
+  const int D = lattice == SLF_D2Q9 ? 2 : 3;
+  const int axis = face >> 1, sgn = (face & 1) ? 1 : -1;
+  if (!lat || !lo || !cnt || face < 0 || axis >= D) return fail(SLF_EINVAL, "bad arguments");
+  int e[3];
+  switch (lattice) {
+    case SLF_D2Q9: if (i < 0 || i >= 9) return 0; e[0] = D2Q9::ex(i); e[1] = D2Q9::ey(i); e[2] = 0; break;
+    case SLF_D3Q19: if (i < 0 || i >= 19) return 0; e[0] = D3Q19::ex(i); e[1] = D3Q19::ey(i); e[2] = D3Q19::ez(i); break;
+    case SLF_D3Q27: if (i < 0 || i >= 27) return 0; e[0] = D3Q27::ex(i); e[1] = D3Q27::ey(i); e[2] = D3Q27::ez(i); break;
+    default: return fail(SLF_EINVAL, "unknown lattice");
+  }
+  if (e[axis] * sgn < 1) return 0;
+  lo[0] = lo[1] = 0; cnt[0] = cnt[1] = 1;
+  face_window(D, lat, e, axis, with_swap, links, lo, cnt);
+  return 1;
+}
+
+int slf_plan_set_face_links(SlfPlan *pl, int links) {
+  if (!pl) return fail(SLF_EINVAL, "null plan");
+  pl->face_links = links & 0x3f;
+  return 0;
+}
+
 int slf_halo_push_face(SlfPlan *pl, uint64_t dist, int face, uint64_t peer_dist, const int *peer_lat, const int *peer_arr,
                        int with_swap, uint64_t signal_sem, uint64_t stream) {
   if (!pl) return fail(SLF_EINVAL, "null plan");
@@ -239,14 +292,8 @@ int slf_halo_push_face(SlfPlan *pl, uint64_t dist, int face, uint64_t peer_dist,
     }
     if (e[axis] * sgn < 1) continue;
     const int slot = with_swap ? opp : i;
-    const int oth[2] = {o1, o2};
     int lo[2] = {0, 0}, cnt[2] = {1, 1};
-    for (int b = 0; b < D - 1; b++) {
-      const int ax = oth[b];
-      cnt[b] = lat[ax] - 2;
-      if (ax < axis) lo[b] = with_swap ? 1 - e[ax] : 1;                        // earlier axis
-      else lo[b] = with_swap ? 1 : 1 + e[ax];                                  // later axis
-    }
+    face_window(D, lat, e, axis, with_swap, pl->face_links, lo, cnt);
     a.src[a.n] = (const float *)dist + d.DS * slot + str[axis] * src_layer;
     a.dst[a.n] = (float *)peer_dist + peer_DS * slot + pstr[axis] * dst_layer;
     a.lo1[a.n] = lo[0]; a.n1[a.n] = cnt[0]; a.lo2[a.n] = lo[1]; a.n2[a.n] = cnt[1];

@@ -45,6 +45,8 @@ struct SlfPlan {
   unsigned int *d_flags = nullptr;     // per-block step counters of the multi-step kernel
   std::vector<long long> layer_off;    // list offsets per outermost-axis layer (size n + 1)
   int link_lo = 0, link_hi = 0;        // neighbours across the low / high face of the split axis
+  int face_links = 0x3f;               // bit f: face f (2 * axis + side) has a neighbour (slf_plan_set_face_links);
+                                       // default "all": the windows of slf_halo_push_face are then the plain ones
   std::vector<StepGraph> graphs;
   std::mutex graph_mutex;
   unsigned int *d_push_done = nullptr; // block counters of halo_push_kernel (last block signals), [2]

@@ -326,12 +326,20 @@ class SubdomainRunner(object):
         d = self._dev
         return {'dist0a': int(d.d_dist_a), 'dist0b': int(d.d_dist_b) if d.d_dist_b else 0, 'sems': int(self._sems)}
 
+    # Node classes that keep what they find in the slots no node streams into (boundary.mako:653-668, :862-877): a
+    # whole-plane push across a face that cuts the domain boundary would overwrite those slots with the neighbour's
+    # never-written ghost entries.  Subdomains holding such nodes exchange through the windowed face push instead.
+    BOUNDARY_SENSITIVE = ('NTDoNothing', 'NTHalfBBWall', 'NTWallTMS')
+
+    def has_boundary_sensitive_nodes(self):
+        return bool(set(self._subdomain.type_ids_by_name()) & set(self.BOUNDARY_SENSITIVE))
+
     def add_link(self, link):
         outer = self.dim - 1
         self._xlinks[link.face] = link
         if link.axis == outer:
             self._links[link.face & 1] = link
-        else:
+        if link.axis != outer or getattr(self, '_windowed_exchange', False):
             self._general = True
         if self._general and any(self._spec._periodicity):
             raise P.UnsupportedConfiguration('native runner: a locally periodic axis next to subdomain links across x / y '
@@ -339,6 +347,8 @@ class SubdomainRunner(object):
                                              % 'xyz'[outer])
         self._drop_graphs()
         self._lib.call('slf_plan_set_links', self._dev.plan, int(0 in self._links), int(1 in self._links))
+        if self._general:
+            self._lib.call('slf_plan_set_face_links', self._dev.plan, sum(1 << f for f in self._xlinks))
 
     def _outer_n(self):
         return self._lat_size[0]

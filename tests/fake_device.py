@@ -143,6 +143,11 @@ class FakeLib(object):
     def _slf_plan_set_links(self, plan, lo, hi):
         self.links[self._key(plan)] = (int(bool(lo)), int(bool(hi)))
 
+    def _slf_plan_set_face_links(self, plan, links):
+        if not hasattr(self, 'face_links'):
+            self.face_links = {}
+        self.face_links[self._key(plan)] = int(links) & 0x3f
+
     def _slf_set_initial_conditions(self, plan, dist, vx, vy, vz, rho, m, stream):
         p = self._p(plan)
         n = p.dist_size
@@ -213,7 +218,8 @@ class FakeLib(object):
         parr = [int(peer_arr[k]) for k in range(D)]
         mine = self._arr(dist, np.float32, p.dist_size * p.Q).reshape([p.Q] + arr[::-1])
         peer = self._arr(peer_dist, np.float32, int(np.prod(parr)) * p.Q).reshape([p.Q] + parr[::-1])
-        for slot, src, dst in halo_ref.face_windows(grid, lat, int(face), bool(with_swap), plat):
+        links = getattr(self, 'face_links', {}).get(self._key(plan), 0x3f)
+        for slot, src, dst in halo_ref.face_windows(grid, lat, int(face), bool(with_swap), plat, links):
             peer[(slot,) + tuple(dst[::-1])] = mine[(slot,) + tuple(src[::-1])]
         self.launches += 1
 

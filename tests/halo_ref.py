@@ -45,12 +45,14 @@ def insert_planes(dist, slots, layer, planes):
         dist[s, layer] = planes[k]
 
 
-def face_windows(grid, lat, face, with_swap, peer_lat):
+def face_windows(grid, lat, face, with_swap, peer_lat, links=0x3f):
     """Dimension-ordered exchange through ANY face (subdomains split along x / y too): for every population that
     crosses `face`, (slot, source index, destination index) as tuples over the axes (x, y[, z]) -- ints along the
     face axis, slices along the others.  Host statement of the window rules of csrc/slf_halo.cuh:
       after streaming steps: earlier axes 1 .. n-2, later axes 1+e .. n-2+e;
-      after in-place steps : earlier axes 1-e .. n-2-e, later axes 1 .. n-2."""
+      after in-place steps : earlier axes 1-e .. n-2-e, later axes 1 .. n-2;
+    `links` (bit 2 * axis + side: that face has a neighbour): along an earlier axis the end position on the side the
+    population came from is dropped when nobody delivered anything there (domain boundary)."""
     D = len(lat)
     axis, hi = face // 2, face & 1
     sgn = 1 if hi else -1
@@ -68,10 +70,20 @@ def face_windows(grid, lat, face, with_swap, peer_lat):
             if ax == axis:
                 src[ax], dst[ax] = src_layer, dst_layer
                 continue
+            cnt = lat[ax] - 2
             if ax < axis:
                 lo = 1 - e[ax] if with_swap else 1
+                came_through = 2 * ax + (0 if e[ax] > 0 else 1)
+                if e[ax] != 0 and not (links >> came_through) & 1:
+                    # positions lo .. lo+cnt-1 minus the one next to / in the ghost column of that side
+                    first, last = lo, lo + cnt - 1
+                    if e[ax] > 0:
+                        first += 1
+                    else:
+                        last -= 1
+                    lo, cnt = first, last - first + 1
             else:
                 lo = 1 if with_swap else 1 + e[ax]
-            src[ax] = dst[ax] = slice(lo, lo + lat[ax] - 2)
+            src[ax] = dst[ax] = slice(lo, lo + max(cnt, 0))
         out.append((slot, tuple(src), tuple(dst)))
     return out

@@ -68,3 +68,35 @@ def test_product_does_not_import_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not pat.search(text), '%s references the oracle' % f
+
+
+def test_face_windows_of_the_library_equal_the_host_reference(library):
+    """slf_halo_face_window (the pure host function slf_halo_push_face takes its windows from) against
+    tests/halo_ref.face_windows, which the CPU stand-in device uses: every lattice, face, step kind and set of
+    linked faces.  No device needed."""
+    import ctypes
+    import itertools
+    import halo_ref
+    from sailfish_b200 import lattice
+    fn = library.slf_halo_face_window
+    fn.restype = ctypes.c_int
+    I3, I2 = ctypes.c_int * 3, ctypes.c_int * 2
+    for lid, name in enumerate(('D2Q9', 'D3Q19', 'D3Q27')):
+        grid = lattice.get(name)
+        D = grid.dim
+        lat = [7, 6, 5][:D]
+        for face, swap, links in itertools.product(range(2 * D), (0, 1), range(0, 64, 1 if D == 2 else 3)):
+            want = dict((slot, (src, dst)) for slot, src, dst in
+                        halo_ref.face_windows(grid, lat, face, bool(swap), lat, links))
+            got = {}
+            for i in range(grid.Q):
+                lo, cnt = I2(0, 0), I2(0, 0)
+                if fn(lid, I3(*(lat + [1] * (3 - D))), face, swap, links, i, lo, cnt):
+                    got[int(grid.opposite[i]) if swap else i] = (list(lo), list(cnt))
+            assert sorted(got) == sorted(want), (name, face, swap, links)
+            axis = face // 2
+            others = [a for a in range(D) if a != axis]
+            for slot, (src, dst) in want.items():
+                lo, cnt = got[slot]
+                for b, ax in enumerate(others):
+                    assert src[ax] == dst[ax] == slice(lo[b], lo[b] + cnt[b]), (name, face, swap, links, slot, ax, src, lo, cnt)

@@ -157,3 +157,62 @@ def test_locally_periodic_axes_inside_a_z_split(fake, per, walls, grid, ap):
     _, many = block_util.run_blocks(sim, EqualSubdomainsGeometry3D, args + ['--subdomains=3'], 8)
     np.testing.assert_array_equal(block_util.merge(one, (10, 9, 12)), block_util.merge(many, (10, 9, 12)))
     assert 'slf_halo_push' in fake.calls
+
+
+def _open_duct3d(wall_name):
+    from sailfish_b200 import node_type as nt
+    from sailfish_b200.lb_single import LBFluidSim
+    from sailfish_b200.subdomain import Subdomain3D
+    wall = getattr(nt, wall_name)
+
+    class Sub(Subdomain3D):
+        """Walls one node thick on the y and z faces of the domain, equilibrium-velocity inlet, do-nothing outlet."""
+        def boundary_conditions(self, hx, hy, hz):
+            w = (hy == 0) | (hy == self.gy - 1) | (hz == 0) | (hz == self.gz - 1)
+            self.set_node(w, wall)
+            free = np.logical_not(w)
+            self.set_node((hx == 0) & free, nt.NTEquilibriumVelocity((0.03, 0.0, 0.0)))
+            self.set_node((hx == self.gx - 1) & free, nt.NTDoNothing)
+
+        def initial_conditions(self, sim, hx, hy, hz):
+            sim.rho[:] = 1.0
+            sim.vx[:] = 0.03
+
+    class Sim(LBFluidSim):
+        subdomain = Sub
+
+        @classmethod
+        def update_defaults(cls, d):
+            d.update(lat_nx=12, lat_ny=9, lat_nz=10, grid='D3Q19')
+    return Sim
+
+
+@pytest.mark.parametrize('ap', ['AA', 'AB'])
+@pytest.mark.parametrize('wall', ['NTFullBBWall', 'NTHalfBBWall', 'NTWallTMS'])
+@pytest.mark.parametrize('geo,one,split', [('equal', ['--subdomains=1'], ['--subdomains=3']),
+                                           ('blocks', ['--blocks=1,1,1'], ['--blocks=2,2,2'])])
+def test_open_duct_with_boundary_sensitive_nodes(fake, geo, one, split, wall, ap):
+    """Do-nothing outlet and link-bounce walls ON THE DOMAIN BOUNDARY, cut by the subdomain faces.  These nodes keep
+    what they find in the slots no node streams into, so a face push must not carry the never-written ghost entries
+    next to the domain boundary across (slf_plan_set_face_links; the reference's partial connection maps): such
+    subdomains exchange through the windowed face push even when they are only split along z."""
+    sim = _open_duct3d(wall)
+    g = EqualSubdomainsGeometry3D if geo == 'equal' else BlockSubdomainsGeometry3D
+    args = ['--access_pattern=' + ap, '--visc=0.06']
+    _, a = block_util.run_blocks(sim, g, args + one, 10)
+    ctrl, b = block_util.run_blocks(sim, g, args + split, 10)
+    np.testing.assert_array_equal(block_util.merge(a, (12, 9, 10)), block_util.merge(b, (12, 9, 10)))
+    assert all(r._general for r in ctrl.runners) and 'slf_plan_set_face_links' in fake.calls
+
+
+@pytest.mark.parametrize('ap', ['AA', 'AB'])
+@pytest.mark.parametrize('geo,one,split', [('equal', ['--subdomains=1'], ['--subdomains=3']),
+                                           ('equal', ['--subdomains=1'], ['--subdomains=2', '--conn_axis=x']),
+                                           ('blocks', ['--blocks=1,1'], ['--blocks=3,2'])])
+def test_channel_with_do_nothing_outlet_on_splits(fake, geo, one, split, ap):
+    cls, zargs = _zoo('channel2d')
+    g = EqualSubdomainsGeometry2D if geo == 'equal' else BlockSubdomainsGeometry2D
+    args = zargs + ['--access_pattern=' + ap, '--visc=0.06']
+    _, a = block_util.run_blocks(cls, g, args + one, 10)
+    _, b = block_util.run_blocks(cls, g, args + split, 10)
+    np.testing.assert_array_equal(block_util.merge(a, (20, 12)), block_util.merge(b, (20, 12)))

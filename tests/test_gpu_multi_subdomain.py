@@ -101,3 +101,19 @@ def test_gpu_d3q27_aa_locally_periodic_inside_z_split(per, walls):
     many = gpu_run(sim, EqualSubdomainsGeometry3D, args + ['--subdomains=3'], 8)
     for a, b in zip(one, many):
         np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.xfail(strict=False, reason='windowed exchange for subdomains with do-nothing / link-bounce nodes '
+                   '(slf_plan_set_face_links): host-side change made after the GPU minutes of the round were spent; the '
+                   'window arithmetic of the library is checked on the CPU (tests/test_abi.py), the scheduling on the '
+                   'CPU stand-in (tests/test_block_decomposition_fake.py); not yet run on hardware')
+@pytest.mark.parametrize('ap', ['AB', 'AA'])
+@pytest.mark.parametrize('wall', ['NTHalfBBWall', 'NTWallTMS'])
+def test_gpu_open_duct_with_boundary_sensitive_nodes_split_in_z(wall, ap):
+    from test_block_decomposition_fake import _open_duct3d
+    sim = _open_duct3d(wall)
+    args = ['--access_pattern=' + ap, '--visc=0.06']
+    one = gpu_run(sim, EqualSubdomainsGeometry3D, args + ['--subdomains=1'], 10)
+    many = gpu_run(sim, EqualSubdomainsGeometry3D, args + ['--subdomains=3'], 10)
+    for a, b in zip(one, many):
+        np.testing.assert_array_equal(a, b)
